@@ -1,0 +1,156 @@
+// aix_internal.cuh -- host-side object definitions behind the opaque C-ABI handles.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/aindex_cuda.h"
+#include "device_common.cuh"
+
+struct aix_mphf {
+    uint64_t n = 0, hash_domain = 0, seed = 0, bv_size = 0, n_words = 0, n_blocks = 0;
+    std::vector<uint64_t> words;        // .pf order (host copy, for save / inspection)
+    std::vector<uint64_t> block_ranks;  // .pf order
+    ulonglong2 *recs_dev = nullptr;     // B200 layout, see device_common.cuh
+    aix::MphfDev dev() const {
+        aix::MphfDev d;
+        d.n = n; d.hash_domain = hash_domain; d.seed = seed;
+        d.magic = hash_domain ? (uint64_t)((((unsigned __int128)1) << 64) / hash_domain) : 0;
+        d.recs = recs_dev;
+        return d;
+    }
+};
+
+struct aix_index23 {
+    uint64_t n = 0;
+    int canonical_only = 0;
+    const aix_mphf *mphf = nullptr;
+    uint4 *recs_dev = nullptr;  // {checker lo, checker hi, tf, 0}
+    aix::Index23Dev dev() const {
+        aix::Index23Dev d;
+        d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev;
+        return d;
+    }
+};
+
+struct aix_index13 {
+    const aix_mphf *mphf = nullptr;
+    uint64_t *tf_mphf_dev = nullptr;    // u64[4^13], .tf.bin order (id = mphf(kmer))
+    uint64_t *tf_direct_dev = nullptr;  // u64[4^13], direct-address order (v = 2-bit value)
+};
+
+struct aix_positions {
+    uint64_t n_indices = 0, n_positions = 0;
+    uint64_t *indices_dev = nullptr;
+    uint64_t *positions_dev = nullptr;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct aix_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // *_dev entry points + pipelines' compute
+    cudaStream_t xfer[2] = {nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    DevBuf scratch[8];                  // grow-only device scratch, indexed by role
+    // count13 streaming state
+    uint32_t *c13_hist32 = nullptr;     // u32[4^13]
+    uint64_t *c13_hist64 = nullptr;     // u64[4^13]
+    uint64_t *c13_stats_dev = nullptr;  // u64[4]: sequences, windows, valid, (unused)
+    uint64_t c13_pending_windows = 0;   // upper bound of increments not yet flushed
+    bool c13_active = false;
+    aix_count_stats c13_range_invalid = {0, 0, 0, 0};
+    // canonical23 result kept between the two passes
+    uint64_t *c23_kmers_dev = nullptr;
+    uint32_t *c23_counts_dev = nullptr;
+    uint64_t c23_n = 0;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    // grow-only scratch allocation
+    int reserve(int slot, size_t bytes, void **out) {
+        DevBuf &b = scratch[slot];
+        if (b.cap < bytes) {
+            if (b.p) cudaFree(b.p);
+            b.p = nullptr; b.cap = 0;
+            size_t want = bytes + (bytes >> 3) + 256;
+            cudaError_t e = cudaMalloc(&b.p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                e = cudaMalloc(&b.p, bytes);
+                want = bytes;
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(AIX_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            }
+            b.cap = want;
+        }
+        *out = b.p;
+        return AIX_OK;
+    }
+};
+
+#define AIX_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return (ctx)->fail(AIX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,          \
+                               cudaGetErrorString(e__));                                         \
+    } while (0)
+
+#define AIX_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != AIX_OK) return rc__; \
+    } while (0)
+
+#define AIX_LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                    \
+        if (e__ != cudaSuccess)                                                                  \
+            return (ctx)->fail(AIX_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,      \
+                               cudaGetErrorString(e__));                                         \
+    } while (0)
+
+static inline unsigned aix_grid(uint64_t work_items, unsigned block) {
+    uint64_t g = (work_items + block - 1) / block;
+    return (unsigned)(g ? g : 1);
+}
+
+// scratch slot roles
+enum { SCR_IN0 = 0, SCR_IN1 = 1, SCR_OUT0 = 2, SCR_OUT1 = 3, SCR_LEN0 = 4, SCR_LEN1 = 5, SCR_TMP0 = 6, SCR_TMP1 = 7 };
+
+// host pointer kind
+static inline bool aix_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// internal cross-file entry points
+namespace aix {
+int mphf_build_layout(aix_ctx *ctx, aix_mphf *m);  // words/block_ranks (host) -> recs_dev
+}

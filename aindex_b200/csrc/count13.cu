@@ -1,0 +1,631 @@
+// count13.cu -- 13-mer counting: rolling 2-bit windows over raw read bytes and a
+// direct-address 4^13 histogram in HBM.
+//
+// Reference: Kmer13Counter (src/count_kmers13.cpp): process_sequence :131-161,
+// normalize_sequence :113-126, is_valid_kmer :101-108, readers :211-272,
+// save_counts :358-388.  The reference evaluates the MPHF once per k-mer occurrence
+// (:148) and bumps counts[mphf(kmer)]; for a fixed .pf that is a fixed permutation of the
+// 2-bit value v of the window, so the GPU counts in direct-address space hist[v] (no hash
+// in the inner loop) and applies perm13 once at the end (aix_count13_finish).
+//
+// K1/K2 kernel shape: one thread per 16 input bytes (one aligned 16-byte load + the
+// previous 16 bytes from the neighbouring lane by shuffle), 29 two-bit codes and two
+// 29-bit masks (valid letter / newline) per thread, window predicates by shift-and
+// doubling, then up to 16 RED.ADD.U32 into the 256 MiB histogram.
+#include "aix_internal.cuh"
+
+namespace aix {
+
+constexpr int kCntBlock = 256;
+constexpr uint32_t kMask26 = (1u << 26) - 1;
+
+// classify one byte: bit0-1 code, bit2 valid (ACGT, either case: std::toupper at
+// count_kmers13.cpp:118), bit3 newline
+__device__ __forceinline__ uint32_t classify(uint32_t c) {
+    uint32_t u = c & 0xDFu;
+    uint32_t valid = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
+    uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+    return code | (valid << 2) | ((c == '\n') << 3);
+}
+
+struct Win16 {
+    uint64_t codes;   // 29 codes, position i at bits [2*(28-i)+1 : 2*(28-i)]; 0..12 lookback, 13..28 own
+    uint32_t wvalid;  // bit s (1..16): window starting at position s is 13 valid letters
+    uint32_t wline;   // bit s: window starting at s contains no newline
+    uint32_t nl;      // bit i: position i is a newline
+};
+
+__device__ __forceinline__ uint32_t run13(uint32_t v) {  // bit i = v[i..i+12] all set
+    uint32_t a1 = v & (v >> 1);
+    uint32_t a2 = a1 & (a1 >> 2);
+    uint32_t a3 = a2 & (a2 >> 4);
+    return a3 & (a2 >> 8) & (v >> 12);
+}
+
+// prev = the 16 bytes before own (only the last 13 are used), both as little-endian uint4
+__device__ __forceinline__ Win16 make_windows(uint4 prev, uint4 own) {
+    uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, own.x, own.y, own.z, own.w};
+    uint64_t codes = 0;
+    uint32_t valid = 0, nl = 0;
+#pragma unroll
+    for (int b = 3; b < 32; ++b) {  // bytes 3..15 of prev = positions 0..12; own = 13..28
+        uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+        uint32_t k = classify(c);
+        int pos = b - 3;
+        codes |= (uint64_t)(k & 3u) << (2 * (28 - pos));
+        valid |= ((k >> 2) & 1u) << pos;
+        nl |= ((k >> 3) & 1u) << pos;
+    }
+    Win16 r;
+    r.codes = codes;
+    r.nl = nl;
+    r.wvalid = run13(valid) & 0x1FFFEu;
+    r.wline = run13(~nl & 0x1FFFFFFFu) & 0x1FFFEu;
+    return r;
+}
+
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// base: 16-byte aligned; owned bytes are [own_begin, own_end) (own_begin multiple of 16).
+// Bytes before own_begin are lookback if own_begin > 0, otherwise the shard start (virtual
+// newline); bytes at or past own_end read as newline.
+template <bool kAggregate>
+__global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
+                                                          uint64_t own_end, uint32_t *__restrict__ hist,
+                                                          unsigned long long *__restrict__ stats) {
+    const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
+    const uint64_t pos = own_begin + t * 16;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint4 nl4 = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    uint4 own = nl4;
+    const bool active = pos < own_end;
+    if (active) {
+        own = __ldcs(reinterpret_cast<const uint4 *>(base + pos));
+        if (pos + 16 > own_end) {  // tail: bytes past the end become newlines
+            uint32_t w[4] = {own.x, own.y, own.z, own.w};
+            uint32_t keep = (uint32_t)(own_end - pos);
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if ((uint32_t)b >= keep) w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (0x0Au << (8 * (b & 3)));
+            own = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    // previous 16 bytes: neighbour lane, or a direct load at the warp boundary
+    uint4 prev;
+    prev.x = __shfl_up_sync(0xFFFFFFFFu, own.x, 1);
+    prev.y = __shfl_up_sync(0xFFFFFFFFu, own.y, 1);
+    prev.z = __shfl_up_sync(0xFFFFFFFFu, own.z, 1);
+    prev.w = __shfl_up_sync(0xFFFFFFFFu, own.w, 1);
+    if (lane == 0) {
+        if (pos >= 16 && pos - 16 < own_end) prev = __ldg(reinterpret_cast<const uint4 *>(base + pos - 16));
+        else prev = nl4;
+    }
+    uint64_t n_win = 0, n_valid = 0, n_seq = 0;
+    if (active) {
+        Win16 w = make_windows(prev, own);
+        n_win = __popc(w.wline);
+        n_valid = __popc(w.wvalid);
+        n_seq = __popc((w.nl << 1) & w.wline);  // first window of a line with >= 13 characters
+        uint32_t pend_k = 0, pend_c = 0;
+#pragma unroll
+        for (int s = 1; s <= 16; ++s) {
+            uint32_t kmer = (uint32_t)(w.codes >> (2 * (16 - s))) & kMask26;
+            bool ok = (w.wvalid >> s) & 1u;
+            if (kAggregate) {
+                // thread-local run-length merge (homopolymer / tandem runs), flushed below
+                if (ok && pend_c && kmer == pend_k) { ++pend_c; continue; }
+                if (pend_c) atomicAdd(hist + pend_k, pend_c);
+                pend_c = ok ? 1u : 0u;
+                pend_k = kmer;
+            } else {
+                if (ok) atomicAdd(hist + kmer, 1u);
+            }
+        }
+        if (kAggregate && pend_c) atomicAdd(hist + pend_k, pend_c);
+    }
+    n_win = warp_sum(n_win);
+    n_valid = warp_sum(n_valid);
+    n_seq = warp_sum(n_seq);
+    if (lane == 0 && n_win) {
+        atomicAdd(stats + 0, (unsigned long long)n_seq);
+        atomicAdd(stats + 1, (unsigned long long)n_win);
+        atomicAdd(stats + 2, (unsigned long long)n_valid);
+    }
+}
+
+// warp-aggregated variant: duplicates inside a warp are merged with match_any before they
+// reach L2 (pays off on low-complexity / highly repetitive input)
+__global__ void __launch_bounds__(kCntBlock) count13_match_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
+                                                                uint64_t own_end, uint32_t *__restrict__ hist,
+                                                                unsigned long long *__restrict__ stats) {
+    const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
+    const uint64_t pos = own_begin + t * 16;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint4 nl4 = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    uint4 own = nl4;
+    const bool active = pos < own_end;
+    if (active) {
+        own = __ldcs(reinterpret_cast<const uint4 *>(base + pos));
+        if (pos + 16 > own_end) {
+            uint32_t w[4] = {own.x, own.y, own.z, own.w};
+            uint32_t keep = (uint32_t)(own_end - pos);
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if ((uint32_t)b >= keep) w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (0x0Au << (8 * (b & 3)));
+            own = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    uint4 prev;
+    prev.x = __shfl_up_sync(0xFFFFFFFFu, own.x, 1);
+    prev.y = __shfl_up_sync(0xFFFFFFFFu, own.y, 1);
+    prev.z = __shfl_up_sync(0xFFFFFFFFu, own.z, 1);
+    prev.w = __shfl_up_sync(0xFFFFFFFFu, own.w, 1);
+    if (lane == 0) {
+        if (pos >= 16 && pos - 16 < own_end) prev = __ldg(reinterpret_cast<const uint4 *>(base + pos - 16));
+        else prev = nl4;
+    }
+    Win16 w = make_windows(prev, own);  // inactive threads: all newlines -> no windows
+    uint64_t n_win = __popc(w.wline), n_valid = __popc(w.wvalid), n_seq = __popc((w.nl << 1) & w.wline);
+#pragma unroll
+    for (int s = 1; s <= 16; ++s) {
+        uint32_t kmer = (uint32_t)(w.codes >> (2 * (16 - s))) & kMask26;
+        bool ok = (w.wvalid >> s) & 1u;
+        uint32_t key = ok ? kmer : 0xFFFFFFFFu;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + kmer, (uint32_t)__popc(peers));
+    }
+    n_win = warp_sum(n_win);
+    n_valid = warp_sum(n_valid);
+    n_seq = warp_sum(n_seq);
+    if (lane == 0 && n_win) {
+        atomicAdd(stats + 0, (unsigned long long)n_seq);
+        atomicAdd(stats + 1, (unsigned long long)n_win);
+        atomicAdd(stats + 2, (unsigned long long)n_valid);
+    }
+}
+
+// hist64[v] += hist32[v]; hist32[v] = 0
+__global__ void flush_hist_kernel(uint32_t *__restrict__ h32, uint64_t *__restrict__ h64) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (uint32_t)AIX_TOTAL_13MERS) return;
+    uint32_t c = h32[v];
+    if (c) {
+        h64[v] += c;
+        h32[v] = 0;
+    }
+}
+
+// tf_out[mphf(v)] += hist64[v] for v in [v_begin, v_end); ids >= 4^13 are the reference's
+// "hash index out of range" branch (count_kmers13.cpp:153-156): counted invalid, not stored
+__global__ void permute13_kernel(MphfDev m, const uint64_t *__restrict__ hist64, uint32_t v_begin, uint32_t v_end,
+                                 unsigned long long *__restrict__ tf_out, unsigned long long *__restrict__ out_of_range) {
+    uint32_t v = v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= v_end) return;
+    uint64_t c = hist64[v];
+    if (!c) return;
+    uint64_t id = mphf_lookup13(m, revcomp13(v));
+    if (id < AIX_TOTAL_13MERS) atomicAdd(tf_out + id, (unsigned long long)c);
+    else atomicAdd(out_of_range, (unsigned long long)c);
+}
+
+// ---- FASTQ: blank every byte that is not on a sequence line (line_no % 4 == 1,
+// count_kmers13.cpp:240-257) so the buffer can be counted as plain text ----------------
+constexpr int kTileBytes = kCntBlock * 16;
+
+__device__ __forceinline__ uint32_t count_nl16(uint4 v) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w}, n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t x = w[i] ^ 0x0A0A0A0Au;  // zero byte <=> newline
+        uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        n += __popc(z);
+    }
+    return n;
+}
+
+__device__ __forceinline__ uint4 load_own16(const uint8_t *base, uint64_t pos, uint64_t own_end) {
+    uint4 own = make_uint4(0, 0, 0, 0);
+    if (pos < own_end) {
+        own = *reinterpret_cast<const uint4 *>(base + pos);
+        if (pos + 16 > own_end) {
+            uint32_t w[4] = {own.x, own.y, own.z, own.w};
+            uint32_t keep = (uint32_t)(own_end - pos);
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if ((uint32_t)b >= keep) w[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
+            own = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    return own;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem /*>=33*/, uint32_t &total) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) smem[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= (unsigned)o) s += y;
+        }
+        smem[lane] = s;  // inclusive per-warp totals
+    }
+    __syncthreads();
+    total = smem[(blockDim.x >> 5) - 1];
+    uint32_t warp_off = wid ? smem[wid - 1] : 0;
+    __syncthreads();
+    return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(kCntBlock) nl_count_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
+                                                           uint64_t own_end, uint32_t *__restrict__ tile_cnt) {
+    __shared__ uint32_t sm[33];
+    const uint64_t pos = own_begin + ((uint64_t)blockIdx.x * kCntBlock + threadIdx.x) * 16;
+    uint32_t n = count_nl16(load_own16(base, pos, own_end));
+    uint32_t total;
+    block_exclusive_scan(n, sm, total);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+// single block: tile_base[i] = line_base + exclusive scan; line_base += total
+__global__ void nl_scan_kernel(uint32_t *__restrict__ tile_cnt, uint64_t *__restrict__ tile_base, uint32_t n_tiles,
+                               unsigned long long *__restrict__ line_base) {
+    __shared__ uint32_t sm[33];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = *line_base;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n_tiles; i0 += blockDim.x) {
+        uint32_t i = i0 + threadIdx.x;
+        uint32_t v = i < n_tiles ? tile_cnt[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, sm, total);
+        if (i < n_tiles) tile_base[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *line_base = carry;
+}
+
+// in place: bytes whose line number % 4 != 1 become '\n'.  The (up to 16) lookback bytes
+// in front of own_begin are handled by thread 0 of block 0, walking backwards.
+__global__ void __launch_bounds__(kCntBlock) fastq_mask_kernel(uint8_t *__restrict__ base, uint64_t own_begin, uint64_t own_end,
+                                                             const uint64_t *__restrict__ tile_base) {
+    __shared__ uint32_t sm[33];
+    const uint64_t pos = own_begin + ((uint64_t)blockIdx.x * kCntBlock + threadIdx.x) * 16;
+    uint4 own = load_own16(base, pos, own_end);
+    uint32_t n = count_nl16(own), total;
+    uint32_t ex = block_exclusive_scan(n, sm, total);
+    uint64_t line = tile_base[blockIdx.x] + ex;
+    if (pos < own_end) {
+        uint32_t w[4] = {own.x, own.y, own.z, own.w};
+        uint32_t lim = (uint32_t)(own_end - pos < 16 ? own_end - pos : 16);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+            bool is_nl = (c == '\n') && (uint32_t)b < lim;
+            if ((line & 3u) != 1u) w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (0x0Au << (8 * (b & 3)));
+            if (is_nl) ++line;
+        }
+        if (lim == 16) *reinterpret_cast<uint4 *>(base + pos) = make_uint4(w[0], w[1], w[2], w[3]);
+        else
+            for (uint32_t b = 0; b < lim; ++b) base[pos + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && own_begin > 0) {
+        uint64_t ln = tile_base[0];  // line number of the byte at own_begin
+        for (uint64_t p = own_begin; p-- > 0;) {
+            if (base[p] == '\n') --ln;  // byte p is the newline that ends line ln-1... (see below)
+            // line number of byte p = newlines strictly before p = ln after the decrement
+            if (base[p] != '\n' && (ln & 3u) != 1u) base[p] = '\n';
+        }
+    }
+}
+
+}  // namespace aix
+
+using namespace aix;
+
+// streaming chunk size for host/device staged input (multiple of kTileBytes)
+static const uint64_t kChunkBytes = 256ull << 20;
+
+static int c13_alloc(aix_ctx *ctx) {
+    if (!ctx->c13_hist32) {
+        cudaError_t e = cudaMalloc(&ctx->c13_hist32, AIX_TOTAL_13MERS * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->c13_hist64, AIX_TOTAL_13MERS * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->c13_stats_dev, 8 * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(AIX_ERR_NOMEM, "count13 buffers: %s", cudaGetErrorString(e));
+        }
+    }
+    return AIX_OK;
+}
+
+static int c13_flush_on(aix_ctx *ctx, cudaStream_t st) {
+    flush_hist_kernel<<<aix_grid(AIX_TOTAL_13MERS, 256), 256, 0, st>>>(ctx->c13_hist32, ctx->c13_hist64);
+    AIX_LAUNCH_CHECK(ctx);
+    ctx->c13_pending_windows = 0;
+    return AIX_OK;
+}
+
+// 0 one RED per window (default), 1 + thread-local run-length merge, 2 warp match_any merge
+static int count_variant() {
+    const char *e = getenv("AIX_COUNT13_VARIANT");
+    return e ? atoi(e) : 0;
+}
+
+static int launch_count(aix_ctx *ctx, cudaStream_t st, const uint8_t *base, uint64_t own_begin, uint64_t own_end) {
+    if (own_end <= own_begin) return AIX_OK;
+    uint64_t threads = (own_end - own_begin + 15) / 16;
+    unsigned grid = aix_grid(threads, kCntBlock);
+    unsigned long long *stats = (unsigned long long *)ctx->c13_stats_dev;
+    switch (count_variant()) {
+        case 1: count13_kernel<true><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
+        case 2: count13_match_kernel<<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
+        default: count13_kernel<false><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
+    }
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+// host-side FASTA normalisation to plain text (one record per line).  Parsing only; the
+// counting itself stays on the device.  TODO(round 2): device stream compaction.
+static void fasta_to_plain(const uint8_t *bytes, uint64_t len, std::vector<uint8_t> &out) {
+    out.clear();
+    out.reserve(len + 1);
+    uint64_t pos = 0;
+    bool open = false;
+    while (pos < len) {
+        const uint8_t *nl = (const uint8_t *)memchr(bytes + pos, '\n', len - pos);
+        uint64_t e = nl ? (uint64_t)(nl - bytes) : len;
+        if (e > pos) {
+            if (bytes[pos] == '>') {
+                if (open) out.push_back('\n');
+                open = false;
+            } else {
+                out.insert(out.end(), bytes + pos, bytes + e);
+                open = true;
+            }
+        }
+        pos = e + 1;
+    }
+    if (open) out.push_back('\n');
+}
+
+static int detect_format_host(const uint8_t *b, uint64_t len) {  // count_kmers13.cpp:194-206
+    if (len == 0 || b[0] == '\n') return AIX_FMT_PLAIN;
+    if (b[0] == '>') return AIX_FMT_FASTA;
+    if (b[0] == '@') return AIX_FMT_FASTQ;
+    return AIX_FMT_PLAIN;
+}
+
+// shared by aix_count13_add (host source) and aix_count13_add_dev (device source)
+static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt, bool src_is_device) {
+    if (!ctx) return AIX_ERR_ARG;
+    if (!ctx->c13_active) return ctx->fail(AIX_ERR_STATE, "aix_count13_begin not called");
+    if (len == 0) return AIX_OK;
+    if (!src) return ctx->fail(AIX_ERR_ARG, "null input");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (fmt == AIX_FMT_DETECT) {
+        uint8_t first = 0;
+        if (src_is_device) AIX_CUDA(ctx, cudaMemcpy(&first, src, 1, cudaMemcpyDeviceToHost));
+        else first = src[0];
+        fmt = detect_format_host(&first, 1);
+    }
+    std::vector<uint8_t> plain;
+    std::vector<uint8_t> host_copy;
+    if (fmt == AIX_FMT_FASTA) {
+        if (src_is_device) {
+            host_copy.resize(len);
+            AIX_CUDA(ctx, cudaMemcpy(host_copy.data(), src, len, cudaMemcpyDeviceToHost));
+            src = host_copy.data();
+            src_is_device = false;
+        }
+        fasta_to_plain(src, len, plain);
+        src = plain.data();
+        len = plain.size();
+        fmt = AIX_FMT_PLAIN;
+        if (len == 0) return AIX_OK;
+    }
+    if (fmt != AIX_FMT_PLAIN && fmt != AIX_FMT_FASTQ) return ctx->fail(AIX_ERR_ARG, "unknown format %d", fmt);
+
+    // every input byte starts at most one window; flush the u32 histogram before it can wrap
+    auto account = [&](uint64_t nbytes, cudaStream_t st) -> int {
+        if (ctx->c13_pending_windows + nbytes >= 0xFFFF0000ull) {
+            // the flush is not atomic with respect to running count kernels: quiesce first
+            AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[0]));
+            AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[1]));
+            AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            AIX_TRY(c13_flush_on(ctx, st));
+            AIX_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        ctx->c13_pending_windows += nbytes;
+        return AIX_OK;
+    };
+
+    // resident plain text: count in place, no copy
+    if (src_is_device && fmt == AIX_FMT_PLAIN && ((uintptr_t)src & 15) == 0) {
+        uint64_t done = 0;
+        const uint64_t step = 1ull << 31;  // keep each launch below the flush threshold
+        while (done < len) {
+            uint64_t n = len - done < step ? len - done : step;
+            AIX_TRY(account(n, ctx->stream));
+            AIX_TRY(launch_count(ctx, ctx->stream, src, done, done + n));
+            done += n;
+        }
+        return AIX_OK;
+    }
+
+    // staged path: chunk c holds [16 lookback bytes][chunk bytes] (the first chunk has no lookback)
+    uint64_t chunk = kChunkBytes;
+    if (const char *e = getenv("AIX_COUNT13_CHUNK")) {  // test hook: force the multi-chunk path on small inputs
+        uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 64) chunk = v & ~15ull;
+    }
+    if (chunk > len) chunk = (len + 15) & ~15ull;
+    const uint32_t max_tiles = (uint32_t)((chunk + kTileBytes - 1) / kTileBytes) + 1;
+    void *buf[2] = {nullptr, nullptr}, *tcnt[2] = {nullptr, nullptr}, *tbase[2] = {nullptr, nullptr};
+    for (int s = 0; s < 2; ++s) {
+        AIX_TRY(ctx->reserve(SCR_IN0 + s, chunk + 64, &buf[s]));
+        if (fmt == AIX_FMT_FASTQ) {
+            AIX_TRY(ctx->reserve(SCR_LEN0 + s, (size_t)max_tiles * 4, &tcnt[s]));
+            AIX_TRY(ctx->reserve(SCR_OUT0 + s, (size_t)max_tiles * 8, &tbase[s]));
+        }
+        if (len <= chunk) break;
+    }
+    unsigned long long *line_base = (unsigned long long *)(ctx->c13_stats_dev + 4);
+    if (fmt == AIX_FMT_FASTQ) AIX_CUDA(ctx, cudaMemsetAsync(line_base, 0, 8, ctx->stream));
+    AIX_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer[0], ctx->ev[0], 0));
+    AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer[1], ctx->ev[0], 0));
+    uint64_t done = 0;
+    int c = 0;
+    while (done < len) {
+        uint64_t n = len - done < chunk ? len - done : chunk;
+        int s = c & 1;
+        cudaStream_t st = ctx->xfer[s];
+        uint64_t lead = done ? 16 : 0;
+        uint8_t *b = (uint8_t *)buf[s];
+        if (fmt == AIX_FMT_FASTQ && c > 0) {
+            // the line counter is carried on the device: chunks must be processed in order
+            AIX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1 + ((c - 1) & 1)], 0));
+        }
+        AIX_CUDA(ctx, cudaMemcpyAsync(b, src + done - lead, n + lead, cudaMemcpyDefault, st));
+        AIX_TRY(account(n, st));
+        if (fmt == AIX_FMT_FASTQ) {
+            uint32_t tiles = (uint32_t)((n + kTileBytes - 1) / kTileBytes);
+            nl_count_kernel<<<tiles, kCntBlock, 0, st>>>(b, lead, lead + n, (uint32_t *)tcnt[s]);
+            AIX_LAUNCH_CHECK(ctx);
+            nl_scan_kernel<<<1, 1024, 0, st>>>((uint32_t *)tcnt[s], (uint64_t *)tbase[s], tiles, line_base);
+            AIX_LAUNCH_CHECK(ctx);
+            AIX_CUDA(ctx, cudaEventRecord(ctx->ev[1 + (c & 1)], st));
+            fastq_mask_kernel<<<tiles, kCntBlock, 0, st>>>(b, lead, lead + n, (const uint64_t *)tbase[s]);
+            AIX_LAUNCH_CHECK(ctx);
+        }
+        AIX_TRY(launch_count(ctx, st, b, lead, lead + n));
+        done += n;
+        ++c;
+    }
+    // later work on ctx->stream (flush / finish) must see the counts
+    AIX_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->xfer[0]));
+    AIX_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->xfer[1]));
+    AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+    AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[4], 0));
+    // host buffers (and the local FASTA copy) may be released by the caller on return
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[0]));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[1]));
+    return AIX_OK;
+}
+
+extern "C" {
+
+int aix_count13_begin(aix_ctx *ctx) {
+    if (!ctx) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_TRY(c13_alloc(ctx));
+    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist32, 0, AIX_TOTAL_13MERS * 4, ctx->stream));
+    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist64, 0, AIX_TOTAL_13MERS * 8, ctx->stream));
+    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_stats_dev, 0, 8 * 8, ctx->stream));
+    ctx->c13_pending_windows = 0;
+    ctx->c13_active = true;
+    return AIX_OK;
+}
+
+int aix_count13_add(aix_ctx *ctx, const uint8_t *bytes, uint64_t len, int fmt) {
+    return c13_add_impl(ctx, bytes, len, fmt, false);
+}
+
+int aix_count13_add_dev(aix_ctx *ctx, const uint8_t *bytes_dev, uint64_t len, int fmt) {
+    return c13_add_impl(ctx, bytes_dev, len, fmt, true);
+}
+
+int aix_count13_flush(aix_ctx *ctx) {
+    if (!ctx || !ctx->c13_active) return ctx ? ctx->fail(AIX_ERR_STATE, "count13 not active") : AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return c13_flush_on(ctx, ctx->stream);
+}
+
+uint64_t *aix_count13_hist_dev(aix_ctx *ctx) { return ctx ? ctx->c13_hist64 : nullptr; }
+
+int aix_count13_stats(aix_ctx *ctx, aix_count_stats *stats) {
+    if (!ctx || !stats || !ctx->c13_active) return AIX_ERR_ARG;
+    uint64_t h[4];
+    AIX_CUDA(ctx, cudaMemcpyAsync(h, ctx->c13_stats_dev, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    stats->sequences = h[0];
+    stats->windows = h[1];
+    stats->valid = h[2];
+    stats->invalid = h[1] - h[2];
+    return AIX_OK;
+}
+
+int aix_count13_finish_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t v_begin, uint64_t v_end, uint64_t *tf_out_dev) {
+    if (!ctx || !m || !tf_out_dev) return AIX_ERR_ARG;
+    if (!ctx->c13_active) return ctx->fail(AIX_ERR_STATE, "count13 not active");
+    if (v_begin > v_end || v_end > AIX_TOTAL_13MERS) return ctx->fail(AIX_ERR_ARG, "bad k-mer range");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (v_end == v_begin) return AIX_OK;
+    permute13_kernel<<<aix_grid(v_end - v_begin, 256), 256, 0, ctx->stream>>>(
+        m->dev(), ctx->c13_hist64, (uint32_t)v_begin, (uint32_t)v_end, (unsigned long long *)tf_out_dev,
+        (unsigned long long *)(ctx->c13_stats_dev + 3));
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+int aix_count13_finish(aix_ctx *ctx, const aix_mphf *m, uint64_t v_begin, uint64_t v_end, uint64_t *tf_out,
+                       aix_count_stats *stats) {
+    if (!ctx || !m || !tf_out) return AIX_ERR_ARG;
+    AIX_TRY(aix_count13_flush(ctx));
+    void *tf_dev;
+    AIX_TRY(ctx->reserve(SCR_TMP0, AIX_TOTAL_13MERS * 8, &tf_dev));
+    AIX_CUDA(ctx, cudaMemsetAsync(tf_dev, 0, AIX_TOTAL_13MERS * 8, ctx->stream));
+    AIX_TRY(aix_count13_finish_dev(ctx, m, v_begin, v_end, (uint64_t *)tf_dev));
+    const bool whole = (v_begin == 0 && v_end == AIX_TOTAL_13MERS);
+    if (whole) {
+        AIX_CUDA(ctx, cudaMemcpyAsync(tf_out, tf_dev, AIX_TOTAL_13MERS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        // a slice lands on arbitrary ids: accumulate into the caller's array on the host
+        std::vector<uint64_t> tmp(AIX_TOTAL_13MERS);
+        AIX_CUDA(ctx, cudaMemcpyAsync(tmp.data(), tf_dev, AIX_TOTAL_13MERS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < AIX_TOTAL_13MERS; ++i) tf_out[i] += tmp[i];
+    }
+    if (stats) {
+        AIX_TRY(aix_count13_stats(ctx, stats));
+        uint64_t oor = 0;
+        AIX_CUDA(ctx, cudaMemcpy(&oor, ctx->c13_stats_dev + 3, 8, cudaMemcpyDeviceToHost));
+        stats->valid -= oor;  // count_kmers13.cpp:153-156
+        stats->invalid += oor;
+    }
+    return AIX_OK;
+}
+
+int aix_count13_end(aix_ctx *ctx) {
+    if (!ctx) return AIX_ERR_ARG;
+    ctx->c13_active = false;
+    return AIX_OK;
+}
+
+int aix_count13(aix_ctx *ctx, const aix_mphf *m, const uint8_t *bytes, uint64_t len, int fmt, uint64_t *tf_out,
+                aix_count_stats *stats) {
+    if (!ctx || !m || !tf_out) return AIX_ERR_ARG;
+    AIX_TRY(aix_count13_begin(ctx));
+    int rc = aix_count13_add(ctx, bytes, len, fmt);
+    if (rc == AIX_OK) rc = aix_count13_finish(ctx, m, 0, AIX_TOTAL_13MERS, tf_out, stats);
+    aix_count13_end(ctx);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// coverage.cu -- K5: per-position term-frequency profile of sequences.
+//
+// Reference: AIndex.get_sequence_coverage (aindex/core/aindex.py:314-322): for every window
+// start i of a sequence, tf = get_tf_value(seq[i:i+k]) (python_wrapper.cpp:644-650 ->
+// get_tf_value_23mer :610-627 or get_tf_value_13mer :482-503); coverage[i] = tf if
+// tf >= cutoff else 0.  No newline / '~' / 'N' skipping: such windows are simply looked up.
+//
+// One thread per output position; a CTA owns 256 consecutive outputs, locates the sequences
+// they belong to by binary search over the output offsets (one coarse search per CTA, one
+// short search per thread) and reads its 23 bytes as six/seven aligned words from L1/L2
+// (neighbouring threads share all but one byte).
+#include "aix_internal.cuh"
+#include "query23.cuh"
+
+namespace aix {
+
+constexpr int kCovBlock = 256;
+
+// out_offs[s] = sum_{t<s} max(0, len_t - k + 1), single CTA, n_seq+1 entries
+__global__ void coverage_offsets_kernel(const int64_t *__restrict__ offs, uint64_t n_seq, int k,
+                                        unsigned long long *__restrict__ out_offs) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint64_t s0 = 0; s0 < n_seq; s0 += blockDim.x) {
+        uint64_t s = s0 + threadIdx.x;
+        unsigned long long v = 0;
+        if (s < n_seq) {
+            int64_t len = offs[s + 1] - offs[s];
+            v = len >= k ? (unsigned long long)(len - k + 1) : 0ull;
+        }
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long t = lane < nw ? warp_tot[lane] : 0ull;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
+                if (lane >= (unsigned)o) t += y;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        unsigned long long base = carry + (wid ? warp_tot[wid - 1] : 0ull);
+        if (s < n_seq) out_offs[s] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[nw - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_offs[n_seq] = carry;
+}
+
+// largest s in [lo, hi] with out_offs[s] <= o  (out_offs[lo] <= o guaranteed)
+__device__ __forceinline__ uint64_t find_seq(const unsigned long long *__restrict__ out_offs, uint64_t lo, uint64_t hi,
+                                             unsigned long long o) {
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(out_offs + mid) <= o) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int K, bool kCanon>
+__global__ void __launch_bounds__(kCovBlock) coverage_kernel(Index23Dev ix, MphfDev m, const uint64_t *__restrict__ tf13_direct,
+                                                           const uint8_t *__restrict__ seqs, const int64_t *__restrict__ offs,
+                                                           const unsigned long long *__restrict__ out_offs, uint64_t n_seq,
+                                                           uint64_t total_out, uint32_t cutoff, uint32_t *__restrict__ out) {
+    __shared__ uint64_t s_range[2];
+    const uint64_t o0 = (uint64_t)blockIdx.x * kCovBlock;
+    if (threadIdx.x < 2) {
+        unsigned long long o = threadIdx.x == 0 ? o0 : (o0 + kCovBlock - 1 < total_out ? o0 + kCovBlock - 1 : total_out - 1);
+        s_range[threadIdx.x] = find_seq(out_offs, 0, n_seq - 1, o);
+    }
+    __syncthreads();
+    const uint64_t o = o0 + threadIdx.x;
+    if (o >= total_out) return;
+    const uint64_t s = find_seq(out_offs, s_range[0], s_range[1], o);
+    const uint8_t *p = seqs + offs[s] + (o - out_offs[s]);
+    uint32_t tf;
+    if (K == 23) {
+        uint64_t r0, r1, r2;
+        load_window23(p, r0, r1, r2);
+        tf = find23_window<kCanon>(ix, m, r0, r1, r2).tf;
+    } else {
+        // get_tf_value_13mer: upper-case ACGT only, u64 count narrowed to u32
+        uint32_t v = 0;
+        bool valid = true;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            uint32_t ch = __ldg(p + j);
+            valid = valid && is_acgt_upper(ch);
+            v = (v << 2) | base_code_strict(ch);
+        }
+        tf = valid ? (uint32_t)__ldg(tf13_direct + v) : 0u;
+    }
+    __stcs(out + o, tf >= cutoff ? tf : 0u);
+}
+
+}  // namespace aix
+
+using namespace aix;
+
+extern "C" {
+
+int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *seqs_dev,
+                     const int64_t *offs_dev, uint64_t n_seq, uint64_t total_bytes, uint64_t total_out, int k,
+                     uint32_t cutoff, uint32_t *out_dev) {
+    (void)total_bytes;
+    if (!ctx) return AIX_ERR_ARG;
+    if (k == 23 && !ix23) return ctx->fail(AIX_ERR_STATE, "23-mer index not loaded");
+    if (k == 13 && !ix13) return ctx->fail(AIX_ERR_STATE, "13-mer index not loaded");
+    if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
+    if (n_seq == 0 || total_out == 0) return AIX_OK;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *oo;
+    AIX_TRY(ctx->reserve(SCR_TMP1, (n_seq + 1) * 8, &oo));
+    coverage_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(offs_dev, n_seq, k, (unsigned long long *)oo);
+    AIX_LAUNCH_CHECK(ctx);
+    unsigned grid = aix_grid(total_out, kCovBlock);
+    Index23Dev id = {};
+    MphfDev md = {};
+    if (k == 23) {
+        id = ix23->dev();
+        md = ix23->mphf->dev();
+        if (ix23->canonical_only)
+            coverage_kernel<23, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+        else
+            coverage_kernel<23, false><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+    } else {
+        coverage_kernel<13, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, ix13->tf_direct_dev, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+    }
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+// Host buffers: sequences are processed in groups of whole sequences (<= ~256 MiB of
+// output per group) on two alternating streams, offsets rebased per group.
+int aix_coverage(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *seqs, const int64_t *offs,
+                 uint64_t n_seq, int k, uint32_t cutoff, uint32_t *out) {
+    if (!ctx) return AIX_ERR_ARG;
+    if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
+    if (n_seq == 0) return AIX_OK;
+    if (!seqs || !offs || !out) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint64_t s = 0; s < n_seq; ++s)
+        if (offs[s + 1] < offs[s]) return ctx->fail(AIX_ERR_ARG, "offsets must be non-decreasing");
+    const uint64_t group_out_target = 64ull << 20;  // output values per group
+    uint64_t s0 = 0, out_done = 0;
+    std::vector<int64_t> rel;
+    // single stream: the group loop is ordered; transfers of the next group overlap through the
+    // copy engines because they are asynchronous with respect to the kernel of the previous one
+    cudaStream_t st = ctx->stream;
+    while (s0 < n_seq) {
+        uint64_t s1 = s0, g_out = 0;
+        while (s1 < n_seq) {
+            int64_t len = offs[s1 + 1] - offs[s1];
+            uint64_t w = len >= k ? (uint64_t)(len - k + 1) : 0;
+            if (g_out && g_out + w > group_out_target) break;
+            g_out += w;
+            ++s1;
+        }
+        const uint64_t g_seq = s1 - s0;
+        const uint64_t byte0 = (uint64_t)offs[s0], g_bytes = (uint64_t)offs[s1] - byte0;
+        if (g_out) {
+            rel.resize(g_seq + 1);
+            for (uint64_t i = 0; i <= g_seq; ++i) rel[i] = offs[s0 + i] - (int64_t)byte0;
+            void *d_seq, *d_offs, *d_out;
+            AIX_TRY(ctx->reserve(SCR_IN0, g_bytes + 64, &d_seq));
+            AIX_TRY(ctx->reserve(SCR_LEN0, (g_seq + 1) * 8, &d_offs));
+            AIX_TRY(ctx->reserve(SCR_OUT0, g_out * 4, &d_out));
+            AIX_CUDA(ctx, cudaMemcpyAsync(d_seq, seqs + byte0, g_bytes, cudaMemcpyHostToDevice, st));
+            AIX_CUDA(ctx, cudaMemcpyAsync(d_offs, rel.data(), (g_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+            AIX_TRY(aix_coverage_dev(ctx, ix23, ix13, (const uint8_t *)d_seq, (const int64_t *)d_offs, g_seq, g_bytes, g_out, k,
+                                     cutoff, (uint32_t *)d_out));
+            AIX_CUDA(ctx, cudaMemcpyAsync(out + out_done, d_out, g_out * 4, cudaMemcpyDeviceToHost, st));
+            AIX_CUDA(ctx, cudaStreamSynchronize(st));  // rel / scratch are reused by the next group
+        }
+        out_done += g_out;
+        s0 = s1;
+    }
+    return AIX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// device_common.cuh -- device-side building blocks shared by every kernel of
+// libaindex_cuda (sm_100a): 2-bit codec, Jenkins lookup8 triple hash, emphf MPHF
+// evaluation on the B200 layout, exact fast modulo.
+//
+// Reference semantics (ad3002/aindex):
+//   codec     src/kmers.cpp:12-85 (encode), :89-257 (decode), :355-388 (reverseDNA)
+//   hash      src/emphf/base_hash.hpp:38-91, mix :127-145
+//   lookup    src/emphf/mphf.hpp:79-89, bitpair_vector.hpp:46-49,
+//             ranked_bitpair_vector.hpp:47-62
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace aix {
+
+// ---------------------------------------------------------------------------------
+// B200 layout of the MPHF.  The reference stores words[] and a rank sample every 512
+// pairs, so rank() walks up to 16 words.  Here every 64-bit word of the bit-pair vector
+// is stored next to the rank of its first pair: one 16-byte load yields both the 2-bit
+// value and everything rank() needs, so a lookup is three independent 16-byte loads
+// (L2 resident: 0.46 B per key) and no dependent fourth access.
+// ---------------------------------------------------------------------------------
+struct MphfDev {
+    uint64_t n;
+    uint64_t hash_domain;
+    uint64_t seed;
+    uint64_t magic;     // floor(2^64 / hash_domain)
+    const ulonglong2 *recs;  // recs[w] = { words[w], rank of pair 32*w }
+};
+
+struct Index23Dev {
+    uint64_t n;
+    int canonical_only;
+    const uint4 *recs;  // recs[h] = { checker lo, checker hi, tf, 0 }: one sector per probe
+};
+
+__device__ __forceinline__ uint64_t ld_u64x2_lo(const ulonglong2 &v) { return v.x; }
+
+// exact h % d for any 64-bit h: q = mulhi(h, floor(2^64/d)) is q_true or q_true-1
+__device__ __forceinline__ uint64_t fastmod(uint64_t h, uint64_t d, uint64_t magic) {
+    uint64_t q = __umul64hi(h, magic);
+    uint64_t r = h - q * d;
+    if (r >= d) r -= d;
+    if (r >= d) r -= d;
+    return r;
+}
+
+// ---- Jenkins lookup8 (base_hash.hpp:127-145) ---------------------------------------
+__device__ __forceinline__ void jenkins_mix(uint64_t &a, uint64_t &b, uint64_t &c) {
+    a -= b; a -= c; a ^= (c >> 43);
+    b -= c; b -= a; b ^= (a << 9);
+    c -= a; c -= b; c ^= (b >> 8);
+    a -= b; a -= c; a ^= (c >> 38);
+    b -= c; b -= a; b ^= (a << 23);
+    c -= a; c -= b; c ^= (b >> 5);
+    a -= b; a -= c; a ^= (c >> 35);
+    b -= c; b -= a; b ^= (a << 49);
+    c -= a; c -= b; c ^= (b >> 11);
+    a -= b; a -= c; a ^= (c >> 12);
+    b -= c; b -= a; b ^= (a << 18);
+    c -= a; c -= b; c ^= (b >> 22);
+}
+
+constexpr uint64_t kGolden = 0x9e3779b97f4a7c13ULL;
+
+// hash of a string shorter than 24 bytes given as three little-endian words:
+// w0 = bytes 0..7, w1 = bytes 8..15, w2 = bytes 16..22 (unused bytes zero)
+__device__ __forceinline__ void jenkins_short(uint64_t seed, uint64_t w0, uint64_t w1, uint64_t w2,
+                                              uint32_t len, uint64_t &a, uint64_t &b, uint64_t &c) {
+    a = seed + w0;
+    b = seed + w1;
+    c = kGolden + len + (w2 << 8);  // base_hash.hpp:57-66: low byte of c holds the length
+    jenkins_mix(a, b, c);
+}
+
+// general length, bytes addressed through p (global or shared); base_hash.hpp:38-91
+__device__ __forceinline__ void jenkins_bytes(uint64_t seed, const uint8_t *p, uint32_t len,
+                                              uint64_t &a, uint64_t &b, uint64_t &c) {
+    a = seed; b = seed; c = kGolden;
+    uint32_t rem = len;
+    while (rem >= 24) {
+        uint64_t w[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 24; ++i) w[i >> 3] |= (uint64_t)p[i] << (8 * (i & 7));
+        a += w[0]; b += w[1]; c += w[2];
+        jenkins_mix(a, b, c);
+        p += 24; rem -= 24;
+    }
+    uint64_t w0 = 0, w1 = 0, w2 = 0;
+    for (uint32_t i = 0; i < rem; ++i) {
+        uint64_t v = p[i];
+        if (i < 8) w0 |= v << (8 * i);
+        else if (i < 16) w1 |= v << (8 * (i - 8));
+        else w2 |= v << (8 * (i - 16));
+    }
+    a += w0; b += w1; c += (uint64_t)len + (w2 << 8);
+    jenkins_mix(a, b, c);
+}
+
+// ---- emphf lookup on the B200 layout (mphf.hpp:79-89) -------------------------------
+__device__ __forceinline__ uint32_t nonzero_pairs64(uint64_t x) {
+    x = (x | (x >> 1)) & 0x5555555555555555ULL;
+    return (uint32_t)__popcll(x);  // == the SWAR count of ranked_bitpair_vector.hpp:92-106
+}
+
+__device__ __forceinline__ uint64_t mphf_eval(const MphfDev &m, uint64_t a, uint64_t b, uint64_t c) {
+    const uint64_t d = m.hash_domain;
+    uint64_t n0 = fastmod(a, d, m.magic);
+    uint64_t n1 = d + fastmod(b, d, m.magic);
+    uint64_t n2 = 2 * d + fastmod(c, d, m.magic);
+    ulonglong2 r0 = __ldg(&m.recs[n0 >> 5]);
+    ulonglong2 r1 = __ldg(&m.recs[n1 >> 5]);
+    ulonglong2 r2 = __ldg(&m.recs[n2 >> 5]);
+    uint32_t s0 = (uint32_t)(n0 & 31) * 2, s1 = (uint32_t)(n1 & 31) * 2, s2 = (uint32_t)(n2 & 31) * 2;
+    uint32_t v = (uint32_t)((r0.x >> s0) & 3) + (uint32_t)((r1.x >> s1) & 3) + (uint32_t)((r2.x >> s2) & 3);
+    uint32_t hidx = v % 3;
+    uint64_t word = hidx == 0 ? r0.x : (hidx == 1 ? r1.x : r2.x);
+    uint64_t base = hidx == 0 ? r0.y : (hidx == 1 ? r1.y : r2.y);
+    uint32_t sh = hidx == 0 ? s0 : (hidx == 1 ? s1 : s2);
+    uint64_t mask = ((uint64_t)1 << sh) - 1;  // sh <= 62
+    return base + nonzero_pairs64(word & mask);
+}
+
+// ---- 2-bit codec --------------------------------------------------------------------
+// kmers.cpp:17-23: A0 C1 G2 T3, anything else (incl. lower case) 0
+__device__ __forceinline__ uint32_t base_code_strict(uint32_t ch) {
+    return ch == 'C' ? 1u : (ch == 'G' ? 2u : (ch == 'T' ? 3u : 0u));
+}
+__device__ __forceinline__ bool is_acgt_upper(uint32_t ch) {
+    return ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
+}
+// ((c>>1)^(c>>2))&3 maps A,a->0 C,c->1 G,g->2 T,t->3 (only meaningful for ACGT letters)
+__device__ __forceinline__ uint32_t base_code_fast(uint32_t ch) { return ((ch >> 1) ^ (ch >> 2)) & 3u; }
+
+__device__ __forceinline__ uint64_t reverse_pairs64(uint64_t x) {
+    x = __brevll(x);                                                          // bit reversal
+    return ((x & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);  // un-swap inside pairs
+}
+// reverseDNA (kmers.cpp:376-381): (~pair_reverse(x)) >> 18; the reference loop is a full
+// 64-bit pair reversal for every input, so this closed form is identical for all x.
+__device__ __forceinline__ uint64_t revcomp23(uint64_t x) { return (~reverse_pairs64(x)) >> 18; }
+__device__ __forceinline__ uint32_t revcomp13(uint32_t x) {  // kmers.cpp:383-388
+    uint32_t r = __brev(x);
+    r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);
+    return (~r) >> 6;
+}
+
+// expand 8 two-bit codes (code j at bits [2j+1:2j]) into 8 ASCII bytes, byte j = "ACGT"[code j]
+__device__ __forceinline__ uint64_t ascii8_from_codes_le(uint32_t x16) {
+    uint32_t t = (x16 | (x16 << 8)) & 0x00FF00FFu;
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    t = (t | (t << 2)) & 0x33333333u;  // nibble j = code j
+    uint32_t lo = __byte_perm(0x54474341u, 0u, t);
+    uint32_t hi = __byte_perm(0x54474341u, 0u, t >> 16);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ASCII string of the k-mer whose REVERSE COMPLEMENT is `rc_of_kmer`, as little-endian words.
+// pair_reverse(u) == ~revcomp(u) on k pairs, i.e. the codes of u in string order sit in
+// ~rc at bits [2j+1:2j]: no bit reversal needed when both strands are at hand.
+__device__ __forceinline__ void ascii_words23_from_rc(uint64_t rc_of_kmer, uint64_t &w0, uint64_t &w1,
+                                                      uint64_t &w2) {
+    uint64_t x = ~rc_of_kmer;
+    w0 = ascii8_from_codes_le((uint32_t)(x & 0xFFFF));
+    w1 = ascii8_from_codes_le((uint32_t)((x >> 16) & 0xFFFF));
+    w2 = ascii8_from_codes_le((uint32_t)((x >> 32) & 0x3FFF)) & 0x00FFFFFFFFFFFFFFULL;  // 7 bytes
+}
+__device__ __forceinline__ void ascii_words13_from_rc(uint32_t rc_of_kmer, uint64_t &w0, uint64_t &w1) {
+    uint32_t x = ~rc_of_kmer;
+    w0 = ascii8_from_codes_le(x & 0xFFFF);
+    w1 = ascii8_from_codes_le((x >> 16) & 0x3FF) & 0x000000FFFFFFFFFFULL;  // 5 bytes
+}
+
+// MPHF id of a packed 23-mer u given its reverse complement r (hashes the ASCII string of u)
+__device__ __forceinline__ uint64_t mphf_lookup23(const MphfDev &m, uint64_t rc_of_u) {
+    uint64_t w0, w1, w2, a, b, c;
+    ascii_words23_from_rc(rc_of_u, w0, w1, w2);
+    jenkins_short(m.seed, w0, w1, w2, 23u, a, b, c);
+    return mphf_eval(m, a, b, c);
+}
+__device__ __forceinline__ uint64_t mphf_lookup13(const MphfDev &m, uint32_t rc_of_u) {
+    uint64_t w0, w1, a, b, c;
+    ascii_words13_from_rc(rc_of_u, w0, w1);
+    jenkins_short(m.seed, w0, w1, 0, 13u, a, b, c);
+    return mphf_eval(m, a, b, c);
+}
+
+// checker/tf probe: returns true and *tf when slot h holds `kmer`
+__device__ __forceinline__ bool probe23(const Index23Dev &ix, uint64_t h, uint64_t kmer, uint32_t &tf) {
+    if (h >= ix.n) return false;
+    uint4 r = __ldg(&ix.recs[h]);
+    uint64_t chk = ((uint64_t)r.y << 32) | r.x;
+    tf = r.z;
+    return chk == kmer;
+}
+
+}  // namespace aix

@@ -1,0 +1,418 @@
+// tf_query.cu -- batched term-frequency queries: 23-mer (MPHF + checker verify + tf
+// gather) and 13-mer (direct-address gather), plus the index uploads.
+//
+// Reference: AindexWrapper::get_tf_value_23mer python_wrapper.cpp:610-627 (and its users
+// :653-664, :700-742, :1219-1286), PHASH_MAP::get_freq/get_pfid hash.hpp:123-170,
+// 13-mer queries python_wrapper.cpp:482-608, :938-980, loaders hash.cpp:367-450,
+// python_wrapper.cpp:404-437.
+//
+// Kernel shape (K3): one query per thread, 256 queries per CTA.  The 23-byte records of a
+// CTA are contiguous, so they are staged into shared memory with coalesced 16-byte
+// streaming loads and re-read per thread as 7 aligned words + funnel shifts.  A query is
+// then ~450 integer instructions, three independent 16-byte L2 loads (MPHF record) and one
+// 16-byte HBM load ({checker, tf} record).  Latency is hidden by occupancy, not by
+// intra-thread pipelining: the loads of a query depend on its hash.
+#include "aix_internal.cuh"
+#include "batch_pipeline.cuh"
+#include "query23.cuh"
+
+namespace aix {
+
+constexpr int kQBlock = 256;
+
+// K3, fixed 23-byte records (the batch path of get_tf_values)
+template <int kMode, bool kCanon>
+__global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
+                                                           uint64_t q, void *__restrict__ out) {
+    __shared__ __align__(16) uint32_t tile[(kQBlock * 23 + 16) / 4 + 4];
+    const uint64_t q0 = (uint64_t)blockIdx.x * kQBlock;
+    const uint64_t byte0 = q0 * 23;  // multiple of 16 (256*23 = 16*368)
+    const uint64_t total = q * 23;
+    constexpr int kVec = kQBlock * 23 / 16;  // 368
+    const uint4 *src = reinterpret_cast<const uint4 *>(recs + byte0);
+    uint4 *dst = reinterpret_cast<uint4 *>(tile);
+    for (int v = threadIdx.x; v < kVec + 1; v += kQBlock) {
+        uint4 x = make_uint4(0, 0, 0, 0);
+        const uint64_t off = byte0 + (uint64_t)v * 16;
+        if (off + 16 <= total) {
+            x = __ldcs(src + v);
+        } else if (off < total) {  // last, partial vector of the batch: never read past the buffer
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (uint32_t b = 0; off + b < total; ++b) w[b >> 2] |= (uint32_t)recs[off + b] << (8 * (b & 3));
+            x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        dst[v] = x;
+    }
+    __syncthreads();
+    const uint64_t i = q0 + threadIdx.x;
+    if (i >= q) return;
+    const uint32_t base = threadIdx.x * 23u;
+    const uint32_t w = base >> 2, sh = (base & 3u) * 8u;
+    uint32_t x0 = tile[w], x1 = tile[w + 1], x2 = tile[w + 2], x3 = tile[w + 3], x4 = tile[w + 4], x5 = tile[w + 5],
+             x6 = tile[w + 6];
+    uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
+             y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
+    uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
+             r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
+    query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
+}
+
+// K3, generic records (any stride, per-record lengths)
+template <int kMode, bool kCanon>
+__global__ void __launch_bounds__(kQBlock) tf23_generic_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
+                                                             uint32_t stride, const uint8_t *__restrict__ lens, uint64_t q,
+                                                             void *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * kQBlock + threadIdx.x;
+    if (i >= q) return;
+    uint32_t len = lens ? lens[i] : stride;
+    if (len > stride) len = stride;
+    const uint8_t *p = recs + i * stride;
+    uint64_t w[3] = {0, 0, 0};
+    const uint32_t nb = len < 23u ? len : 23u;
+    for (uint32_t j = 0; j < nb; ++j) w[j >> 3] |= (uint64_t)__ldg(p + j) << (8 * (j & 7));
+    query23<kMode, kCanon>(ix, m, w[0], w[1], w[2], len, p, i, out);
+}
+
+// PHASH_MAP::get_freq(uint64_t) (hash.hpp:123-140)
+template <bool kCanon>
+__global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__restrict__ ukmers, uint64_t q,
+                                  uint32_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    // get_bitset_dna23 decodes the low 46 bits only, so bits above do not reach the hash, but
+    // the checker comparison uses the full 64-bit value
+    uint64_t k = ukmers[i];
+    uint64_t lo = k & ((1ULL << 46) - 1);
+    uint64_t rl = revcomp23(lo);
+    uint32_t res = 0, tf;
+    uint64_t h1 = mphf_lookup23(m, rl);
+    if (probe23(ix, h1, k, tf)) res = tf;
+    else {
+        uint64_t rk = revcomp23(k);       // reverseDNA: bits above 46 of k fall off, rk == rl
+        uint64_t h2 = mphf_lookup23(m, lo);  // hashes the ASCII string of rk
+        if (probe23(ix, h2, rk, tf)) res = tf;
+    }
+    out[i] = res;
+}
+
+// ---- index upload helpers ----------------------------------------------------------------
+__global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const uint32_t *__restrict__ tf, uint64_t n,
+                                    uint4 *__restrict__ recs, int *__restrict__ non_canonical) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c = checker[i];
+    recs[i] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), tf[i], 0u);
+    if ((c >> 46) != 0 || c > revcomp23(c)) *non_canonical = 1;
+}
+
+__global__ void tf13_direct_kernel(MphfDev m, const uint64_t *__restrict__ tf_mphf, uint64_t *__restrict__ tf_direct) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (uint32_t)AIX_TOTAL_13MERS) return;
+    uint64_t id = mphf_lookup13(m, revcomp13(v));
+    tf_direct[v] = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;  // python_wrapper.cpp:498-500
+}
+
+// ---- K4: 13-mer queries ----------------------------------------------------------------------
+// python_wrapper.cpp:505-517: reverse, complement ACGT, leave anything else as it is
+__device__ __forceinline__ uint32_t comp13_char(uint32_t c) {
+    return c == 'A' ? 'T' : (c == 'T' ? 'A' : (c == 'G' ? 'C' : (c == 'C' ? 'G' : c)));
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kQBlock) tf13_kernel(MphfDev m, const uint64_t *__restrict__ tf_mphf,
+                                                     const uint64_t *__restrict__ tf_direct, const uint8_t *__restrict__ recs,
+                                                     uint32_t stride, const uint8_t *__restrict__ lens, uint64_t q,
+                                                     void *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * kQBlock + threadIdx.x;
+    if (i >= q) return;
+    uint32_t len = lens ? lens[i] : stride;
+    if (len > stride) len = stride;
+    const uint8_t *p = recs + i * stride;
+    uint32_t ch[13];
+    bool valid = len == 13u;
+    uint32_t v = 0;
+    if (len == 13u) {
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            ch[j] = __ldg(p + j);
+            valid = valid && is_acgt_upper(ch[j]);
+            v = (v << 2) | base_code_strict(ch[j]);
+        }
+    }
+    if (kMode == AIX_Q_TF) {
+        // :482-503 / :938-980: len == 13 and upper-case ACGT only, value narrowed to u32
+        ((uint32_t *)out)[i] = valid ? (uint32_t)tf_direct[v] : 0u;
+        return;
+    }
+    uint64_t fwd = 0, rev = 0;
+    if (len == 13u) {
+        if (valid) {
+            fwd = tf_direct[v];
+            rev = tf_direct[revcomp13(v)];
+        } else {
+            // :533-542: no validity check -- the raw bytes are hashed; an id of 4^13 (possible
+            // for non-keys) is out of bounds in the reference and defined as 0 here
+            uint64_t w0 = 0, w1 = 0, x0 = 0, x1 = 0, a, b, c;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+                uint64_t f = ch[j], g = comp13_char(ch[12 - j]);
+                if (j < 8) { w0 |= f << (8 * j); x0 |= g << (8 * j); }
+                else { w1 |= f << (8 * (j - 8)); x1 |= g << (8 * (j - 8)); }
+            }
+            jenkins_short(m.seed, w0, w1, 0, 13u, a, b, c);
+            uint64_t id = mphf_eval(m, a, b, c);
+            fwd = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
+            jenkins_short(m.seed, x0, x1, 0, 13u, a, b, c);
+            id = mphf_eval(m, a, b, c);
+            rev = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
+        }
+    }
+    if (kMode == AIX_Q_TOTAL) ((uint64_t *)out)[i] = fwd + rev;
+    else {
+        ((uint64_t *)out)[2 * i] = fwd;
+        ((uint64_t *)out)[2 * i + 1] = rev;
+    }
+}
+
+static size_t out_bytes23(int mode) {
+    switch (mode) {
+        case AIX_Q_TF: return 4;
+        case AIX_Q_BOTH: return 8;
+        default: return 8;
+    }
+}
+
+template <int kMode>
+static void launch23_mode(const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
+                          uint64_t q, void *out) {
+    Index23Dev id = ix->dev();
+    MphfDev md = ix->mphf->dev();
+    unsigned grid = aix_grid(q, kQBlock);
+    const bool fixed = (stride == 23 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
+    if (fixed) {
+        if (ix->canonical_only) tf23_fixed_kernel<kMode, true><<<grid, kQBlock, 0, st>>>(id, md, recs, q, out);
+        else tf23_fixed_kernel<kMode, false><<<grid, kQBlock, 0, st>>>(id, md, recs, q, out);
+    } else {
+        if (ix->canonical_only) tf23_generic_kernel<kMode, true><<<grid, kQBlock, 0, st>>>(id, md, recs, stride, lens, q, out);
+        else tf23_generic_kernel<kMode, false><<<grid, kQBlock, 0, st>>>(id, md, recs, stride, lens, q, out);
+    }
+}
+
+int launch_tf23(aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
+                const uint8_t *lens, uint64_t q, int mode, void *out) {
+    if (q == 0) return AIX_OK;
+    switch (mode) {
+        case AIX_Q_TF: launch23_mode<AIX_Q_TF>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_TOTAL: launch23_mode<AIX_Q_TOTAL>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_BOTH: launch23_mode<AIX_Q_BOTH>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_PFID: launch23_mode<AIX_Q_PFID>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_STRAND: launch23_mode<AIX_Q_STRAND>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_KID: launch23_mode<AIX_Q_KID>(ix, st, recs, stride, lens, q, out); break;
+        default: return ctx->fail(AIX_ERR_ARG, "unknown query mode %d", mode);
+    }
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+int launch_tf13(aix_ctx *ctx, const aix_index13 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
+                const uint8_t *lens, uint64_t q, int mode, void *out) {
+    if (q == 0) return AIX_OK;
+    MphfDev md = ix->mphf->dev();
+    unsigned grid = aix_grid(q, kQBlock);
+    switch (mode) {
+        case AIX_Q_TF: tf13_kernel<AIX_Q_TF><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
+        case AIX_Q_TOTAL: tf13_kernel<AIX_Q_TOTAL><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
+        case AIX_Q_BOTH: tf13_kernel<AIX_Q_BOTH><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
+        default: return ctx->fail(AIX_ERR_ARG, "unknown 13-mer query mode %d", mode);
+    }
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+}  // namespace aix
+
+using namespace aix;
+
+static int read_file(aix_ctx *ctx, const std::string &path, std::vector<uint8_t> &buf) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return ctx->fail(AIX_ERR_IO, "required file not found: %s", path.c_str());
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(sz > 0 ? (size_t)sz : 0);
+    bool ok = buf.empty() || fread(buf.data(), 1, buf.size(), f) == buf.size();
+    fclose(f);
+    return ok ? AIX_OK : ctx->fail(AIX_ERR_IO, "short read: %s", path.c_str());
+}
+
+extern "C" {
+
+int aix_index23_upload_dev(aix_ctx *ctx, const aix_mphf *m, const uint64_t *checker_dev, const uint32_t *tf_dev,
+                           uint64_t n, aix_index23 **out) {
+    if (!ctx || !m || !out) return AIX_ERR_ARG;
+    *out = nullptr;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    aix_index23 *ix = new aix_index23();
+    ix->n = n; ix->mphf = m;
+    int *flag_dev = nullptr;
+    cudaError_t e = cudaMalloc(&ix->recs_dev, (n ? n : 1) * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&flag_dev, sizeof(int));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        aix_index23_destroy(ctx, ix);
+        return ctx->fail(AIX_ERR_NOMEM, "index23 upload: %s", cudaGetErrorString(e));
+    }
+    int flag = 0;
+    cudaMemsetAsync(flag_dev, 0, sizeof(int), ctx->stream);
+    if (n) {
+        index23_pack_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(checker_dev, tf_dev, n, ix->recs_dev, flag_dev);
+        ctx->launches++;
+    }
+    cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(flag_dev);
+    if (e != cudaSuccess) {
+        aix_index23_destroy(ctx, ix);
+        return ctx->fail(AIX_ERR_CUDA, "index23 upload: %s", cudaGetErrorString(e));
+    }
+    ix->canonical_only = flag ? 0 : 1;
+    *out = ix;
+    return AIX_OK;
+}
+
+int aix_index23_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *checker, const uint32_t *tf, uint64_t n,
+                       aix_index23 **out) {
+    if (!ctx || !m || !out || (n && (!checker || !tf))) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *c_dev = nullptr;
+    uint32_t *t_dev = nullptr;
+    cudaError_t e = cudaMalloc(&c_dev, (n ? n : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&t_dev, (n ? n : 1) * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (c_dev) cudaFree(c_dev);
+        return ctx->fail(AIX_ERR_NOMEM, "index23 staging: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(c_dev, checker, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(t_dev, tf, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = aix_index23_upload_dev(ctx, m, c_dev, t_dev, n, out);
+    cudaFree(c_dev);
+    cudaFree(t_dev);
+    return rc;
+}
+
+int aix_index23_load_prefix(aix_ctx *ctx, const char *prefix, aix_mphf **mphf_out, aix_index23 **out) {
+    if (!ctx || !prefix || !mphf_out || !out) return AIX_ERR_ARG;
+    *mphf_out = nullptr; *out = nullptr;
+    std::string p(prefix);
+    std::vector<uint8_t> kb, tb;
+    AIX_TRY(read_file(ctx, p + ".kmers.bin", kb));
+    AIX_TRY(read_file(ctx, p + ".tf.bin", tb));
+    uint64_t n = kb.size() / 8;  // hash.cpp:388-392
+    if (tb.size() / 4 < n) return ctx->fail(AIX_ERR_IO, "%s.tf.bin shorter than %s.kmers.bin", prefix, prefix);
+    aix_mphf *m = nullptr;
+    AIX_TRY(aix_mphf_load_pf(ctx, (p + ".pf").c_str(), &m));
+    int rc = aix_index23_upload(ctx, m, (const uint64_t *)kb.data(), (const uint32_t *)tb.data(), n, out);
+    if (rc != AIX_OK) {
+        aix_mphf_destroy(ctx, m);
+        return rc;
+    }
+    *mphf_out = m;
+    return AIX_OK;
+}
+
+void aix_index23_destroy(aix_ctx *ctx, aix_index23 *ix) {
+    if (!ix) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (ix->recs_dev) cudaFree(ix->recs_dev);
+    delete ix;
+}
+
+int aix_index23_info(const aix_index23 *ix, uint64_t info[2]) {
+    if (!ix || !info) return AIX_ERR_ARG;
+    info[0] = ix->n;
+    info[1] = (uint64_t)ix->canonical_only;
+    return AIX_OK;
+}
+
+int aix_tf23_batch_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs_dev, uint32_t stride,
+                       const uint8_t *lens_dev, uint64_t q, int mode, void *out_dev) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    return launch_tf23(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
+}
+
+int aix_tf23_batch(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
+                   uint64_t q, int mode, void *out) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    if (mode < AIX_Q_TF || mode > AIX_Q_KID) return ctx->fail(AIX_ERR_ARG, "unknown query mode %d", mode);
+    return run_record_batches(ctx, recs, stride, lens, q, out, out_bytes23(mode),
+                              [&](cudaStream_t st, const uint8_t *r, const uint8_t *l, uint64_t nq, void *o) {
+                                  return launch_tf23(ctx, ix, st, r, stride, l, nq, mode, o);
+                              });
+}
+
+int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q, uint32_t *out) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    Index23Dev id = ix->dev();
+    MphfDev md = ix->mphf->dev();
+    return run_record_batches(ctx, (const uint8_t *)ukmers, 8, nullptr, q, out, 4,
+                              [&](cudaStream_t st, const uint8_t *r, const uint8_t *, uint64_t nq, void *o) {
+                                  get_freq23_kernel<false><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, (const uint64_t *)r, nq, (uint32_t *)o);
+                                  AIX_LAUNCH_CHECK(ctx);
+                                  return AIX_OK;
+                              });
+}
+
+int aix_index13_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *tf64, aix_index13 **out) {
+    if (!ctx || !m || !tf64 || !out) return AIX_ERR_ARG;
+    *out = nullptr;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    aix_index13 *ix = new aix_index13();
+    ix->mphf = m;
+    cudaError_t e = cudaMalloc(&ix->tf_mphf_dev, AIX_TOTAL_13MERS * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->tf_direct_dev, AIX_TOTAL_13MERS * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        aix_index13_destroy(ctx, ix);
+        return ctx->fail(AIX_ERR_NOMEM, "index13 upload: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(ix->tf_mphf_dev, tf64, AIX_TOTAL_13MERS * 8, cudaMemcpyHostToDevice, ctx->stream);
+    tf13_direct_kernel<<<aix_grid(AIX_TOTAL_13MERS, 256), 256, 0, ctx->stream>>>(m->dev(), ix->tf_mphf_dev, ix->tf_direct_dev);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        aix_index13_destroy(ctx, ix);
+        return ctx->fail(AIX_ERR_CUDA, "index13 upload: %s", cudaGetErrorString(e));
+    }
+    *out = ix;
+    return AIX_OK;
+}
+
+void aix_index13_destroy(aix_ctx *ctx, aix_index13 *ix) {
+    if (!ix) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (ix->tf_mphf_dev) cudaFree(ix->tf_mphf_dev);
+    if (ix->tf_direct_dev) cudaFree(ix->tf_direct_dev);
+    delete ix;
+}
+
+int aix_tf13_batch_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *recs_dev, uint32_t stride,
+                       const uint8_t *lens_dev, uint64_t q, int mode, void *out_dev) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    return launch_tf13(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
+}
+
+int aix_tf13_batch(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
+                   uint64_t q, int mode, void *out) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    if (mode < AIX_Q_TF || mode > AIX_Q_BOTH) return ctx->fail(AIX_ERR_ARG, "unknown 13-mer query mode %d", mode);
+    size_t ob = mode == AIX_Q_TF ? 4 : (mode == AIX_Q_TOTAL ? 8 : 16);
+    return run_record_batches(ctx, recs, stride, lens, q, out, ob,
+                              [&](cudaStream_t st, const uint8_t *r, const uint8_t *l, uint64_t nq, void *o) {
+                                  return launch_tf13(ctx, ix, st, r, stride, l, nq, mode, o);
+                              });
+}
+
+}  // extern "C"

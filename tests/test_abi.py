@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/aindex_cuda.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from aindex_b200 import build
+    build.build_cuda()
+    return build.LIB
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "aindex_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aix_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = [s for s in _declared() if s not in exported]
+    assert not missing, f"declared in aindex_cuda.h but not exported: {missing}"
+
+
+def test_ctypes_signatures_cover_header(built):
+    from aindex_b200 import capi
+    assert sorted(capi.SIGNATURES) == _declared()
+    L = capi.lib()
+    assert L.aix_version().startswith(b"aindex_b200")
+
+
+def test_sm100a_code_present(built):
+    out = subprocess.run(["cuobjdump", "-lelf", built], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from aindex_b200 import capi
+    with pytest.raises(capi.AixError) as e:
+        capi.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reach into oracle/ (test infrastructure)."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "aindex_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle\b|oracle/|liboracle|aindex_oracle", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

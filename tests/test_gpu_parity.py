@@ -1,0 +1,463 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, aindex_b200.capi) against
+  (a) the golden fixtures produced by the unmodified reference (tests/golden/), and
+  (b) the CPU oracle (oracle/) on seeded inputs.
+Everything is integer work: the bar is bit-exact equality.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def rc(s: bytes) -> bytes:
+    return s.translate(COMP)[::-1]
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from aindex_b200 import capi as c
+    return c
+
+
+@pytest.fixture(scope="module")
+def ctx(capi):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def g23(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden23.npz"))
+
+
+@pytest.fixture(scope="module")
+def g13(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden13.npz"))
+
+
+@pytest.fixture(scope="module")
+def idx23(capi, ctx, golden_dir):
+    return capi.Index23.load_prefix(ctx, os.path.join(golden_dir, "idx23"))
+
+
+@pytest.fixture(scope="module")
+def oidx23(oracle, golden_dir):
+    return oracle.Index23.load_prefix(os.path.join(golden_dir, "idx23"))
+
+
+def _queries(recs, lens):
+    return [recs[i, :lens[i]].tobytes() for i in range(recs.shape[0])]
+
+
+# ---------------------------------------------------------------------------- codec / hash
+def test_jenkins_and_codec(oracle, ctx):
+    rng = np.random.default_rng(7)
+    strs = [rng.integers(0, 256, size=int(n), dtype=np.uint8).tobytes() for n in rng.integers(0, 90, size=300)]
+    strs += [b"A" * n for n in (0, 1, 7, 8, 9, 15, 16, 17, 22, 23, 24, 25, 47, 48, 49, 71, 72, 73)]
+    seed = 0x0123456789ABCDEF
+    got = ctx.jenkins64(seed, strs)
+    for s, g in zip(strs, got):
+        assert tuple(int(x) for x in g) == oracle.jenkins64(seed, s)
+    kmers = [rng.choice(ACGT, size=23).tobytes() for _ in range(200)]
+    kmers += [b"ACGTNACGTacgtACGT~ACGTAC", b"", b"ACG", b"N" * 23]
+    for k, enc, dec, rev in ((23, oracle.dna23_bitset, oracle.bitset_dna23, oracle.reverse_dna23),
+                             (13, oracle.dna13_bitset, oracle.bitset_dna13, oracle.reverse_dna13)):
+        vals = ctx.encode(kmers, k)
+        assert [int(v) for v in vals] == [enc(s) for s in kmers]
+        assert [d.tobytes().decode() for d in ctx.decode(vals, k)] == [dec(int(v)) for v in vals]
+        assert [int(v) for v in ctx.revcomp(vals, k)] == [rev(int(v)) for v in vals]
+    seq = rng.choice(np.frombuffer(b"ACGTNacgt\n~", dtype=np.uint8), size=1001).tobytes()
+    assert np.array_equal(ctx.pack_2bit(seq), oracle.dna_bitset_pack(seq))
+    for k, enc, rev in ((23, oracle.dna23_bitset, oracle.reverse_dna23), (13, oracle.dna13_bitset, oracle.reverse_dna13)):
+        fwd, rcv, valid = ctx.rolling_kmers(seq, k)
+        for i in range(0, len(seq) - k + 1, 7):
+            w = seq[i:i + k]
+            assert int(fwd[i]) == enc(w) and int(rcv[i]) == rev(enc(w))
+            assert int(valid[i]) == (1 if not w.strip(b"ACGT") else 0)
+
+
+def test_mphf_lookup_golden(capi, ctx, idx23, g23, pf13, oracle):
+    recs, lens = g23["recs"], g23["lens"]
+    assert np.array_equal(idx23.mphf.lookup(_queries(recs, lens)), g23["hash"])
+    m = capi.Mphf.load(ctx, pf13)
+    kat = {b"AAAAAAAAAAAAA": 51399613, b"AAAAAAAAAAAAC": 20651245, b"ACGTACGTACGTA": 11618410,
+           b"TTTTTTTTTTTTT": 16974388, b"GATTACAGATTAC": 34020858}
+    assert m.lookup(list(kat)).tolist() == list(kat.values())
+    # the full permutation, uint32 LE, is pinned by md5 and is a bijection
+    perm = m.perm13()
+    assert hashlib.md5(perm.tobytes()).hexdigest() == "3864cfb768e7d5182b9b88df1b23b575"
+    assert np.array_equal(np.sort(perm), np.arange(1 << 26, dtype=np.uint32))
+    # .pf round trip is byte-identical
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "x.pf")
+        m.save(p)
+        assert hashlib.md5(open(p, "rb").read()).hexdigest() == "5fadfc861de1b04045926a24b32e456a"
+
+
+# ---------------------------------------------------------------------------- 23-mer queries
+def test_tf23_golden_all_modes(capi, idx23, g23):
+    q = _queries(g23["recs"], g23["lens"])
+    assert idx23.info == {"n": int(g23["n_kmers"][0]), "canonical_only": True}
+    assert np.array_equal(idx23.query(q, capi.Q_TF), g23["tf"])
+    assert np.array_equal(idx23.query(q, capi.Q_TOTAL), g23["total"])
+    assert np.array_equal(idx23.query(q, capi.Q_BOTH), g23["both"])
+    assert np.array_equal(idx23.query(q, capi.Q_KID), g23["kid"])
+    assert np.array_equal(idx23.query(q, capi.Q_STRAND), g23["strand"])
+    # single-query calls agree with the batch (test_aindex_functionality.py:911-913)
+    for i in range(0, len(q), 97):
+        assert idx23.query([q[i]], capi.Q_TF)[0] == g23["tf"][i]
+
+
+def _mixed_queries(rng, oidx, n):
+    """hits on both strands, misses, N / lower case / junk, odd lengths."""
+    from oracle import oracle as O
+    out = []
+    chk = oidx.checker
+    for i in rng.choice(chk.size, size=n, replace=True):
+        km = O.bitset_dna23(int(chk[i])).encode()
+        r = rng.random()
+        if r < 0.3:
+            out.append(km)
+        elif r < 0.6:
+            out.append(rc(km))
+        elif r < 0.8:
+            out.append(rng.choice(ACGT, size=23).tobytes())
+        elif r < 0.9:
+            b = bytearray(km if rng.random() < 0.5 else rc(km))
+            b[int(rng.integers(0, 23))] = int(rng.choice(np.frombuffer(b"NnacgtX~\n\x00\xff", dtype=np.uint8)))
+            out.append(bytes(b))
+        else:
+            ln = int(rng.integers(0, 60))
+            base = (km + rc(km) + km)[:ln]
+            out.append(base)
+    return out
+
+
+def test_tf23_vs_oracle_mixed(capi, oracle, idx23, oidx23):
+    rng = np.random.default_rng(11)
+    q = _mixed_queries(rng, oidx23, 4000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH),
+                        (capi.Q_PFID, oracle.MODE_PFID), (capi.Q_STRAND, oracle.MODE_STRAND), (capi.Q_KID, oracle.MODE_KID)):
+        got = idx23.query(q, mode)
+        want = oidx23.batch(recs, lens, omode)
+        assert np.array_equal(got, want), f"mode {mode}"
+
+
+def test_tf23_fixed_stride_fast_path(capi, oracle, idx23, oidx23):
+    """uint8[q,23] records: the shared-memory staged kernel, incl. a ragged last CTA."""
+    rng = np.random.default_rng(12)
+    for nq in (1, 255, 256, 257, 10007):
+        q = [x for x in _mixed_queries(rng, oidx23, 2 * nq) if len(x) == 23][:nq]
+        recs = np.frombuffer(b"".join(q), dtype=np.uint8).reshape(len(q), 23).copy()
+        for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_BOTH, oracle.MODE_BOTH), (capi.Q_PFID, oracle.MODE_PFID),
+                            (capi.Q_STRAND, oracle.MODE_STRAND)):
+            assert np.array_equal(idx23.query(recs, mode), oidx23.batch(recs, None, omode))
+    assert np.array_equal(idx23.get_freq(oidx23.checker[:500]), oidx23.tf[:500])
+    assert idx23.query(np.zeros((0, 23), dtype=np.uint8)).size == 0
+
+
+def test_tf23_non_canonical_index_two_probe_path(capi, oracle, ctx, oidx23):
+    """An index that stores some k-mers in their non-canonical orientation (what the reference's
+    broken kmer_counter produces) must take the exact forward-then-reverse path."""
+    rng = np.random.default_rng(13)
+    kmers = oidx23.checker.copy()
+    flip = rng.random(kmers.size) < 0.4
+    kmers[flip] = np.array([oracle.reverse_dna23(int(x)) for x in kmers[flip]], dtype=np.uint64)
+    counts = rng.integers(1, 1000, size=kmers.size).astype(np.uint32)
+    m = capi.Mphf.build(ctx, kmers, 23)
+    words, ranks = m.arrays()
+    om = oracle.Mphf.from_arrays(m.info["n"], m.info["hash_domain"], m.info["seed"], words, ranks)
+    ids = om.lookup_batch(np.array([list(oracle.bitset_dna23(int(x)).encode()) for x in kmers], dtype=np.uint8))
+    assert np.array_equal(np.sort(ids), np.arange(kmers.size, dtype=np.uint64))  # minimal + perfect
+    checker = np.zeros_like(kmers)
+    tf = np.zeros_like(counts)
+    checker[ids.astype(np.int64)] = kmers
+    tf[ids.astype(np.int64)] = counts
+    ix = capi.Index23.upload(ctx, m, checker, tf)
+    assert ix.info["canonical_only"] is False
+    oix = oracle.Index23(om, checker, tf)
+    q = _mixed_queries(rng, oix, 3000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH),
+                        (capi.Q_PFID, oracle.MODE_PFID), (capi.Q_STRAND, oracle.MODE_STRAND), (capi.Q_KID, oracle.MODE_KID)):
+        assert np.array_equal(ix.query(q, mode), oix.batch(recs, lens, omode)), f"mode {mode}"
+    q23 = [x for x in q if len(x) == 23]
+    r23 = np.frombuffer(b"".join(q23), dtype=np.uint8).reshape(len(q23), 23).copy()
+    assert np.array_equal(ix.query(r23, capi.Q_TF), oix.batch(r23, None, oracle.MODE_TF))
+
+
+# ---------------------------------------------------------------------------- MPHF build
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 1000, 200_000])
+def test_mphf_build_is_minimal_perfect(capi, oracle, ctx, n):
+    rng = np.random.default_rng(100 + n)
+    kmers = np.unique(rng.integers(0, 1 << 46, size=n + n // 8 + 4, dtype=np.uint64))[:n]
+    rng.shuffle(kmers)
+    m = capi.Mphf.build(ctx, kmers, 23)
+    info = m.info
+    assert info["n"] == n and info["hash_domain"] == (int(np.ceil(n * 1.23)) + 2) // 3
+    words, ranks = m.arrays()
+    om = oracle.Mphf.from_arrays(info["n"], info["hash_domain"], info["seed"], words, ranks)
+    recs = ctx.decode(kmers, 23)
+    ids_gpu = m.lookup(recs)
+    ids_cpu = om.lookup_batch(recs, threads=8)
+    assert np.array_equal(ids_gpu, ids_cpu)
+    assert np.array_equal(np.sort(ids_gpu), np.arange(n, dtype=np.uint64))
+    # the block ranks follow ranked_bitpair_vector.hpp:17-31
+    nz = np.array([bin((int(w) | (int(w) >> 1)) & 0x5555555555555555).count("1") for w in words[:4096]], dtype=np.uint64)
+    blocks = min(ranks.size, nz.size // 16)
+    want = np.concatenate([[0], np.cumsum(nz.reshape(-1, 16)[:blocks].sum(axis=1))])[:blocks]
+    assert np.array_equal(ranks[:blocks], want.astype(np.uint64))
+
+
+def test_index_build_pipeline_vs_bruteforce(capi, oracle, ctx):
+    """reads -> canonical 23-mer table -> MPHF -> checker/tf fill -> queries, against a brute-force
+    dictionary (tests/analyze_kmers.py definition) and the oracle on the built index."""
+    rng = np.random.default_rng(21)
+    genome = rng.choice(ACGT, size=30000).tobytes()
+    lines = []
+    for i in range(1500):
+        ln = int(rng.integers(20, 160))
+        st = int(rng.integers(0, len(genome) - ln))
+        r = genome[st:st + ln]
+        if rng.random() < 0.5:
+            r = rc(r)
+        if i % 50 == 7:
+            r = r[:10] + b"N" + r[11:]
+        if i % 31 == 3:
+            r = r + b"~" + rc(genome[st:st + 40])
+        lines.append(r)
+    reads = b"\n".join(lines) + b"\n"
+    want = {}
+    for line in reads.split(b"\n"):
+        for i in range(len(line) - 22):
+            km = line[i:i + 23]
+            if km.strip(b"ACGT"):
+                continue
+            c = min(km, rc(km))
+            want[c] = want.get(c, 0) + 1
+    kmers, counts = ctx.canonical23_count(reads)
+    assert kmers.size == len(want)
+    assert np.all(kmers[1:] > kmers[:-1])
+    dec = ctx.decode(kmers, 23)
+    for i in range(0, kmers.size, 37):
+        assert want[dec[i].tobytes()] == int(counts[i])
+    assert int(counts.sum()) == sum(want.values())
+    m = capi.Mphf.build(ctx, kmers, 23)
+    checker = np.zeros(kmers.size, dtype=np.uint64)
+    tf = np.zeros(kmers.size, dtype=np.uint32)
+    ctx.check(capi.lib().aix_index23_fill(ctx.handle, m._h, kmers.ctypes.data, counts.ctypes.data, kmers.size,
+                                          checker.ctypes.data, tf.ctypes.data))
+    ix = capi.Index23.upload(ctx, m, checker, tf)
+    assert ix.info["canonical_only"] is True
+    words, ranks = m.arrays()
+    oix = oracle.Index23(oracle.Mphf.from_arrays(m.info["n"], m.info["hash_domain"], m.info["seed"], words, ranks), checker, tf)
+    q = _mixed_queries(rng, oix, 5000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    got = ix.query(q, capi.Q_TF)
+    assert np.array_equal(got, oix.batch(recs, lens, oracle.MODE_TF))
+    for s, t in zip(q, got):
+        if len(s) == 23 and not s.strip(b"ACGT"):
+            assert int(t) == want.get(min(s, rc(s)), 0)
+    # positions index on the same reads: every bucket full, ascending, pointing at the k-mer
+    indices, positions = ix.positions_build(reads)
+    oi, op = oix.positions_build(reads)
+    assert np.array_equal(indices, oi) and np.array_equal(positions, op)
+    assert (positions > 0).all()
+
+
+# ---------------------------------------------------------------------------- 13-mers
+@pytest.fixture(scope="module")
+def m13(capi, ctx, pf13):
+    return capi.Mphf.load(ctx, pf13)
+
+
+def test_count13_reference_fixtures(capi, ctx, m13):
+    """count_kmers13 on the reference's tests/data files: md5 of the 512 MiB output."""
+    data = b"ATCGATCGATCGATCG\nGCTAGCTAGCTAGCTA\nTTTTAAAACCCCGGGG\nNNNNNNNNNNNNNNNN\n"
+    tf, st = ctx.count13(m13, data)
+    assert st == {"sequences": 4, "windows": 16, "valid": 12, "invalid": 4}
+    assert hashlib.md5(tf.tobytes()).hexdigest() == "f02208bc8a20909ddadd8500ecbf608a"
+    tf, st = ctx.count13(m13, b"")
+    assert st["windows"] == 0 and not tf.any()
+    tf, st = ctx.count13(m13, b"ACGTACGTACGT\n")  # 12 characters: skipped before it counts as a sequence
+    assert st == {"sequences": 0, "windows": 0, "valid": 0, "invalid": 0}
+
+
+@pytest.mark.parametrize("name", ["plain", "plain_nonl", "fastq", "fasta", "crlf"])
+def test_count13_golden(capi, ctx, m13, g13, name):
+    tf, st = ctx.count13(m13, g13[f"{name}_data"])
+    assert [st["sequences"], st["windows"], st["valid"], st["invalid"]] == g13[f"{name}_stats"].tolist()
+    nz = np.nonzero(tf)[0]
+    assert np.array_equal(nz.astype(np.uint32), g13[f"{name}_ids"])
+    assert np.array_equal(tf[nz], g13[f"{name}_counts"])
+    assert hashlib.md5(tf.tobytes()).hexdigest() == str(g13[f"{name}_md5"])
+
+
+def _random_reads(rng, n_reads, read_len, alphabet=b"ACGT", n_rate=0.0):
+    a = rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=(n_reads, read_len + 1))
+    if n_rate:
+        a[rng.random(a.shape) < n_rate] = ord("N")
+    a[:, read_len] = ord("\n")
+    return a.reshape(-1)
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_count13_vs_oracle_and_chunking(capi, oracle, ctx, m13, variant, monkeypatch):
+    """2 MB of reads against the oracle; the same input through the multi-chunk streaming path
+    (forced small chunks) and through every atomics variant must give the same histogram."""
+    import aindex_b200.capi as c
+    rng = np.random.default_rng(31)
+    data = _random_reads(rng, 13000, 150, b"ACGTacgt", n_rate=0.002)
+    want, wst = oracle.count13_direct(data)
+    perm = m13.perm13()
+    lib = c.lib()
+    monkeypatch.setenv("AIX_COUNT13_CHUNK", "65536")
+    monkeypatch.setenv("AIX_COUNT13_VARIANT", variant)
+    tf = np.zeros(1 << 26, dtype=np.uint64)
+    st = c.CountStats()
+    ctx.check(lib.aix_count13_begin(ctx.handle))
+    half = (data.size // 2 // 151) * 151
+    ctx.check(lib.aix_count13_add(ctx.handle, data[:half].ctypes.data, half, c.FMT_PLAIN))
+    ctx.check(lib.aix_count13_add(ctx.handle, data[half:].ctypes.data, data.size - half, c.FMT_PLAIN))
+    ctx.check(lib.aix_count13_finish(ctx.handle, m13._h, 0, 1 << 26, tf.ctypes.data, st))
+    ctx.check(lib.aix_count13_end(ctx.handle))
+    assert st.as_dict() == wst
+    assert np.array_equal(tf[perm.astype(np.int64)], want)
+    assert int(tf.sum()) == wst["valid"]
+
+
+def test_tf13_golden(capi, ctx, m13, g13):
+    tf = np.zeros(1 << 26, dtype=np.uint64)
+    tf[g13["plain_ids"]] = g13["plain_counts"]
+    ix = capi.Index13.upload(ctx, m13, tf)
+    q = _queries(g13["q_recs"], g13["q_lens"])
+    assert np.array_equal(ix.query(q, capi.Q_TF), g13["q_tf"])
+    ok = g13["q_ok"]
+    qok = [q[i] for i in ok]
+    assert np.array_equal(ix.query(qok, capi.Q_TOTAL), g13["q_total"])
+    assert np.array_equal(ix.query(qok, capi.Q_BOTH), g13["q_both"])
+    # positions index: compute_aindex13 (1 thread) output
+    indices, positions = ix.positions_build(g13["plain_data"])
+    assert np.array_equal(positions, g13["pos13_positions"])
+    assert hashlib.md5(indices.tobytes()).hexdigest() == str(g13["pos13_indices_md5"])
+
+
+def test_tf13_vs_oracle_odd_queries(capi, oracle, ctx, m13, g13):
+    tf = np.zeros(1 << 26, dtype=np.uint64)
+    tf[g13["plain_ids"]] = g13["plain_counts"]
+    ix = capi.Index13.upload(ctx, m13, tf)
+    oix = oracle.Index13(oracle.Mphf.load(oracle.PF13_PATH), tf)
+    rng = np.random.default_rng(41)
+    q = [rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), size=int(n)).tobytes()
+         for n in rng.choice([0, 5, 12, 13, 13, 13, 14, 16], size=1500)]
+    q += _queries(g13["q_recs"], g13["q_lens"])
+    recs, lens = oracle.pack_queries(q, stride=16)
+    for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH)):
+        assert np.array_equal(ix.query(q, mode), oix.batch(recs, lens, omode))
+    # coverage, k = 13 (aindex.py:314-322 over get_tf_value_13mer)
+    seq = g13["plain_data"][:3000].tobytes().replace(b"\n", b"")
+    for cutoff in (0, 2):
+        assert np.array_equal(ix.coverage(seq, cutoff=cutoff), oix.coverage(seq, cutoff))
+
+
+def test_all_4p13_query_is_perm(capi, ctx, m13):
+    """config 1: tf query of all 4^13 13-mers in numeric order == tf re-indexed by perm13."""
+    rng = np.random.default_rng(43)
+    tf = rng.integers(0, 1 << 40, size=1 << 26, dtype=np.uint64)
+    ix = capi.Index13.upload(ctx, m13, tf)
+    perm = m13.perm13().astype(np.int64)
+    block = 1 << 22
+    for start in (0, 17 * block // 4, (1 << 26) - block):
+        v = np.arange(start, start + block, dtype=np.uint64)
+        recs = ctx.decode(v, 13)
+        got = ix.query(recs, capi.Q_TF)
+        assert np.array_equal(got, tf[perm[start:start + block]].astype(np.uint32))
+
+
+# ---------------------------------------------------------------------------- coverage / positions
+def test_coverage23_golden(idx23, g23):
+    so, co = g23["cov_seq_off"], g23["cov_off"]
+    got = idx23.coverage(g23["cov_seq"], so, cutoff=0)
+    assert np.array_equal(got, g23["cov_val"])
+    for j in range(len(so) - 1):
+        one = idx23.coverage(g23["cov_seq"][so[j]:so[j + 1]], cutoff=3)
+        want = g23["cov_val"][co[j]:co[j + 1]]
+        assert np.array_equal(one, np.where(want >= 3, want, 0))
+
+
+def test_coverage23_vs_oracle_long(capi, oracle, idx23, oidx23, golden_dir):
+    rng = np.random.default_rng(51)
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    seqs, offs = [], [0]
+    for _ in range(40):
+        st = int(rng.integers(0, reads.size - 2000))
+        s = reads[st:st + int(rng.integers(1, 1500))].copy()
+        seqs.append(s)
+        offs.append(offs[-1] + s.size)
+    cat = np.concatenate(seqs)
+    got = idx23.coverage(cat, np.array(offs, dtype=np.int64), cutoff=2)
+    want = np.concatenate([oidx23.coverage(s, 2) for s in seqs])
+    assert np.array_equal(got, want)
+
+
+def test_positions23_golden(capi, ctx, idx23, g23, golden_dir):
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    indices, positions = idx23.positions_build(reads)
+    assert np.array_equal(indices, np.fromfile(os.path.join(golden_dir, "idx23.indices.bin"), dtype=np.uint64))
+    assert np.array_equal(positions, np.fromfile(os.path.join(golden_dir, "idx23.index.bin"), dtype=np.uint64))
+    pos = capi.Positions(ctx, indices, positions)
+    q = _queries(g23["recs"], g23["lens"])
+    qi = g23["pos_qidx"]
+    offs, vals = pos.query(idx23, [q[i] for i in qi], 23)
+    assert np.array_equal(offs, g23["pos_off"]) and np.array_equal(vals, g23["pos_val"])
+    # len(get_positions) == tf (test_aindex_functionality.py:376-380); absent / odd queries -> []
+    tfs = idx23.query([q[i] for i in qi])
+    assert np.array_equal(np.diff(offs).astype(np.uint32), tfs)
+    offs, vals = pos.query(idx23, [b"A" * 23, b"ACGT", b"N" * 23], 23)
+    assert vals.size == 0
+
+
+def test_positions23_overflow_and_underflow(capi, oracle, ctx, oidx23, golden_dir):
+    """tf larger / smaller than the true occurrence count: zero tail / first-tf-kept."""
+    rng = np.random.default_rng(61)
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    tf = oidx23.tf.copy()
+    sel = rng.random(tf.size) < 0.3
+    tf[sel] = np.maximum(1, tf[sel] // 2)
+    sel2 = rng.random(tf.size) < 0.2
+    tf[sel2] += 3
+    m = capi.Mphf.from_arrays(ctx, oidx23.mphf.n, oidx23.mphf.hash_domain, oidx23.mphf.seed, oidx23.mphf.words,
+                              oidx23.mphf.block_ranks)
+    ix = capi.Index23.upload(ctx, m, oidx23.checker, tf)
+    oix = oracle.Index23(oidx23.mphf, oidx23.checker, tf)
+    indices, positions = ix.positions_build(reads)
+    oi, op = oix.positions_build(reads)
+    assert np.array_equal(indices, oi) and np.array_equal(positions, op)
+
+
+# ---------------------------------------------------------------------------- size-independent properties
+def test_large_batch_properties(capi, ctx, idx23, oidx23):
+    """2 M queries through the chunked host pipeline: revcomp invariance, total == 2 x tf,
+    batch == concatenation of sub-batches."""
+    rng = np.random.default_rng(71)
+    n = 2_000_000
+    pick = rng.integers(0, oidx23.n, size=n)
+    km = ctx.decode(oidx23.checker[pick], 23)
+    miss = rng.random(n) < 0.5
+    km[miss] = rng.choice(ACGT, size=(int(miss.sum()), 23))
+    tf = idx23.query(km)
+    rcv = ctx.decode(ctx.revcomp(ctx.encode(km, 23), 23), 23)
+    assert np.array_equal(idx23.query(rcv), tf)
+    assert np.array_equal(tf[~miss], oidx23.tf[pick[~miss]])
+    assert np.array_equal(idx23.query(km, capi.Q_TOTAL), 2 * tf.astype(np.uint64))
+    parts = np.concatenate([idx23.query(km[i:i + 333_333]) for i in range(0, n, 333_333)])
+    assert np.array_equal(parts, tf)
