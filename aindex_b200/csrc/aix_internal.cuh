@@ -20,7 +20,8 @@ struct aix_mphf {
     aix::MphfDev dev() const {
         aix::MphfDev d;
         d.n = n; d.hash_domain = hash_domain; d.seed = seed;
-        d.magic = hash_domain ? (uint64_t)((((unsigned __int128)1) << 64) / hash_domain) : 0;
+        // floor(2^64 / d); for d == 1 the quotient does not fit: 2^64-1 still gives q in {q_true-1, q_true}
+        d.magic = hash_domain > 1 ? (uint64_t)((((unsigned __int128)1) << 64) / hash_domain) : ~0ULL;
         d.recs = recs_dev;
         return d;
     }

@@ -73,10 +73,14 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // base: 16-byte aligned; owned bytes are [own_begin, own_end) (own_begin multiple of 16).
 // Bytes before own_begin are lookback if own_begin > 0, otherwise the shard start (virtual
 // newline); bytes at or past own_end read as newline.
+// slice_shift/slice_id: multi-pass mode -- only k-mers with (kmer >> slice_shift) == slice_id are
+// counted in this launch, so the histogram slice being updated (4^13 * 4 B >> passes) stays
+// L2 resident; slice_shift == 32 counts everything.  Stats are accumulated by pass 0 only.
 template <bool kAggregate>
 __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
                                                           uint64_t own_end, uint32_t *__restrict__ hist,
-                                                          unsigned long long *__restrict__ stats) {
+                                                          unsigned long long *__restrict__ stats, uint32_t slice_shift,
+                                                          uint32_t slice_id) {
     const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
     const uint64_t pos = own_begin + t * 16;
     const unsigned lane = threadIdx.x & 31u;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__res
 #pragma unroll
         for (int s = 1; s <= 16; ++s) {
             uint32_t kmer = (uint32_t)(w.codes >> (2 * (16 - s))) & kMask26;
-            bool ok = (w.wvalid >> s) & 1u;
+            bool ok = ((w.wvalid >> s) & 1u) && (slice_shift >= 32u || (kmer >> slice_shift) == slice_id);
             if (kAggregate) {
                 // thread-local run-length merge (homopolymer / tandem runs), flushed below
                 if (ok && pend_c && kmer == pend_k) { ++pend_c; continue; }
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__res
         }
         if (kAggregate && pend_c) atomicAdd(hist + pend_k, pend_c);
     }
+    if (slice_shift < 32u && slice_id != 0u) return;
     n_win = warp_sum(n_win);
     n_valid = warp_sum(n_valid);
     n_seq = warp_sum(n_seq);
@@ -370,12 +375,22 @@ static int launch_count(aix_ctx *ctx, cudaStream_t st, const uint8_t *base, uint
     uint64_t threads = (own_end - own_begin + 15) / 16;
     unsigned grid = aix_grid(threads, kCntBlock);
     unsigned long long *stats = (unsigned long long *)ctx->c13_stats_dev;
-    switch (count_variant()) {
-        case 1: count13_kernel<true><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
-        case 2: count13_match_kernel<<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
-        default: count13_kernel<false><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats); break;
+    int passes_log2 = 0;
+    if (const char *e = getenv("AIX_COUNT13_PASSES_LOG2")) passes_log2 = atoi(e);
+    if (passes_log2 < 0) passes_log2 = 0;
+    if (passes_log2 > 6) passes_log2 = 6;
+    const int variant = count_variant();
+    if (variant == 2) {
+        count13_match_kernel<<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats);
+        AIX_LAUNCH_CHECK(ctx);
+        return AIX_OK;
     }
-    AIX_LAUNCH_CHECK(ctx);
+    const uint32_t shift = passes_log2 ? (uint32_t)(26 - passes_log2) : 32u;
+    for (uint32_t p = 0; p < (1u << passes_log2); ++p) {
+        if (variant == 1) count13_kernel<true><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats, shift, p);
+        else count13_kernel<false><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats, shift, p);
+        AIX_LAUNCH_CHECK(ctx);
+    }
     return AIX_OK;
 }
 

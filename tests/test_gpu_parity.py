@@ -196,7 +196,17 @@ def test_tf23_non_canonical_index_two_probe_path(capi, oracle, ctx, oidx23):
 
 
 # ---------------------------------------------------------------------------- MPHF build
-@pytest.mark.parametrize("n", [1, 2, 3, 17, 1000, 200_000])
+def test_mphf_build_two_keys_is_unbuildable(capi, ctx):
+    """n = 2 gives hash_domain 1 (mphf.hpp:27): both hyperedges are (0,1,2) for every seed, so the
+    reference's trial loop (mphf.hpp:47-51) never ends; here it is a clean error."""
+    with pytest.raises(capi.AixError) as e:
+        capi.Mphf.build(ctx, np.array([5, 9], dtype=np.uint64), 23)
+    assert e.value.code == -6
+    m = capi.Mphf.build(ctx, np.zeros(0, dtype=np.uint64), 23)
+    assert m.info["n"] == 0
+
+
+@pytest.mark.parametrize("n", [1, 3, 17, 1000, 200_000])
 def test_mphf_build_is_minimal_perfect(capi, oracle, ctx, n):
     rng = np.random.default_rng(100 + n)
     kmers = np.unique(rng.integers(0, 1 << 46, size=n + n // 8 + 4, dtype=np.uint64))[:n]
@@ -213,9 +223,11 @@ def test_mphf_build_is_minimal_perfect(capi, oracle, ctx, n):
     assert np.array_equal(np.sort(ids_gpu), np.arange(n, dtype=np.uint64))
     # the block ranks follow ranked_bitpair_vector.hpp:17-31
     nz = np.array([bin((int(w) | (int(w) >> 1)) & 0x5555555555555555).count("1") for w in words[:4096]], dtype=np.uint64)
+    nz = np.concatenate([nz, np.zeros((-nz.size) % 16, dtype=np.uint64)])
     blocks = min(ranks.size, nz.size // 16)
-    want = np.concatenate([[0], np.cumsum(nz.reshape(-1, 16)[:blocks].sum(axis=1))])[:blocks]
+    want = np.concatenate([[0], np.cumsum(nz.reshape(-1, 16).sum(axis=1))])[:blocks]
     assert np.array_equal(ranks[:blocks], want.astype(np.uint64))
+    assert int(nz.sum()) == n or words.size > 4096
 
 
 def test_index_build_pipeline_vs_bruteforce(capi, oracle, ctx):
