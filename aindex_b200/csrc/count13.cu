@@ -19,49 +19,52 @@ namespace aix {
 constexpr int kCntBlock = 256;
 constexpr uint32_t kMask26 = (1u << 26) - 1;
 
-// classify one byte: bit0-1 code, bit2 valid (ACGT, either case: std::toupper at
-// count_kmers13.cpp:118), bit3 newline
-__device__ __forceinline__ uint32_t classify(uint32_t c) {
-    uint32_t u = c & 0xDFu;
-    uint32_t valid = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
-    uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
-    return code | (valid << 2) | ((c == '\n') << 3);
+// ---- SIMD classification of 16 input bytes -------------------------------------------------
+// codes: 16 two-bit codes, byte 0 in bits 31:30 ... byte 15 in bits 1:0 (A0 C1 G2 T3 via
+//        ((c>>1)^(c>>2))&3, meaningful where the byte is valid)
+// masks: bit i      = byte i is an ACGT letter of either case (std::toupper, count_kmers13.cpp:118)
+//        bit 16 + i = byte i is '\n'
+struct Sum16 {
+    uint32_t codes;
+    uint32_t masks;
+};
+
+// bit 7 of every non-zero byte of x
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+// bits 7/15/23/31 -> bits 0/1/2/3
+__device__ __forceinline__ uint32_t gather_msb4(uint32_t x) { return ((x >> 7) * 0x01020408u) >> 24; }
+
+template <bool kNeedNl>
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &codes8, uint32_t &valid4, uint32_t &nl4) {
+    uint32_t c4 = ((w >> 1) ^ (w >> 2)) & 0x03030303u;  // letter code of every byte
+    codes8 = (c4 * 0x40100401u) >> 24;                   // c0<<6 | c1<<4 | c2<<2 | c3
+    uint32_t t = c4 | (c4 >> 4);
+    uint32_t sel = __byte_perm(t, 0u, 0x4420);           // nibble j = code of byte j
+    uint32_t expect = __byte_perm(0x54474341u, 0u, sel); // "ACGT"[code]: the only byte that is valid
+    valid4 = gather_msb4(nonzero_bytes(expect ^ (w & 0xDFDFDFDFu))) ^ 0xFu;
+    nl4 = kNeedNl ? (gather_msb4(nonzero_bytes(w ^ 0x0A0A0A0Au)) ^ 0xFu) : 0u;
 }
 
-struct Win16 {
-    uint64_t codes;   // 29 codes, position i at bits [2*(28-i)+1 : 2*(28-i)]; 0..12 lookback, 13..28 own
-    uint32_t wvalid;  // bit s (1..16): window starting at position s is 13 valid letters
-    uint32_t wline;   // bit s: window starting at s contains no newline
-    uint32_t nl;      // bit i: position i is a newline
-};
+template <bool kNeedNl>
+__device__ __forceinline__ Sum16 classify16(uint4 v) {
+    uint32_t c0, c1, c2, c3, v0, v1, v2, v3, n0, n1, n2, n3;
+    classify4<kNeedNl>(v.x, c0, v0, n0);
+    classify4<kNeedNl>(v.y, c1, v1, n1);
+    classify4<kNeedNl>(v.z, c2, v2, n2);
+    classify4<kNeedNl>(v.w, c3, v3, n3);
+    Sum16 s;
+    s.codes = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    s.masks = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12) | (n0 << 16) | (n1 << 20) | (n2 << 24) | (n3 << 28);
+    return s;
+}
 
 __device__ __forceinline__ uint32_t run13(uint32_t v) {  // bit i = v[i..i+12] all set
     uint32_t a1 = v & (v >> 1);
     uint32_t a2 = a1 & (a1 >> 2);
     uint32_t a3 = a2 & (a2 >> 4);
     return a3 & (a2 >> 8) & (v >> 12);
-}
-
-// prev = the 16 bytes before own (only the last 13 are used), both as little-endian uint4
-__device__ __forceinline__ Win16 make_windows(uint4 prev, uint4 own) {
-    uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, own.x, own.y, own.z, own.w};
-    uint64_t codes = 0;
-    uint32_t valid = 0, nl = 0;
-#pragma unroll
-    for (int b = 3; b < 32; ++b) {  // bytes 3..15 of prev = positions 0..12; own = 13..28
-        uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-        uint32_t k = classify(c);
-        int pos = b - 3;
-        codes |= (uint64_t)(k & 3u) << (2 * (28 - pos));
-        valid |= ((k >> 2) & 1u) << pos;
-        nl |= ((k >> 3) & 1u) << pos;
-    }
-    Win16 r;
-    r.codes = codes;
-    r.nl = nl;
-    r.wvalid = run13(valid) & 0x1FFFEu;
-    r.wline = run13(~nl & 0x1FFFFFFFu) & 0x1FFFEu;
-    return r;
 }
 
 __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
@@ -73,123 +76,91 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // base: 16-byte aligned; owned bytes are [own_begin, own_end) (own_begin multiple of 16).
 // Bytes before own_begin are lookback if own_begin > 0, otherwise the shard start (virtual
 // newline); bytes at or past own_end read as newline.
-// slice_shift/slice_id: multi-pass mode -- only k-mers with (kmer >> slice_shift) == slice_id are
-// counted in this launch, so the histogram slice being updated (4^13 * 4 B >> passes) stays
-// L2 resident; slice_shift == 32 counts everything.  Stats are accumulated by pass 0 only.
-template <bool kAggregate>
+//
+// Each thread classifies its own 16 bytes once (SIMD over 32-bit words) and receives the
+// summary of the previous 16 bytes from the neighbouring lane (shuffle), the neighbouring
+// warp (shared memory) or, for the first thread of a CTA, by classifying them itself.
+// Positions 0..12 = lookback bytes 3..15, positions 13..28 = own bytes; the window starting at
+// position s (1..16) ends on an own byte and is emitted by this thread.
+//
+// smask/sval: multi-pass mode -- only k-mers whose byte offset satisfies (off & smask) == sval
+// are counted in this launch, so the histogram slice being updated stays L2 resident
+// (smask = 0: single pass).  kStats: accumulate the count_kmers13 statistics (first pass only).
+// kVariant: 0 one RED per window, 1 thread-local run-length merge, 2 warp match_any merge.
+template <bool kStats, int kVariant>
 __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
                                                           uint64_t own_end, uint32_t *__restrict__ hist,
-                                                          unsigned long long *__restrict__ stats, uint32_t slice_shift,
-                                                          uint32_t slice_id) {
+                                                          unsigned long long *__restrict__ stats, uint32_t smask,
+                                                          uint32_t sval) {
+    __shared__ uint2 edge[kCntBlock / 32];
     const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
     const uint64_t pos = own_begin + t * 16;
-    const unsigned lane = threadIdx.x & 31u;
-    const uint4 nl4 = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-    uint4 own = nl4;
-    const bool active = pos < own_end;
-    if (active) {
-        own = __ldcs(reinterpret_cast<const uint4 *>(base + pos));
-        if (pos + 16 > own_end) {  // tail: bytes past the end become newlines
-            uint32_t w[4] = {own.x, own.y, own.z, own.w};
-            uint32_t keep = (uint32_t)(own_end - pos);
-#pragma unroll
-            for (int b = 0; b < 16; ++b)
-                if ((uint32_t)b >= keep) w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (0x0Au << (8 * (b & 3)));
-            own = make_uint4(w[0], w[1], w[2], w[3]);
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    Sum16 own;
+    own.codes = 0;
+    own.masks = 0xFFFF0000u;  // inactive: 16 newlines
+    if (pos < own_end) {
+        own = classify16<kStats>(__ldcs(reinterpret_cast<const uint4 *>(base + pos)));
+        if (pos + 16 > own_end) {  // tail: bytes past the end are newlines
+            uint32_t keep = (1u << (uint32_t)(own_end - pos)) - 1u;
+            own.masks = (own.masks & (keep | (keep << 16))) | ((~keep & 0xFFFFu) << 16);
         }
     }
-    // previous 16 bytes: neighbour lane, or a direct load at the warp boundary
-    uint4 prev;
-    prev.x = __shfl_up_sync(0xFFFFFFFFu, own.x, 1);
-    prev.y = __shfl_up_sync(0xFFFFFFFFu, own.y, 1);
-    prev.z = __shfl_up_sync(0xFFFFFFFFu, own.z, 1);
-    prev.w = __shfl_up_sync(0xFFFFFFFFu, own.w, 1);
+    Sum16 prev;
+    prev.codes = __shfl_up_sync(0xFFFFFFFFu, own.codes, 1);
+    prev.masks = __shfl_up_sync(0xFFFFFFFFu, own.masks, 1);
+    if (lane == 31) edge[wid] = make_uint2(own.codes, own.masks);
+    __syncthreads();
     if (lane == 0) {
-        if (pos >= 16 && pos - 16 < own_end) prev = __ldg(reinterpret_cast<const uint4 *>(base + pos - 16));
-        else prev = nl4;
-    }
-    uint64_t n_win = 0, n_valid = 0, n_seq = 0;
-    if (active) {
-        Win16 w = make_windows(prev, own);
-        n_win = __popc(w.wline);
-        n_valid = __popc(w.wvalid);
-        n_seq = __popc((w.nl << 1) & w.wline);  // first window of a line with >= 13 characters
-        uint32_t pend_k = 0, pend_c = 0;
-#pragma unroll
-        for (int s = 1; s <= 16; ++s) {
-            uint32_t kmer = (uint32_t)(w.codes >> (2 * (16 - s))) & kMask26;
-            bool ok = ((w.wvalid >> s) & 1u) && (slice_shift >= 32u || (kmer >> slice_shift) == slice_id);
-            if (kAggregate) {
-                // thread-local run-length merge (homopolymer / tandem runs), flushed below
-                if (ok && pend_c && kmer == pend_k) { ++pend_c; continue; }
-                if (pend_c) atomicAdd(hist + pend_k, pend_c);
-                pend_c = ok ? 1u : 0u;
-                pend_k = kmer;
-            } else {
-                if (ok) atomicAdd(hist + kmer, 1u);
-            }
-        }
-        if (kAggregate && pend_c) atomicAdd(hist + pend_k, pend_c);
-    }
-    if (slice_shift < 32u && slice_id != 0u) return;
-    n_win = warp_sum(n_win);
-    n_valid = warp_sum(n_valid);
-    n_seq = warp_sum(n_seq);
-    if (lane == 0 && n_win) {
-        atomicAdd(stats + 0, (unsigned long long)n_seq);
-        atomicAdd(stats + 1, (unsigned long long)n_win);
-        atomicAdd(stats + 2, (unsigned long long)n_valid);
-    }
-}
-
-// warp-aggregated variant: duplicates inside a warp are merged with match_any before they
-// reach L2 (pays off on low-complexity / highly repetitive input)
-__global__ void __launch_bounds__(kCntBlock) count13_match_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
-                                                                uint64_t own_end, uint32_t *__restrict__ hist,
-                                                                unsigned long long *__restrict__ stats) {
-    const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
-    const uint64_t pos = own_begin + t * 16;
-    const unsigned lane = threadIdx.x & 31u;
-    const uint4 nl4 = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-    uint4 own = nl4;
-    const bool active = pos < own_end;
-    if (active) {
-        own = __ldcs(reinterpret_cast<const uint4 *>(base + pos));
-        if (pos + 16 > own_end) {
-            uint32_t w[4] = {own.x, own.y, own.z, own.w};
-            uint32_t keep = (uint32_t)(own_end - pos);
-#pragma unroll
-            for (int b = 0; b < 16; ++b)
-                if ((uint32_t)b >= keep) w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (0x0Au << (8 * (b & 3)));
-            own = make_uint4(w[0], w[1], w[2], w[3]);
+        if (wid > 0) {
+            uint2 e = edge[wid - 1];
+            prev.codes = e.x;
+            prev.masks = e.y;
+        } else if (pos >= 16 && pos - 16 < own_end) {  // CTA boundary: the 16 bytes before are whole
+            prev = classify16<kStats>(__ldg(reinterpret_cast<const uint4 *>(base + pos - 16)));
+        } else {
+            prev.codes = 0;
+            prev.masks = 0xFFFF0000u;  // shard start = virtual newline
         }
     }
-    uint4 prev;
-    prev.x = __shfl_up_sync(0xFFFFFFFFu, own.x, 1);
-    prev.y = __shfl_up_sync(0xFFFFFFFFu, own.y, 1);
-    prev.z = __shfl_up_sync(0xFFFFFFFFu, own.z, 1);
-    prev.w = __shfl_up_sync(0xFFFFFFFFu, own.w, 1);
-    if (lane == 0) {
-        if (pos >= 16 && pos - 16 < own_end) prev = __ldg(reinterpret_cast<const uint4 *>(base + pos - 16));
-        else prev = nl4;
-    }
-    Win16 w = make_windows(prev, own);  // inactive threads: all newlines -> no windows
-    uint64_t n_win = __popc(w.wline), n_valid = __popc(w.wvalid), n_seq = __popc((w.nl << 1) & w.wline);
+    const uint32_t valid29 = ((prev.masks & 0xFFFFu) >> 3) | ((own.masks & 0xFFFFu) << 13);
+    const uint32_t wvalid = run13(valid29) & 0x1FFFEu;
+    // byte offsets into the histogram: (prev:own codes) << 2, window s at bits [2(16-s)+2 ...]
+    const uint32_t lo2 = own.codes << 2, hi2 = __funnelshift_l(own.codes, prev.codes, 2);
+    constexpr uint32_t kOffMask = kMask26 << 2;
+    uint32_t pend_off = 0, pend_c = 0;
 #pragma unroll
     for (int s = 1; s <= 16; ++s) {
-        uint32_t kmer = (uint32_t)(w.codes >> (2 * (16 - s))) & kMask26;
-        bool ok = (w.wvalid >> s) & 1u;
-        uint32_t key = ok ? kmer : 0xFFFFFFFFu;
-        unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-        if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + kmer, (uint32_t)__popc(peers));
+        const uint32_t off = __funnelshift_r(lo2, hi2, 2 * (16 - s)) & kOffMask;
+        const bool ok = ((wvalid >> s) & 1u) && ((off & smask) == sval);
+        if (kVariant == 0) {
+            if (ok) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
+        } else if (kVariant == 1) {
+            if (ok && pend_c && off == pend_off) { ++pend_c; continue; }
+            if (pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
+            pend_c = ok ? 1u : 0u;
+            pend_off = off;
+        } else {
+            const uint32_t key = ok ? off : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+            if (ok && lane == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), (uint32_t)__popc(peers));
+        }
     }
-    n_win = warp_sum(n_win);
-    n_valid = warp_sum(n_valid);
-    n_seq = warp_sum(n_seq);
-    if (lane == 0 && n_win) {
-        atomicAdd(stats + 0, (unsigned long long)n_seq);
-        atomicAdd(stats + 1, (unsigned long long)n_win);
-        atomicAdd(stats + 2, (unsigned long long)n_valid);
+    if (kVariant == 1 && pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
+    if (kStats) {
+        const uint32_t nl29 = (prev.masks >> 19) | ((own.masks >> 16) << 13);
+        const uint32_t wline = run13(~nl29 & 0x1FFFFFFFu) & 0x1FFFEu;
+        uint64_t n_win = __popc(wline), n_valid = __popc(wvalid);
+        uint64_t n_seq = __popc((nl29 << 1) & wline);  // first window of a line with >= 13 characters
+        n_win = warp_sum(n_win);
+        n_valid = warp_sum(n_valid);
+        n_seq = warp_sum(n_seq);
+        if (lane == 0 && n_win) {
+            atomicAdd(stats + 0, (unsigned long long)n_seq);
+            atomicAdd(stats + 1, (unsigned long long)n_win);
+            atomicAdd(stats + 2, (unsigned long long)n_valid);
+        }
     }
 }
 
@@ -375,20 +346,28 @@ static int launch_count(aix_ctx *ctx, cudaStream_t st, const uint8_t *base, uint
     uint64_t threads = (own_end - own_begin + 15) / 16;
     unsigned grid = aix_grid(threads, kCntBlock);
     unsigned long long *stats = (unsigned long long *)ctx->c13_stats_dev;
-    int passes_log2 = 0;
+    // 4 passes over 64 MiB histogram slices: random REDs run at 210 G/s while the slice is L2
+    // resident, against 32 G/s on the whole 256 MiB table (profiles/atomic_roofline.txt)
+    int passes_log2 = 2;
     if (const char *e = getenv("AIX_COUNT13_PASSES_LOG2")) passes_log2 = atoi(e);
     if (passes_log2 < 0) passes_log2 = 0;
     if (passes_log2 > 6) passes_log2 = 6;
     const int variant = count_variant();
-    if (variant == 2) {
-        count13_match_kernel<<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats);
-        AIX_LAUNCH_CHECK(ctx);
-        return AIX_OK;
-    }
-    const uint32_t shift = passes_log2 ? (uint32_t)(26 - passes_log2) : 32u;
+    const uint32_t smask = passes_log2 ? (((1u << passes_log2) - 1u) << (28 - passes_log2)) : 0u;
     for (uint32_t p = 0; p < (1u << passes_log2); ++p) {
-        if (variant == 1) count13_kernel<true><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats, shift, p);
-        else count13_kernel<false><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats, shift, p);
+        const uint32_t sval = passes_log2 ? (p << (28 - passes_log2)) : 0u;
+#define AIX_C13_LAUNCH(STATS, VAR) \
+    count13_kernel<STATS, VAR><<<grid, kCntBlock, 0, st>>>(base, own_begin, own_end, ctx->c13_hist32, stats, smask, sval)
+        if (p == 0) {
+            if (variant == 1) AIX_C13_LAUNCH(true, 1);
+            else if (variant == 2) AIX_C13_LAUNCH(true, 2);
+            else AIX_C13_LAUNCH(true, 0);
+        } else {
+            if (variant == 1) AIX_C13_LAUNCH(false, 1);
+            else if (variant == 2) AIX_C13_LAUNCH(false, 2);
+            else AIX_C13_LAUNCH(false, 0);
+        }
+#undef AIX_C13_LAUNCH
         AIX_LAUNCH_CHECK(ctx);
     }
     return AIX_OK;
