@@ -38,7 +38,13 @@ __global__ void gather16_kernel(const uint4 *__restrict__ idx, uint64_t n4, cons
     out[i] = a.x ^ b.y ^ c.z ^ d.w;
 }
 
-int main() {
+int main(int argc, char **argv) {
+    if (argc > 1) {  // optional: L2 fetch granularity in bytes (32 / 64 / 128)
+        CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1])));
+    }
+    size_t gran = 0;
+    CK(cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity));
+    printf("cudaLimitMaxL2FetchGranularity=%zu\n", gran);
     const uint64_t n = 1ull << 29;  // 512 Mi keys = 2 GiB of keys per launch
     uint32_t *keys, *table, *out;
     CK(cudaMalloc(&keys, n * 4));

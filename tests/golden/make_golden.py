@@ -14,6 +14,8 @@ the reference pybind11 module -- never by the oracle restatement or the CUDA pat
   golden13.npz   count_kmers13 output (non-zero id/count pairs + md5 of the 512 MiB
                  file + stats), 13-mer query answers, compute_aindex13 positions.
 
+  golden_reads.npz + idx23.ridx   read access / rid / start answers (python tests/golden/make_golden.py reads)
+
 Usage: python tests/golden/make_golden.py
 """
 import hashlib
@@ -319,7 +321,44 @@ def golden_kat():
     np.savez_compressed(os.path.join(HERE, "golden_kat.npz"), **out)
 
 
+def golden_reads():
+    """Read access / position -> read mapping of the reference module on the committed idx23
+    fixture (python_wrapper.cpp:261-322, :666-698, :757-789).  Writes idx23.ridx (the
+    compute_reads layout: rid, start, end-exclusive) and golden_reads.npz."""
+    ref = O.ref_module()
+    reads = open(os.path.join(HERE, "idx23.reads"), "rb").read()
+    with open(os.path.join(HERE, "idx23.ridx"), "w") as f:
+        pos = 0
+        for rid, line in enumerate(reads.split(b"\n")[:-1]):
+            f.write(f"{rid}\t{pos}\t{pos + len(line)}\n")
+            pos += len(line) + 1
+    w = ref.AindexWrapper()
+    prefix = os.path.join(HERE, "idx23")
+    w.load_from_prefix_23mer(prefix, prefix + ".reads")
+    w.load_aindex_from_prefix_23mer(prefix, 100000)
+    rng = np.random.default_rng(77)
+    n_reads = int(w.n_reads)
+    starts = np.cumsum([0] + [len(l) + 1 for l in reads.split(b"\n")[:-1]])
+    probe = sorted(set(int(x) for x in rng.integers(0, len(reads), size=300)) |
+                   set(int(s + d) for s in starts[:40] for d in (-2, -1, 0, 1) if 0 <= s + d < len(reads)))
+    out = {"pos": np.array(probe, dtype=np.uint64),
+           "rid": np.array([w.get_rid(p) for p in probe], dtype=np.uint64),
+           "start": np.array([w.get_start(p) for p in probe], dtype=np.uint64),
+           "n_reads": np.array([n_reads], dtype=np.uint64),
+           "reads_size": np.array([w.reads_size], dtype=np.uint64)}
+    rids = [0, 1, 2, 7, n_reads - 1, n_reads, n_reads + 5]
+    out["read_rid"] = np.array(rids, dtype=np.uint64)
+    out["read_str"] = np.array([w.get_read_by_rid(r).encode() for r in rids])
+    spans = [(0, 30, False), (5, 40, True), (100, 100, False), (200, 150, False), (len(reads) - 10, len(reads) - 2, True)]
+    out["span"] = np.array([(a, b, int(c)) for a, b, c in spans], dtype=np.int64)
+    out["span_str"] = np.array([w.get_read(a, b, c).encode() for a, b, c in spans])
+    np.savez_compressed(os.path.join(HERE, "golden_reads.npz"), **out)
+    print(f"golden_reads: n_reads={n_reads} probes={len(probe)}")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "reads":
+        return golden_reads()
     if not os.path.isdir(BIN):
         raise SystemExit("oracle/_ref missing: run oracle/build_ref.sh in the build container")
     ref = O.ref_module()
@@ -329,6 +368,7 @@ def main():
         golden23(rng, ref, genome, reads, kmers, counts, prefix)
         golden13(rng, ref, tmp)
     golden_kat()
+    golden_reads()
 
 
 if __name__ == "__main__":
