@@ -1,0 +1,163 @@
+"""Sharding and the one collective of the hot path, for one-process-per-GPU runs.
+
+The path shards naturally:
+  * tf / coverage / position queries: index replicated on every GPU, queries split evenly,
+    results concatenated -- no data-path collective;
+  * 13-mer counting: reads split into contiguous byte ranges cut at line (record) boundaries,
+    every GPU builds a full direct-address 4^13 histogram, then ONE exchange step: an NCCL
+    reduce-scatter (sum) over k-mer ranges; rank r owns [r, r+1) * 4^13 / world.
+
+Everything here is host logic on torch.distributed process groups: it runs on NCCL with the
+device histogram exposed by libaindex_cuda (aix_count13_hist_dev) and on gloo with CPU tensors
+(tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+TOTAL_13MERS = 1 << 26
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of n items for `rank` (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def kmer_range(rank: int, world: int) -> Tuple[int, int]:
+    """k-mer value range of the 4^13 histogram owned by `rank` after the reduce-scatter."""
+    if TOTAL_13MERS % world:
+        raise ValueError("world size must divide 4^13 (use 1, 2, 4, 8, ...)")
+    step = TOTAL_13MERS // world
+    return rank * step, (rank + 1) * step
+
+
+def shard_reads(data: np.ndarray, world: int, lines_per_record: int = 1) -> List[Tuple[int, int]]:
+    """Byte ranges [begin, end) of a reads buffer, one per rank, cut right after a '\\n' that
+    ends a record (plain text: every line; FASTQ: every 4th line).  The ranges are disjoint,
+    cover the buffer, and every range starts at a record start, so per-shard k-mer counting
+    sees exactly the windows of the whole file (no window spans a newline)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    n = int(data.size)
+    cuts = [0]
+    if world > 1 and n:
+        if lines_per_record == 1:
+            for r in range(1, world):
+                target = max(cuts[-1], (n * r) // world)
+                # next newline at or after target-1 ends a line; cut after it
+                nl = np.flatnonzero(data[max(target - 1, 0):min(n, target + (1 << 20))] == 10)
+                while nl.size == 0 and target < n:  # very long line: widen the search
+                    target2 = min(n, target + (1 << 20))
+                    nl = np.flatnonzero(data[max(target - 1, 0):min(n, target2 + (1 << 24))] == 10)
+                    if target2 >= n:
+                        break
+                cut = max(target - 1, 0) + int(nl[0]) + 1 if nl.size else n
+                cuts.append(min(max(cut, cuts[-1]), n))
+        else:
+            nl_pos = np.flatnonzero(data == 10)
+            rec_ends = nl_pos[lines_per_record - 1::lines_per_record] + 1  # byte after each record
+            for r in range(1, world):
+                target = (n * r) // world
+                i = int(np.searchsorted(rec_ends, target, side="left"))
+                cut = int(rec_ends[i]) if i < rec_ends.size else n
+                cuts.append(min(max(cut, cuts[-1]), n))
+    while len(cuts) < world:
+        cuts.append(n)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def reduce_scatter_hist(hist, group=None):
+    """Sum the per-rank direct-address histograms; return this rank's k-mer slice.
+
+    hist: int64 tensor [4^13] (a view of the library's device buffer on NCCL, a CPU tensor on gloo).
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return hist
+    lo, hi = kmer_range(rank, world)
+    out = torch.empty(hi - lo, dtype=hist.dtype, device=hist.device)
+    try:
+        dist.reduce_scatter_tensor(out, hist, op=dist.ReduceOp.SUM, group=group)
+    except (RuntimeError, NotImplementedError):
+        # backends without reduce-scatter (gloo): all-reduce a copy, keep the own slice
+        tmp = hist.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(tmp[lo:hi])
+    return out
+
+
+def sum_to_rank0(t, group=None):
+    """Element-wise sum of a tensor onto rank 0 (the scattered MPHF-order partial results)."""
+    import torch.distributed as dist
+    if dist.get_world_size(group) > 1:
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def gather_concat(local: np.ndarray, group=None) -> np.ndarray:
+    """Concatenate per-rank result arrays (queries were split with shard_range) on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    parts = [None] * world
+    dist.all_gather_object(parts, np.ascontiguousarray(local), group=group)
+    return np.concatenate(parts)
+
+
+def count13_distributed(ctx, mphf, shard: np.ndarray, fmt: int, group=None):
+    """13-mer counting of one rank's shard + reduce-scatter + MPHF permutation.
+
+    Returns (tf uint64[4^13] in .tf.bin order on rank 0 else None, merged stats dict)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    lib = capi.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shard = np.ascontiguousarray(shard, dtype=np.uint8).reshape(-1)
+    ctx.check(lib.aix_count13_begin(ctx.handle))
+    ctx.check(lib.aix_count13_add(ctx.handle, shard.ctypes.data, shard.size, fmt))
+    ctx.check(lib.aix_count13_flush(ctx.handle))
+    st = capi.CountStats()
+    ctx.check(lib.aix_count13_stats(ctx.handle, st))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    hist = wrap_device_i64(lib.aix_count13_hist_dev(ctx.handle), TOTAL_13MERS, dev)
+    tf_dev = torch.zeros(TOTAL_13MERS, dtype=torch.int64, device=dev)
+    with torch.cuda.stream(stream):
+        mine = reduce_scatter_hist(hist, group)
+        lo, hi = kmer_range(rank, world)
+        if world > 1:
+            hist[lo:hi].copy_(mine)  # the library permutes out of its own buffer
+        ctx.check(lib.aix_count13_finish_dev(ctx.handle, mphf._h, lo, hi, tf_dev.data_ptr()))
+        sum_to_rank0(tf_dev, group)
+        stats = torch.tensor([st.sequences, st.windows, st.valid, st.invalid], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(stats, group=group)
+    stream.synchronize()
+    ctx.check(lib.aix_count13_end(ctx.handle))
+    keys = ("sequences", "windows", "valid", "invalid")
+    merged = dict(zip(keys, (int(x) for x in stats.cpu())))
+    return (tf_dev.cpu().numpy().view(np.uint64) if rank == 0 else None), merged
+
+
+def wrap_device_i64(ptr: int, n: int, dev):
+    """torch int64 view of a device buffer owned by libaindex_cuda (no copy)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device=dev)

@@ -1,0 +1,56 @@
+"""Run under torchrun (one rank per GPU): distributed 13-mer counting (shard -> count ->
+NCCL reduce-scatter -> permute -> sum to rank 0) must equal the single-GPU result bit for bit,
+and sharded 23-mer queries must concatenate to the single-GPU answers."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from aindex_b200 import capi, dist as D  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    g = os.path.join(ROOT, "tests", "golden")
+    ix = capi.Index23.load_prefix(ctx, os.path.join(g, "idx23"))
+    rng = np.random.default_rng(5)
+    reads = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=(40000, 101), p=[.2475, .2475, .2475, .2475, .01])
+    reads[:, 100] = 10
+    data = reads.reshape(-1)
+    # the 13-mer MPHF: the reference-built one when present, else built on the GPU (identical on
+    # every rank: same keys, same seed sequence)
+    pf13 = os.path.join(ROOT, "oracle", "_ref", "data", "all_13mers.pf")
+    m13 = capi.Mphf.load(ctx, pf13) if os.path.exists(pf13) else capi.Mphf.build(ctx, np.arange(1 << 26, dtype=np.uint64), 13)
+    b, e = D.shard_reads(data, world)[rank]
+    tf, st = D.count13_distributed(ctx, m13, data[b:e], capi.FMT_PLAIN)
+    ok = True
+    if rank == 0:
+        want, wst = ctx.count13(m13, data, capi.FMT_PLAIN)
+        ok = bool(np.array_equal(tf, want)) and st == wst
+        print(f"count13 x{world}: equal={ok} valid={st['valid']} md5={hashlib.md5(tf.tobytes()).hexdigest()}")
+    # sharded queries
+    q = ctx.decode(np.fromfile(os.path.join(g, "idx23.kmers.bin"), dtype=np.uint64)[:5000], 23)
+    q[::3] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(len(q[::3]), 23))
+    qb, qe = D.shard_range(len(q), rank, world)
+    got = D.gather_concat(ix.query(q[qb:qe]))
+    ok = ok and bool(np.array_equal(got, ix.query(q)))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_OK" if int(flag.item()) else "MULTI_GPU_FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

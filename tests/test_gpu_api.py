@@ -237,3 +237,14 @@ def test_build_index_from_reads_roundtrip(cpp, golden_dir, tmp_path, oracle):
     assert np.array_equal(mine.batch(km), ref.batch(km))
     w.load_from_prefix_23mer(prefix)
     assert w.get_tf_values(km).tolist() == ref.batch(km).tolist()
+
+
+def test_multi_gpu_count_and_queries():
+    """2 ranks on 2 GPUs (skipped on a single-GPU box): NCCL reduce-scatter path == single GPU."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
