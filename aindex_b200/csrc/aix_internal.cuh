@@ -32,9 +32,10 @@ struct aix_index23 {
     int canonical_only = 0;
     const aix_mphf *mphf = nullptr;
     uint4 *recs_dev = nullptr;  // {checker lo, checker hi, tf, 0}
+    uint8_t *fp_dev = nullptr;  // fingerprint tier (may be null)
     aix::Index23Dev dev() const {
         aix::Index23Dev d;
-        d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev;
+        d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev; d.fp = fp_dev;
         return d;
     }
 };
@@ -68,7 +69,7 @@ struct aix_ctx {
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
     uint64_t *c13_hist64 = nullptr;     // u64[4^13]
-    uint64_t *c13_stats_dev = nullptr;  // u64[4]: sequences, windows, valid, (unused)
+    uint64_t *c13_stats_dev = nullptr;  // statistics slots, layout in count13.cu (kStatBase)
     uint64_t c13_pending_windows = 0;   // upper bound of increments not yet flushed
     bool c13_active = false;
     aix_count_stats c13_range_invalid = {0, 0, 0, 0};

@@ -18,6 +18,9 @@ namespace aix {
 
 constexpr int kCntBlock = 256;
 constexpr uint32_t kMask26 = (1u << 26) - 1;
+// statistics buffer (u64): [3] out-of-range ids, [4] FASTQ line counter, [kStatBase + 3*slot + j] =
+// sequences / windows / valid of slot `slot` (summed on the host in aix_count13_stats)
+constexpr uint32_t kStatBase = 8, kStatSlots = 64, kStatWords = kStatBase + 3 * kStatSlots;
 
 // ---- SIMD classification of 16 input bytes -------------------------------------------------
 // codes: 16 two-bit codes, byte 0 in bits 31:30 ... byte 15 in bits 1:0 (A0 C1 G2 T3 via
@@ -149,17 +152,31 @@ __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__res
     }
     if (kVariant == 1 && pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
     if (kStats) {
+        // count_kmers13 statistics: per thread <= 16 of each kind, so one packed 32-bit REDUX per
+        // warp, one shared-memory word per warp and three global atomics per CTA on one of
+        // kStatSlots slot triples (every warp hitting the same three addresses serialises in L2
+        // and made this pass 4.6x slower than the others: profiles/r01_count13_ncu.txt)
+        __shared__ uint32_t wstat[kCntBlock / 32];
         const uint32_t nl29 = (prev.masks >> 19) | ((own.masks >> 16) << 13);
         const uint32_t wline = run13(~nl29 & 0x1FFFFFFFu) & 0x1FFFEu;
-        uint64_t n_win = __popc(wline), n_valid = __popc(wvalid);
-        uint64_t n_seq = __popc((nl29 << 1) & wline);  // first window of a line with >= 13 characters
-        n_win = warp_sum(n_win);
-        n_valid = warp_sum(n_valid);
-        n_seq = warp_sum(n_seq);
-        if (lane == 0 && n_win) {
-            atomicAdd(stats + 0, (unsigned long long)n_seq);
-            atomicAdd(stats + 1, (unsigned long long)n_win);
-            atomicAdd(stats + 2, (unsigned long long)n_valid);
+        const uint32_t n_win = __popc(wline), n_valid = __popc(wvalid);
+        const uint32_t n_seq = __popc((nl29 << 1) & wline);  // first window of a line with >= 13 characters
+        const uint32_t packed = __reduce_add_sync(0xFFFFFFFFu, (n_seq << 20) | (n_win << 10) | n_valid);
+        if (lane == 0) wstat[wid] = packed;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t s_seq = 0, s_win = 0, s_valid = 0;
+#pragma unroll
+            for (int w = 0; w < kCntBlock / 32; ++w) {
+                const uint32_t x = wstat[w];
+                s_seq += x >> 20; s_win += (x >> 10) & 0x3FFu; s_valid += x & 0x3FFu;
+            }
+            if (s_win) {
+                unsigned long long *slot = stats + kStatBase + 3u * (blockIdx.x & (kStatSlots - 1u));
+                atomicAdd(slot + 0, (unsigned long long)s_seq);
+                atomicAdd(slot + 1, (unsigned long long)s_win);
+                atomicAdd(slot + 2, (unsigned long long)s_valid);
+            }
         }
     }
 }
@@ -319,7 +336,7 @@ static int c13_alloc(aix_ctx *ctx) {
     if (!ctx->c13_hist32) {
         cudaError_t e = cudaMalloc(&ctx->c13_hist32, AIX_TOTAL_13MERS * 4);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->c13_hist64, AIX_TOTAL_13MERS * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->c13_stats_dev, 8 * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->c13_stats_dev, kStatWords * 8);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return ctx->fail(AIX_ERR_NOMEM, "count13 buffers: %s", cudaGetErrorString(e));
@@ -530,7 +547,7 @@ int aix_count13_begin(aix_ctx *ctx) {
     AIX_TRY(c13_alloc(ctx));
     AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist32, 0, AIX_TOTAL_13MERS * 4, ctx->stream));
     AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist64, 0, AIX_TOTAL_13MERS * 8, ctx->stream));
-    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_stats_dev, 0, 8 * 8, ctx->stream));
+    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_stats_dev, 0, kStatWords * 8, ctx->stream));
     ctx->c13_pending_windows = 0;
     ctx->c13_active = true;
     return AIX_OK;
@@ -554,9 +571,11 @@ uint64_t *aix_count13_hist_dev(aix_ctx *ctx) { return ctx ? ctx->c13_hist64 : nu
 
 int aix_count13_stats(aix_ctx *ctx, aix_count_stats *stats) {
     if (!ctx || !stats || !ctx->c13_active) return AIX_ERR_ARG;
-    uint64_t h[4];
-    AIX_CUDA(ctx, cudaMemcpyAsync(h, ctx->c13_stats_dev, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t raw[kStatWords], h[3] = {0, 0, 0};
+    AIX_CUDA(ctx, cudaMemcpyAsync(raw, ctx->c13_stats_dev, sizeof raw, cudaMemcpyDeviceToHost, ctx->stream));
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < kStatSlots; ++s)
+        for (int j = 0; j < 3; ++j) h[j] += raw[kStatBase + 3 * s + j];
     stats->sequences = h[0];
     stats->windows = h[1];
     stats->valid = h[2];

@@ -32,7 +32,17 @@ struct Index23Dev {
     uint64_t n;
     int canonical_only;
     const uint4 *recs;  // recs[h] = { checker lo, checker hi, tf, 0 }: one sector per probe
+    // Optional L2-resident filter tier: fp[h] = fingerprint8(checker[h]).  A probe whose
+    // fingerprint differs cannot verify, so it never touches the HBM record: on miss-dominated
+    // batches (the reference's own stress workload) 255/256 of the random HBM probes disappear.
+    // Exact: fp mismatch => checker mismatch; a match is always confirmed on the full record.
+    const uint8_t *fp;  // nullptr = tier disabled (index too large to keep n bytes in L2)
 };
+
+__device__ __host__ __forceinline__ uint32_t fingerprint8(uint64_t kmer) {
+    uint32_t x = (uint32_t)kmer ^ (uint32_t)(kmer >> 23);
+    return (x ^ (x >> 9)) & 0xFFu;
+}
 
 // ---- cache-policy loads ---------------------------------------------------------------
 // The MPHF records (0.46 B/key, ~31 MB for 50 M keys) are hit three times per query and must
@@ -214,6 +224,11 @@ __device__ __forceinline__ uint64_t mphf_lookup13(const MphfDev &m, uint32_t rc_
 // checker/tf probe: returns true and *tf when slot h holds `kmer`
 __device__ __forceinline__ bool probe23(const Index23Dev &ix, uint64_t h, uint64_t kmer, uint32_t &tf) {
     if (h >= ix.n) return false;
+    if (ix.fp != nullptr) {
+        uint32_t f;
+        asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(ix.fp + h), "l"(l2_policy_evict_last()));
+        if (f != fingerprint8(kmer)) return false;
+    }
     uint4 r = ld_evict_first_u32x4(&ix.recs[h]);
     uint64_t chk = ((uint64_t)r.y << 32) | r.x;
     tf = r.z;

@@ -97,11 +97,12 @@ __global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__re
 
 // ---- index upload helpers ----------------------------------------------------------------
 __global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const uint32_t *__restrict__ tf, uint64_t n,
-                                    uint4 *__restrict__ recs, int *__restrict__ non_canonical) {
+                                    uint4 *__restrict__ recs, uint8_t *__restrict__ fp, int *__restrict__ non_canonical) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t c = checker[i];
     recs[i] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), tf[i], 0u);
+    if (fp) fp[i] = (uint8_t)fingerprint8(c);
     if ((c >> 46) != 0 || c > revcomp23(c)) *non_canonical = 1;
 }
 
@@ -262,10 +263,19 @@ int aix_index23_upload_dev(aix_ctx *ctx, const aix_mphf *m, const uint64_t *chec
         aix_index23_destroy(ctx, ix);
         return ctx->fail(AIX_ERR_NOMEM, "index23 upload: %s", cudaGetErrorString(e));
     }
+    // fingerprint tier: n bytes that must stay in L2 next to the MPHF records (16 B per 32 nodes)
+    uint64_t fp_budget = 96ull << 20;
+    if (const char *e = getenv("AIX_FP_TIER_MAX_BYTES")) fp_budget = strtoull(e, nullptr, 10);
+    if (n && n + m->n_words * 16 <= fp_budget) {
+        if (cudaMalloc(&ix->fp_dev, n) != cudaSuccess) {
+            cudaGetLastError();
+            ix->fp_dev = nullptr;
+        }
+    }
     int flag = 0;
     cudaMemsetAsync(flag_dev, 0, sizeof(int), ctx->stream);
     if (n) {
-        index23_pack_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(checker_dev, tf_dev, n, ix->recs_dev, flag_dev);
+        index23_pack_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(checker_dev, tf_dev, n, ix->recs_dev, ix->fp_dev, flag_dev);
         ctx->launches++;
     }
     cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -325,6 +335,7 @@ void aix_index23_destroy(aix_ctx *ctx, aix_index23 *ix) {
     if (!ix) return;
     if (ctx) cudaSetDevice(ctx->device);
     if (ix->recs_dev) cudaFree(ix->recs_dev);
+    if (ix->fp_dev) cudaFree(ix->fp_dev);
     delete ix;
 }
 

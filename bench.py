@@ -97,6 +97,27 @@ def make_queries(torch, dev, n, seed):
     return out
 
 
+def make_hit_queries(torch, dev, reads, n, seed):
+    """Q2 half: 23-byte substrings of the reads at random offsets, random strand."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n_reads, width = reads.shape
+    out = torch.empty((n, 23), device=dev, dtype=torch.uint8)
+    ar = torch.arange(23, device=dev, dtype=torch.int64)
+    comp = torch.zeros(256, device=dev, dtype=torch.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    chunk = 10_000_000
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        r = torch.randint(0, n_reads, (e - s,), generator=g, device=dev, dtype=torch.int64)
+        o = torch.randint(0, width - 1 - 23 + 1, (e - s,), generator=g, device=dev, dtype=torch.int64)
+        sub = reads.reshape(-1)[(r * width + o)[:, None] + ar[None, :]]
+        flip = torch.rand((e - s,), generator=g, device=dev) < 0.5
+        out[s:e] = torch.where(flip[:, None], comp[sub.long()].flip(1), sub)
+    return out
+
+
 def build_index(torch, capi, ctx, reads):
     """reads (device tensor) -> canonical 23-mer table -> GPU MPHF -> {checker, tf} fill.
     Returns (mphf, index, checker_dev, tf_dev, n)."""
@@ -263,6 +284,10 @@ def run_ours(args):
     mphf, index, checker_t, tf_t, n_keys = build_index(torch, capi, ctx, reads)
     ctx.sync()
     index_build_s = time.perf_counter() - t_idx
+    # Q2 (reported under extra): 50 % substrings of the reads (hits, either strand) + 50 % random
+    q2_n = min(args.queries, 20_000_000)
+    q2_dev = torch.cat([make_hit_queries(torch, dev, reads, q2_n // 2, 4 + rank), make_queries(torch, dev, q2_n - q2_n // 2, 5 + rank)])
+    q2_dev = q2_dev[torch.randperm(q2_n, device=dev)].contiguous()
     del reads
     torch.cuda.empty_cache()
     q_dev = make_queries(torch, dev, args.queries, 3 + rank)
@@ -314,6 +339,22 @@ def run_ours(args):
     value = world * args.queries / (ms_per_step / 1e3)
     hits = int((out_dev > 0).sum().item())
 
+    # ---- Q2: 50 % hits (device resident) ---------------------------------------------------------
+    q2_out = torch.empty(q2_n, device=dev, dtype=torch.int32)
+    for _ in range(3):
+        index.query_dev(q2_dev.data_ptr(), 23, None, q2_n, capi.Q_TF, q2_out.data_ptr())
+    ctx.sync()
+    qa, qb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qa.record(stream)
+    for _ in range(args.steps):
+        index.query_dev(q2_dev.data_ptr(), 23, None, q2_n, capi.Q_TF, q2_out.data_ptr())
+    qb.record(stream)
+    ctx.sync()
+    q2_ms = qa.elapsed_time(qb) / args.steps
+    q2 = {"queries": q2_n, "hit_fraction": float((q2_out > 0).float().mean().item()), "ms_per_step": q2_ms,
+          "value": q2_n / (q2_ms / 1e3), "unit": "queries/s (per GPU, device resident)"}
+    del q2_dev, q2_out
+
     # ---- e2e: host buffers through the C-ABI (pinned) -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -353,8 +394,9 @@ def run_ours(args):
                 "traffic": None}
 
     # ---- 13-mer counting (second half of the metric), per-GPU shard of C3 -------------------------
-    extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries},
-             "setup_s": setup_s}
+    extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries,
+                       "canonical_only": index.info["canonical_only"]},
+             "tf23_q2_half_hits": q2, "setup_s": setup_s}
     creads = None
     if args.count_reads > 0:
         del q_dev
