@@ -97,9 +97,15 @@ SIGNATURES = {
     "aix_positions_build23": (_i, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "aix_positions_total13": (_i, [_vp, _vp, _vp]),
     "aix_positions_build13": (_i, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "aix_positions_build23_dev": (_i, [_vp, _vp, _vp, _u64, _pp]),
+    "aix_positions_build13_dev": (_i, [_vp, _vp, _vp, _u64, _pp]),
+    "aix_positions_info": (_i, [_vp, _vp]),
+    "aix_positions_arrays_dev": (_i, [_vp, _pp, _pp]),
+    "aix_positions_download": (_i, [_vp, _vp, _vp, _vp]),
     "aix_positions_upload": (_i, [_vp, _vp, _u64, _vp, _u64, _pp]),
     "aix_positions_destroy": (None, [_vp, _vp]),
     "aix_positions_query": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u64, _i, _vp, _vp, _vp]),
+    "aix_positions_query_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u64, _i, _vp, _vp, _vp]),
     "aix_canonical23_count": (_i, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "aix_canonical23_count_dev": (_i, [_vp, _vp, _u64, _vp]),
     "aix_canonical23_result_dev": (_i, [_vp, _pp, _pp, _vp]),
@@ -511,13 +517,44 @@ def _coverage(ctx, ix23, ix13, seqs, offs, k, cutoff):
 class Positions:
     """aix_positions: .indices.bin / .index.bin resident in HBM."""
 
-    def __init__(self, ctx: Context, indices, positions):
+    def __init__(self, ctx: Context, indices=None, positions=None, handle=None):
         self.ctx = ctx
+        if handle is not None:
+            self._h = handle
+            return
         indices = np.ascontiguousarray(indices, dtype=np.uint64)
         positions = np.ascontiguousarray(positions, dtype=np.uint64)
         self._h = C.c_void_p()
         ctx.check(lib().aix_positions_upload(ctx.handle, _p(indices), indices.size, _p(positions),
                                              positions.size, C.byref(self._h)))
+
+    @classmethod
+    def build_dev(cls, index, reads_ptr: int, n_bytes: int, k: int) -> "Positions":
+        """Build from a .reads image already in HBM (readable 8 bytes past n_bytes); stays in HBM."""
+        h = C.c_void_p()
+        fn = lib().aix_positions_build23_dev if k == 23 else lib().aix_positions_build13_dev
+        index.ctx.check(fn(index.ctx.handle, index._h, reads_ptr, n_bytes, C.byref(h)))
+        return cls(index.ctx, handle=h)
+
+    @property
+    def info(self):
+        a = (C.c_uint64 * 2)()
+        self.ctx.check(lib().aix_positions_info(self._h, a))
+        return {"n_indices": int(a[0]), "n_positions": int(a[1])}
+
+    def device_arrays(self):
+        """-> (indices_ptr, positions_ptr) device addresses of the u64 arrays."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().aix_positions_arrays_dev(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download(self):
+        """-> (indices uint64[n+1], positions uint64[total]) = .indices.bin / .index.bin contents."""
+        inf = self.info
+        indices = np.zeros(inf["n_indices"], dtype=np.uint64)
+        positions = np.zeros(inf["n_positions"], dtype=np.uint64)
+        self.ctx.check(lib().aix_positions_download(self.ctx.handle, self._h, _p(indices), _p(positions)))
+        return indices, positions
 
     def close(self):
         if self._h:

@@ -232,6 +232,91 @@ __global__ void canonical23_kernel(const uint8_t *__restrict__ bytes, uint64_t l
     }
 }
 
+// Inputs with 2^31 or more windows (or more than the HBM at hand can sort at once) are
+// processed in passes over ranges of the canonical value: pass A counts the k-mers per
+// top-12-bit bin, the host groups bins into ranges that fit, pass B emits the k-mers of one
+// range compactly (order is irrelevant: they are sorted next).
+constexpr int kCanBinsLog2 = 12;
+constexpr int kCanBins = 1 << kCanBinsLog2;
+
+// the 16 canonical k-mers of a thread (all-ones = invalid window or past the end)
+__device__ __forceinline__ void canonical23_roll(const uint8_t *__restrict__ bytes, uint64_t n_win, uint64_t i0,
+                                                 uint64_t (&km)[kCanRoll]) {
+    const uint64_t mask = (1ULL << 46) - 1;
+    uint64_t f = 0, r = 0;
+    uint32_t bad = 0;
+    for (int j = 0; j < 22; ++j) {
+        uint32_t ch = bytes[i0 + j];
+        uint64_t c = base_code_strict(ch);
+        f = (f << 2) | c;
+        r = (r >> 2) | ((3 - c) << 44);
+        bad = (bad << 1) | (is_acgt_upper(ch) ? 0u : 1u);
+    }
+#pragma unroll
+    for (int t = 0; t < kCanRoll; ++t) {
+        km[t] = ~0ULL;
+        if (i0 + t < n_win) {
+            uint32_t ch = bytes[i0 + t + 22];
+            uint64_t c = base_code_strict(ch);
+            f = ((f << 2) | c) & mask;
+            r = (r >> 2) | ((3 - c) << 44);
+            bad = ((bad << 1) | (is_acgt_upper(ch) ? 0u : 1u)) & ((1u << 23) - 1);
+            if (!bad) km[t] = f <= r ? f : r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) canonical23_bins_kernel(const uint8_t *__restrict__ bytes, uint64_t len,
+                                                             unsigned long long *__restrict__ bins) {
+    __shared__ uint32_t sbin[kCanBins];
+    for (int i = threadIdx.x; i < kCanBins; i += blockDim.x) sbin[i] = 0;
+    __syncthreads();
+    const uint64_t n_win = len - 22;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kCanRoll;
+    if (i0 < n_win) {
+        uint64_t km[kCanRoll];
+        canonical23_roll(bytes, n_win, i0, km);
+#pragma unroll
+        for (int t = 0; t < kCanRoll; ++t)
+            if (km[t] != ~0ULL) atomicAdd(&sbin[(uint32_t)(km[t] >> (46 - kCanBinsLog2))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCanBins; i += blockDim.x)
+        if (sbin[i]) atomicAdd(bins + i, (unsigned long long)sbin[i]);
+}
+
+// k-mers with lo <= value < hi, appended to out[*cursor ...] (one atomic per warp)
+__global__ void __launch_bounds__(128) canonical23_range_kernel(const uint8_t *__restrict__ bytes, uint64_t len, uint64_t lo,
+                                                              uint64_t hi, uint64_t *__restrict__ out,
+                                                              unsigned long long *__restrict__ cursor) {
+    const uint64_t n_win = len - 22;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kCanRoll;
+    uint64_t km[kCanRoll];
+    uint32_t c = 0;
+    if (i0 < n_win) {
+        canonical23_roll(bytes, n_win, i0, km);
+#pragma unroll
+        for (int t = 0; t < kCanRoll; ++t) c += (km[t] >= lo && km[t] < hi) ? 1u : 0u;
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    if (c) {
+        uint64_t w = base + (x - c);
+#pragma unroll
+        for (int t = 0; t < kCanRoll; ++t)
+            if (km[t] >= lo && km[t] < hi) out[w++] = km[t];
+    }
+}
+
 }  // namespace aix
 
 using namespace aix;
@@ -411,6 +496,193 @@ int aix_index23_fill(aix_ctx *ctx, const aix_mphf *m, const uint64_t *kmers, con
     return AIX_OK;
 }
 
+// sort + run-length of `n_keys` k-mers held in keys (keys_alt = spare of the same size, cnts = u32[n_keys]);
+// the unique k-mers end up in *uniq_out (one of the two key buffers) with their counts in cnts
+static int c23_sort_rle(aix_ctx *ctx, uint64_t *keys, uint64_t *keys_alt, uint32_t *cnts, uint64_t n_keys, int end_bit,
+                        uint64_t **uniq_out, uint64_t *n_uniq) {
+    cudaStream_t st = ctx->stream;
+    *n_uniq = 0;
+    *uniq_out = keys_alt;
+    if (n_keys == 0) return AIX_OK;
+    void *tmp = nullptr;
+    int *n_runs = nullptr;
+    auto cleanup = [&]() { cudaFree(tmp); cudaFree(n_runs); };
+    cub::DoubleBuffer<uint64_t> db(keys, keys_alt);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int)n_keys, 0, end_bit, st);
+    cudaError_t e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cudaMalloc(&n_runs, sizeof(int));
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)n_keys, 0, end_bit, st);
+    ctx->launches += 8;
+    if (e != cudaSuccess) {
+        cudaGetLastError(); cleanup();
+        return ctx->fail(AIX_ERR_CUDA, "canonical23 sort: %s", cudaGetErrorString(e));
+    }
+    uint64_t *sorted = db.Current();
+    uint64_t *spare = db.Alternate();  // reused for the unique keys
+    cudaFree(tmp); tmp = nullptr;
+    size_t tmp2 = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, sorted, spare, cnts, n_runs, (int)n_keys, st);
+    e = cudaMalloc(&tmp, tmp2 ? tmp2 : 1);
+    if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(tmp, tmp2, sorted, spare, cnts, n_runs, (int)n_keys, st);
+    ctx->launches += 3;
+    int h_runs = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_runs, n_runs, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_CUDA, "canonical23 run-length: %s", cudaGetErrorString(e));
+    }
+    *uniq_out = spare;
+    *n_uniq = (uint64_t)h_runs;
+    return AIX_OK;
+}
+
+// per-pass key capacity: CUB takes int counts, and keys + spare + counts + sort scratch must fit
+static uint64_t c23_pass_capacity(uint64_t reserve_bytes) {
+    uint64_t cap = (1ull << 31) - 4096;
+    if (const char *e = getenv("AIX_CANONICAL23_PASS_KEYS")) {  // test hook: force the multi-pass path
+        uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 1024) return v < cap ? v : cap;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        uint64_t usable = free_b > reserve_bytes ? free_b - reserve_bytes : 0;
+        uint64_t by_mem = usable / 26;  // 8 + 8 + 4 bytes per key + onesweep scratch + slack
+        if (by_mem < cap) cap = by_mem;
+    }
+    return cap;
+}
+
+static int c23_single_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t n_win, uint64_t *n_out) {
+    uint64_t *keys = nullptr, *keys_alt = nullptr;
+    uint32_t *cnts = nullptr;
+    auto cleanup = [&]() { cudaFree(keys); cudaFree(keys_alt); cudaFree(cnts); };
+    cudaError_t e = cudaMalloc(&keys, n_win * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&keys_alt, n_win * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&cnts, n_win * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); cleanup();
+        return ctx->fail(AIX_ERR_NOMEM, "canonical23 buffers: %s", cudaGetErrorString(e));
+    }
+    canonical23_kernel<<<aix_grid((n_win + kCanRoll - 1) / kCanRoll, 128), 128, 0, ctx->stream>>>(reads_dev, len, keys);
+    ctx->launches++;
+    uint64_t *uniq = nullptr, n = 0;
+    int rc = c23_sort_rle(ctx, keys, keys_alt, cnts, n_win, 64, &uniq, &n);
+    if (rc != AIX_OK) { cleanup(); return rc; }
+    uint64_t last_key = 0;
+    if (n) e = cudaMemcpy(&last_key, uniq + (n - 1), 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && n && last_key == ~0ULL) --n;  // the invalid-window sentinel sorts last
+    if (e == cudaSuccess && n) {
+        e = cudaMalloc(&ctx->c23_kmers_dev, n * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->c23_counts_dev, n * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_kmers_dev, uniq, n * 8, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_counts_dev, cnts, n * 4, cudaMemcpyDeviceToDevice);
+    }
+    cleanup();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_NOMEM, "canonical23 result: %s", cudaGetErrorString(e));
+    }
+    ctx->c23_n = n;
+    *n_out = n;
+    return AIX_OK;
+}
+
+static int c23_multi_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t n_win, uint64_t cap, uint64_t *n_out) {
+    cudaStream_t st = ctx->stream;
+    const unsigned grid = aix_grid((n_win + kCanRoll - 1) / kCanRoll, 128);
+    unsigned long long *bins_dev = nullptr, *cursor = nullptr;
+    uint64_t *keys = nullptr, *keys_alt = nullptr;
+    uint32_t *cnts = nullptr;
+    struct Seg { uint64_t *k; uint32_t *c; uint64_t n; };
+    std::vector<Seg> segs;
+    auto cleanup = [&]() {
+        cudaFree(bins_dev); cudaFree(cursor); cudaFree(keys); cudaFree(keys_alt); cudaFree(cnts);
+        for (auto &g : segs) { cudaFree(g.k); cudaFree(g.c); }
+    };
+#define C23_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            cudaGetLastError(); cleanup();                                                          \
+            return ctx->fail(AIX_ERR_CUDA, "canonical23 %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+        }                                                                                           \
+    } while (0)
+    C23_CUDA(cudaMalloc(&bins_dev, kCanBins * 8));
+    C23_CUDA(cudaMalloc(&cursor, 8));
+    C23_CUDA(cudaMemsetAsync(bins_dev, 0, kCanBins * 8, st));
+    canonical23_bins_kernel<<<grid, 128, 0, st>>>(reads_dev, len, bins_dev);
+    ctx->launches++;
+    std::vector<unsigned long long> bins(kCanBins);
+    C23_CUDA(cudaMemcpyAsync(bins.data(), bins_dev, kCanBins * 8, cudaMemcpyDeviceToHost, st));
+    C23_CUDA(cudaStreamSynchronize(st));
+    uint64_t max_bin = 0;
+    for (auto b : bins) max_bin = b > max_bin ? b : max_bin;
+    if (max_bin > cap) {
+        cleanup();
+        return ctx->fail(AIX_ERR_NOMEM, "canonical23: one k-mer range holds %llu windows, more than a pass can sort (%llu)",
+                         (unsigned long long)max_bin, (unsigned long long)cap);
+    }
+    // ranges of whole bins with at most `cap` k-mers each
+    std::vector<std::pair<int, int>> ranges;
+    uint64_t largest = 0;
+    for (int b = 0; b < kCanBins;) {
+        uint64_t acc = 0;
+        int e = b;
+        while (e < kCanBins && acc + bins[e] <= cap) acc += bins[e++];
+        if (acc) ranges.push_back({b, e});
+        largest = acc > largest ? acc : largest;
+        b = e;
+    }
+    C23_CUDA(cudaMalloc(&keys, (largest ? largest : 1) * 8));
+    C23_CUDA(cudaMalloc(&keys_alt, (largest ? largest : 1) * 8));
+    C23_CUDA(cudaMalloc(&cnts, (largest ? largest : 1) * 4));
+    uint64_t n_total = 0;
+    for (auto &rg : ranges) {
+        const uint64_t lo = (uint64_t)rg.first << (46 - kCanBinsLog2), hi = (uint64_t)rg.second << (46 - kCanBinsLog2);
+        C23_CUDA(cudaMemsetAsync(cursor, 0, 8, st));
+        canonical23_range_kernel<<<grid, 128, 0, st>>>(reads_dev, len, lo, hi, keys, cursor);
+        ctx->launches++;
+        unsigned long long n_keys = 0;
+        C23_CUDA(cudaMemcpyAsync(&n_keys, cursor, 8, cudaMemcpyDeviceToHost, st));
+        C23_CUDA(cudaStreamSynchronize(st));
+        uint64_t *uniq = nullptr, n = 0;
+        int rc = c23_sort_rle(ctx, keys, keys_alt, cnts, n_keys, 46, &uniq, &n);
+        if (rc != AIX_OK) { cleanup(); return rc; }
+        if (n) {
+            Seg g = {nullptr, nullptr, n};
+            segs.push_back(g);
+            C23_CUDA(cudaMalloc(&segs.back().k, n * 8));
+            C23_CUDA(cudaMalloc(&segs.back().c, n * 4));
+            C23_CUDA(cudaMemcpyAsync(segs.back().k, uniq, n * 8, cudaMemcpyDeviceToDevice, st));
+            C23_CUDA(cudaMemcpyAsync(segs.back().c, cnts, n * 4, cudaMemcpyDeviceToDevice, st));
+            C23_CUDA(cudaStreamSynchronize(st));
+            n_total += n;
+        }
+    }
+    cudaFree(keys); keys = nullptr;
+    cudaFree(keys_alt); keys_alt = nullptr;
+    cudaFree(cnts); cnts = nullptr;
+    if (n_total) {
+        C23_CUDA(cudaMalloc(&ctx->c23_kmers_dev, n_total * 8));
+        C23_CUDA(cudaMalloc(&ctx->c23_counts_dev, n_total * 4));
+        uint64_t at = 0;
+        for (auto &g : segs) {  // ranges are ascending, so the concatenation is sorted
+            C23_CUDA(cudaMemcpyAsync(ctx->c23_kmers_dev + at, g.k, g.n * 8, cudaMemcpyDeviceToDevice, st));
+            C23_CUDA(cudaMemcpyAsync(ctx->c23_counts_dev + at, g.c, g.n * 4, cudaMemcpyDeviceToDevice, st));
+            at += g.n;
+        }
+        C23_CUDA(cudaStreamSynchronize(st));
+    }
+#undef C23_CUDA
+    cleanup();
+    ctx->c23_n = n_total;
+    *n_out = n_total;
+    return AIX_OK;
+}
+
 // distinct canonical 23-mers + counts of a reads image already in HBM; the result stays in
 // ctx (c23_*), sorted ascending
 int aix_canonical23_count_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t *n_out) {
@@ -422,66 +694,10 @@ int aix_canonical23_count_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t l
     *n_out = 0;
     if (len < 23) return AIX_OK;
     const uint64_t n_win = len - 22;
-    if (n_win >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "canonical23: reads image too large for one pass (%llu windows)", (unsigned long long)n_win);
-    uint64_t *keys = nullptr, *keys_alt = nullptr, *uniq = nullptr;
-    uint32_t *cnts = nullptr;
-    int *n_runs = nullptr;
-    void *tmp = nullptr;
-    auto cleanup = [&]() { cudaFree(keys); cudaFree(keys_alt); cudaFree(uniq); cudaFree(cnts); cudaFree(n_runs); cudaFree(tmp); };
-    cudaError_t e = cudaMalloc(&keys, n_win * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&keys_alt, n_win * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&n_runs, sizeof(int));
-    if (e != cudaSuccess) {
-        cudaGetLastError(); cleanup();
-        return ctx->fail(AIX_ERR_NOMEM, "canonical23 buffers: %s", cudaGetErrorString(e));
-    }
-    cudaStream_t st = ctx->stream;
-    canonical23_kernel<<<aix_grid((n_win + kCanRoll - 1) / kCanRoll, 128), 128, 0, st>>>(reads_dev, len, keys);
-    ctx->launches++;
-    cub::DoubleBuffer<uint64_t> db(keys, keys_alt);
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int)n_win, 0, 64, st);
-    e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)n_win, 0, 64, st);
-    ctx->launches += 8;
-    if (e != cudaSuccess) {
-        cudaGetLastError(); cleanup();
-        return ctx->fail(AIX_ERR_CUDA, "canonical23 sort: %s", cudaGetErrorString(e));
-    }
-    uint64_t *sorted = db.Current();
-    uint64_t *spare = db.Alternate();  // reused for the unique keys
-    cudaFree(tmp); tmp = nullptr;
-    e = cudaMalloc(&cnts, n_win * 4);
-    size_t tmp2 = 0;
-    if (e == cudaSuccess) cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, sorted, spare, cnts, n_runs, (int)n_win, st);
-    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp2 ? tmp2 : 1);
-    if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(tmp, tmp2, sorted, spare, cnts, n_runs, (int)n_win, st);
-    ctx->launches += 3;
-    int h_runs = 0;
-    uint64_t last_key = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_runs, n_runs, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess && h_runs > 0) e = cudaMemcpy(&last_key, spare + (h_runs - 1), 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) {
-        cudaGetLastError(); cleanup();
-        return ctx->fail(AIX_ERR_CUDA, "canonical23 run-length: %s", cudaGetErrorString(e));
-    }
-    uint64_t n = (uint64_t)h_runs;
-    if (n && last_key == ~0ULL) --n;  // the invalid-window sentinel sorts last
-    if (n) {
-        e = cudaMalloc(&ctx->c23_kmers_dev, n * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->c23_counts_dev, n * 4);
-        if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_kmers_dev, spare, n * 8, cudaMemcpyDeviceToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_counts_dev, cnts, n * 4, cudaMemcpyDeviceToDevice);
-        if (e != cudaSuccess) {
-            cudaGetLastError(); cleanup();
-            return ctx->fail(AIX_ERR_NOMEM, "canonical23 result: %s", cudaGetErrorString(e));
-        }
-    }
-    cleanup();
-    ctx->c23_n = n;
-    *n_out = n;
-    return AIX_OK;
+    const uint64_t cap = c23_pass_capacity(n_win);  // leave room for the result (12 B per distinct k-mer, twice)
+    if (cap < 1024) return ctx->fail(AIX_ERR_NOMEM, "canonical23: not enough free HBM");
+    if (n_win <= cap) return c23_single_pass(ctx, reads_dev, len, n_win, n_out);
+    return c23_multi_pass(ctx, reads_dev, len, n_win, cap, n_out);
 }
 
 int aix_canonical23_result_dev(aix_ctx *ctx, const uint64_t **kmers_dev, const uint32_t **counts_dev, uint64_t *n) {

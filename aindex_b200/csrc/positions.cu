@@ -345,19 +345,26 @@ static uint64_t first_start(const uint8_t *c, uint64_t len, uint64_t k) {
     return start;
 }
 
+// Device part of the build.  reads_dev must be readable for 8 bytes past len (aligned word
+// loads of the last windows); `start` = first_start of the image.  On success *indices_dev
+// (u64[n+1]) and *positions_dev (u64[total], at least one element) are owned by the caller.
 template <int K, typename F>
-static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n, const uint8_t *reads, uint64_t len,
-                      uint64_t *indices_out, uint64_t *positions_out) {
+static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n, const uint8_t *reads_dev, uint64_t len,
+                      uint64_t start, unsigned long long **indices_dev, unsigned long long **positions_dev,
+                      uint64_t *total_out) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     unsigned long long *indices = nullptr, *positions = nullptr, *tmp = nullptr, *tmp_off = nullptr, *tiles = nullptr;
     uint32_t *occ = nullptr, *cursor = nullptr, *medium = nullptr, *large = nullptr;
-    uint8_t *reads_dev = nullptr;
     int *over = nullptr;
     unsigned int *cls = nullptr;
+    auto cleanup_tmp = [&]() {
+        cudaFree(tmp); cudaFree(tmp_off); cudaFree(tiles);
+        cudaFree(occ); cudaFree(cursor); cudaFree(medium); cudaFree(large); cudaFree(over); cudaFree(cls);
+    };
     auto cleanup = [&]() {
-        cudaFree(indices); cudaFree(positions); cudaFree(tmp); cudaFree(tmp_off); cudaFree(tiles);
-        cudaFree(occ); cudaFree(cursor); cudaFree(medium); cudaFree(large); cudaFree(reads_dev); cudaFree(over); cudaFree(cls);
+        cleanup_tmp();
+        cudaFree(indices); cudaFree(positions);
     };
 #define PB_CUDA(call)                                                                                   \
     do {                                                                                                \
@@ -379,12 +386,8 @@ static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
     PB_CUDA(cudaMalloc(&positions, (total ? total : 1) * 8));
     PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
     if (len >= (uint64_t)K && n && total) {
-        const uint64_t start = first_start(reads, len, K);
         const uint64_t n_win_end = len - K + 1;
         if (start < n_win_end) {
-            PB_CUDA(cudaMalloc(&reads_dev, len + 64));
-            PB_CUDA(cudaMemcpyAsync(reads_dev, reads, len, cudaMemcpyHostToDevice, st));
-            PB_CUDA(cudaMemsetAsync(reads_dev + len, '\n', 64, st));
             PB_CUDA(cudaMalloc(&occ, n * 4));
             PB_CUDA(cudaMalloc(&cursor, n * 4));
             PB_CUDA(cudaMalloc(&medium, n * 4));
@@ -395,9 +398,13 @@ static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
             PB_CUDA(cudaMemsetAsync(cursor, 0, n * 4, st));
             PB_CUDA(cudaMemsetAsync(over, 0, sizeof(int), st));
             PB_CUDA(cudaMemsetAsync(cls, 0, 2 * sizeof(unsigned int), st));
-            const unsigned grid = aix_grid(n_win_end - start, 256);
-            positions_scan_kernel<K, 0><<<grid, 256, 0, st>>>(id, md, reads_dev, start, n_win_end, occ, nullptr, nullptr);
-            ctx->launches++;
+            // grids are limited to 2^31-1 CTAs: scan the image in launches of <= 2^38 windows
+            const uint64_t kLaunchWin = 1ull << 38;
+            for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
+                const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
+                positions_scan_kernel<K, 0><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, reads_dev, w0, w1, occ, nullptr, nullptr);
+                ctx->launches++;
+            }
             classify_kernel<<<aix_grid(n, 256), 256, 0, st>>>(tf, occ, n, over, medium, large, cls, kSmallMax, kMediumMax);
             ctx->launches++;
             int h_over = 0;
@@ -418,8 +425,11 @@ static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
                 data = tmp;
                 off = tmp_off;
             }
-            positions_scan_kernel<K, 1><<<grid, 256, 0, st>>>(id, md, reads_dev, start, n_win_end, cursor, off, data);
-            ctx->launches++;
+            for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
+                const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
+                positions_scan_kernel<K, 1><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, reads_dev, w0, w1, cursor, off, data);
+                ctx->launches++;
+            }
             sort_small_kernel<<<aix_grid(n, 256), 256, 0, st>>>(data, off, occ, n, kSmallMax);
             ctx->launches++;
             if (h_cls[0]) {
@@ -456,11 +466,76 @@ static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
             }
         }
     }
-    PB_CUDA(cudaMemcpyAsync(indices_out, indices, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (total) PB_CUDA(cudaMemcpyAsync(positions_out, positions, total * 8, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
 #undef PB_CUDA
-    cleanup();
+    cleanup_tmp();
+    *indices_dev = indices;
+    *positions_dev = positions;
+    *total_out = total;
+    return AIX_OK;
+}
+
+// host image -> device build -> host arrays
+template <int K, typename F>
+static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n, const uint8_t *reads, uint64_t len,
+                      uint64_t *indices_out, uint64_t *positions_out) {
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *reads_dev = nullptr;
+    cudaError_t e = cudaMalloc(&reads_dev, len + 64);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_NOMEM, "positions build: reads image: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(reads_dev, reads, len, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(reads_dev + len, '\n', 64, ctx->stream);
+    unsigned long long *indices = nullptr, *positions = nullptr;
+    uint64_t total = 0;
+    int rc = build_core<K>(ctx, id, md, tf, n, reads_dev, len, first_start(reads, len, K), &indices, &positions, &total);
+    cudaFree(reads_dev);
+    if (rc != AIX_OK) return rc;
+    e = cudaMemcpyAsync(indices_out, indices, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(positions_out, positions, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(indices);
+    cudaFree(positions);
+    if (e != cudaSuccess) return ctx->fail(AIX_ERR_CUDA, "positions build: download: %s", cudaGetErrorString(e));
+    return AIX_OK;
+}
+
+// first_start of an image that lives in HBM: the prologue only looks at a prefix, fetched in pieces
+static int first_start_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t k, uint64_t *start_out) {
+    const uint64_t kPiece = 1ull << 20;
+    std::vector<uint8_t> buf;
+    uint64_t base = 0;  // windows before `base` are known to be skipped
+    while (true) {
+        const uint64_t n = len - base < kPiece ? len - base : kPiece;
+        buf.resize(n);
+        AIX_CUDA(ctx, cudaMemcpy(buf.data(), reads_dev + base, n, cudaMemcpyDeviceToHost));
+        const uint64_t s = first_start(buf.data(), n, k);
+        if (s + k <= n || base + n == len) {  // settled inside the piece, or the image ended
+            *start_out = base + s;
+            return AIX_OK;
+        }
+        base += s > 0 ? s : 1;  // unreachable s == 0 (then s + k <= n unless n < k = image end)
+    }
+}
+
+template <int K, typename F>
+static int build_dev_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n, const uint8_t *reads_dev, uint64_t len,
+                          aix_positions **out) {
+    *out = nullptr;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t start = 0;
+    if (len >= (uint64_t)K) AIX_TRY(first_start_dev(ctx, reads_dev, len, K, &start));
+    unsigned long long *indices = nullptr, *positions = nullptr;
+    uint64_t total = 0;
+    AIX_TRY((build_core<K>(ctx, id, md, tf, n, reads_dev, len, start, &indices, &positions, &total)));
+    aix_positions *p = new aix_positions();
+    p->n_indices = n + 1;
+    p->n_positions = total;
+    p->indices_dev = (uint64_t *)indices;
+    p->positions_dev = (uint64_t *)positions;
+    *out = p;
     return AIX_OK;
 }
 
@@ -522,6 +597,44 @@ int aix_positions_build13(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *re
     return build_impl<13>(ctx, none, ix->mphf->dev(), TfFromU64{ix->tf_mphf_dev}, AIX_TOTAL_13MERS, reads, len, indices_out, positions_out);
 }
 
+int aix_positions_build23_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *reads_dev, uint64_t len,
+                              aix_positions **out) {
+    if (!ctx || !ix || !out || (len && !reads_dev)) return AIX_ERR_ARG;
+    return build_dev_impl<23>(ctx, ix->dev(), ix->mphf->dev(), TfFromRecs{ix->recs_dev}, ix->n, reads_dev, len, out);
+}
+
+int aix_positions_build13_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *reads_dev, uint64_t len,
+                              aix_positions **out) {
+    if (!ctx || !ix || !out || (len && !reads_dev)) return AIX_ERR_ARG;
+    Index23Dev none = {};
+    return build_dev_impl<13>(ctx, none, ix->mphf->dev(), TfFromU64{ix->tf_mphf_dev}, AIX_TOTAL_13MERS, reads_dev, len, out);
+}
+
+int aix_positions_info(const aix_positions *p, uint64_t info[2]) {
+    if (!p || !info) return AIX_ERR_ARG;
+    info[0] = p->n_indices;
+    info[1] = p->n_positions;
+    return AIX_OK;
+}
+
+int aix_positions_arrays_dev(const aix_positions *p, const uint64_t **indices_dev, const uint64_t **positions_dev) {
+    if (!p) return AIX_ERR_ARG;
+    if (indices_dev) *indices_dev = p->indices_dev;
+    if (positions_dev) *positions_dev = p->positions_dev;
+    return AIX_OK;
+}
+
+int aix_positions_download(aix_ctx *ctx, const aix_positions *p, uint64_t *indices_out, uint64_t *positions_out) {
+    if (!ctx || !p) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (indices_out && p->n_indices)
+        AIX_CUDA(ctx, cudaMemcpyAsync(indices_out, p->indices_dev, p->n_indices * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (positions_out && p->n_positions)
+        AIX_CUDA(ctx, cudaMemcpyAsync(positions_out, p->positions_dev, p->n_positions * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AIX_OK;
+}
+
 int aix_positions_upload(aix_ctx *ctx, const uint64_t *indices, uint64_t n_indices, const uint64_t *positions,
                          uint64_t n_positions, aix_positions **out) {
     if (!ctx || !out || (n_indices && !indices) || (n_positions && !positions)) return AIX_ERR_ARG;
@@ -551,6 +664,37 @@ void aix_positions_destroy(aix_ctx *ctx, aix_positions *p) {
     delete p;
 }
 
+int aix_positions_query_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const aix_positions *p,
+                            const uint8_t *recs_dev, uint32_t stride, const uint8_t *lens_dev, uint64_t q, int k,
+                            uint64_t *counts_dev, const uint64_t *offs_dev, uint64_t *pos_out_dev) {
+    if (!ctx || !p) return AIX_ERR_ARG;
+    if (k == 23 && !ix23) return ctx->fail(AIX_ERR_STATE, "23-mer index not loaded");
+    if (k == 13 && !ix13) return ctx->fail(AIX_ERR_STATE, "13-mer index not loaded");
+    if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
+    if (q == 0) return AIX_OK;
+    if (!recs_dev || !stride || (!counts_dev && !pos_out_dev) || (pos_out_dev && !offs_dev)) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Index23Dev id = {};
+    MphfDev md;
+    if (k == 23) {
+        id = ix23->dev();
+        md = ix23->mphf->dev();
+        positions_query_kernel<23><<<aix_grid(q, 128), 128, 0, st>>>(
+            id, md, (const unsigned long long *)p->indices_dev, p->n_indices, (const unsigned long long *)p->positions_dev,
+            p->n_positions, recs_dev, stride, lens_dev, q, (unsigned long long *)counts_dev,
+            (const unsigned long long *)offs_dev, (unsigned long long *)pos_out_dev);
+    } else {
+        md = ix13->mphf->dev();
+        positions_query_kernel<13><<<aix_grid(q, 128), 128, 0, st>>>(
+            id, md, (const unsigned long long *)p->indices_dev, p->n_indices, (const unsigned long long *)p->positions_dev,
+            p->n_positions, recs_dev, stride, lens_dev, q, (unsigned long long *)counts_dev,
+            (const unsigned long long *)offs_dev, (unsigned long long *)pos_out_dev);
+    }
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
 int aix_positions_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const aix_positions *p,
                         const uint8_t *recs, uint32_t stride, const uint8_t *lens, uint64_t q, int k, uint64_t *counts_out,
                         const uint64_t *offs, uint64_t *pos_out) {
@@ -577,23 +721,8 @@ int aix_positions_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13
         AIX_CUDA(ctx, cudaMemcpyAsync(o_dev, offs, (q + 1) * 8, cudaMemcpyHostToDevice, st));
         AIX_TRY(ctx->reserve(SCR_TMP0, (total ? total : 1) * 8, &out_dev));
     }
-    Index23Dev id = {};
-    MphfDev md;
-    if (k == 23) {
-        id = ix23->dev();
-        md = ix23->mphf->dev();
-        positions_query_kernel<23><<<aix_grid(q, 128), 128, 0, st>>>(
-            id, md, (const unsigned long long *)p->indices_dev, p->n_indices, (const unsigned long long *)p->positions_dev,
-            p->n_positions, (const uint8_t *)r_dev, stride, (const uint8_t *)l_dev, q, (unsigned long long *)c_dev,
-            (const unsigned long long *)o_dev, (unsigned long long *)out_dev);
-    } else {
-        md = ix13->mphf->dev();
-        positions_query_kernel<13><<<aix_grid(q, 128), 128, 0, st>>>(
-            id, md, (const unsigned long long *)p->indices_dev, p->n_indices, (const unsigned long long *)p->positions_dev,
-            p->n_positions, (const uint8_t *)r_dev, stride, (const uint8_t *)l_dev, q, (unsigned long long *)c_dev,
-            (const unsigned long long *)o_dev, (unsigned long long *)out_dev);
-    }
-    AIX_LAUNCH_CHECK(ctx);
+    AIX_TRY(aix_positions_query_dev(ctx, ix23, ix13, p, (const uint8_t *)r_dev, stride, (const uint8_t *)l_dev, q, k,
+                                    (uint64_t *)c_dev, (const uint64_t *)o_dev, (uint64_t *)out_dev));
     if (counts_out) AIX_CUDA(ctx, cudaMemcpyAsync(counts_out, c_dev, q * 8, cudaMemcpyDeviceToHost, st));
     if (pos_out && total) AIX_CUDA(ctx, cudaMemcpyAsync(pos_out, out_dev, total * 8, cudaMemcpyDeviceToHost, st));
     AIX_CUDA(ctx, cudaStreamSynchronize(st));

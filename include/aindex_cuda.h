@@ -226,6 +226,20 @@ int aix_positions_build23(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *re
 int aix_positions_total13(aix_ctx *ctx, const aix_index13 *ix, uint64_t *total);
 int aix_positions_build13(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *reads, uint64_t len,
                           uint64_t *indices_out, uint64_t *positions_out);
+/* same on a .reads image already in HBM (readable for 8 bytes past len); the index stays in
+ * HBM as an aix_positions object (C5 at full size: 51 GB of positions never leave the GPU) */
+int aix_positions_build23_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *reads_dev,
+                              uint64_t len, aix_positions **out);
+int aix_positions_build13_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *reads_dev,
+                              uint64_t len, aix_positions **out);
+/* info[0] = number of indices (n+1), info[1] = number of positions (indices[n]) */
+int aix_positions_info(const aix_positions *p, uint64_t info[2]);
+int aix_positions_arrays_dev(const aix_positions *p, const uint64_t **indices_dev,
+                             const uint64_t **positions_dev);
+/* AIndexCompressed::save (hash.hpp:470-486): the arrays as they are written to
+ * .indices.bin / .index.bin (either pointer may be NULL) */
+int aix_positions_download(aix_ctx *ctx, const aix_positions *p, uint64_t *indices_out,
+                           uint64_t *positions_out);
 /* AindexWrapper::load_aindex (python_wrapper.cpp:361-402): upload .indices.bin/.index.bin */
 int aix_positions_upload(aix_ctx *ctx, const uint64_t *indices, uint64_t n_indices,
                          const uint64_t *positions, uint64_t n_positions, aix_positions **out);
@@ -237,6 +251,11 @@ int aix_positions_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13
                         const aix_positions *p, const uint8_t *recs, uint32_t stride,
                         const uint8_t *lens, uint64_t q, int k, uint64_t *counts_out,
                         const uint64_t *offs, uint64_t *pos_out);
+/* same, all buffers in HBM; asynchronous on aix_ctx_stream() */
+int aix_positions_query_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13,
+                            const aix_positions *p, const uint8_t *recs_dev, uint32_t stride,
+                            const uint8_t *lens_dev, uint64_t q, int k, uint64_t *counts_dev,
+                            const uint64_t *offs_dev, uint64_t *pos_out_dev);
 
 /* ---- canonical 23-mer table (input of the index build) ------------ */
 /* distinct canonical 23-mers (min(kmer, revcomp), ACGT-only windows, '\n' and '~'

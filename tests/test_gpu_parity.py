@@ -473,3 +473,56 @@ def test_large_batch_properties(capi, ctx, idx23, oidx23):
     assert np.array_equal(idx23.query(km, capi.Q_TOTAL), 2 * tf.astype(np.uint64))
     parts = np.concatenate([idx23.query(km[i:i + 333_333]) for i in range(0, n, 333_333)])
     assert np.array_equal(parts, tf)
+
+
+# ---------------------------------------------------------------------------- device-resident paths
+def test_positions_dev_build_and_query_match_host_path(capi, ctx, idx23, g23, golden_dir):
+    """aix_positions_build23_dev / aix_positions_query_dev (everything stays in HBM) against the
+    golden .indices.bin / .index.bin and the host-buffer query path."""
+    import torch
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    buf = torch.full((reads.size + 64,), 10, dtype=torch.uint8, device="cuda:0")
+    buf[:reads.size] = torch.from_numpy(reads).cuda()
+    torch.cuda.synchronize()
+    pos = capi.Positions.build_dev(idx23, buf.data_ptr(), reads.size, 23)
+    indices, positions = pos.download()
+    assert np.array_equal(indices, np.fromfile(os.path.join(golden_dir, "idx23.indices.bin"), dtype=np.uint64))
+    assert np.array_equal(positions, np.fromfile(os.path.join(golden_dir, "idx23.index.bin"), dtype=np.uint64))
+    assert pos.info == {"n_indices": indices.size, "n_positions": positions.size}
+    q = _queries(g23["recs"], g23["lens"])
+    offs, vals = pos.query(idx23, [q[i] for i in g23["pos_qidx"]], 23)
+    assert np.array_equal(offs, g23["pos_off"]) and np.array_equal(vals, g23["pos_val"])
+    # a leading run of separator-only windows (first_start prologue, hash.cpp:973-988)
+    lead = np.frombuffer(b"\n~\n" + b"ACGT\n" * 3, dtype=np.uint8)
+    reads2 = np.concatenate([lead, reads])
+    buf2 = torch.full((reads2.size + 64,), 10, dtype=torch.uint8, device="cuda:0")
+    buf2[:reads2.size] = torch.from_numpy(reads2).cuda()
+    torch.cuda.synchronize()
+    i2, p2 = capi.Positions.build_dev(idx23, buf2.data_ptr(), reads2.size, 23).download()
+    hi, hp = idx23.positions_build(reads2)
+    assert np.array_equal(i2, hi) and np.array_equal(p2, hp)
+    assert np.array_equal(p2[p2 > 0], positions[positions > 0] + lead.size)
+
+
+def test_canonical23_multi_pass_equals_single_pass(capi, ctx, monkeypatch):
+    """Inputs too large for one sort are counted in passes over k-mer ranges; forcing tiny passes on
+    a small input must give the same sorted table."""
+    rng = np.random.default_rng(97)
+    genome = rng.choice(ACGT, size=40000).tobytes()
+    lines = []
+    for i in range(3000):
+        st = int(rng.integers(0, len(genome) - 150))
+        r = genome[st:st + int(rng.integers(10, 150))]
+        if rng.random() < 0.5:
+            r = rc(r)
+        if i % 40 == 3:
+            r = r[:7] + b"N" + r[8:]
+        lines.append(r)
+    reads = b"\n".join(lines) + b"\n"
+    k1, c1 = ctx.canonical23_count(reads)
+    monkeypatch.setenv("AIX_CANONICAL23_PASS_KEYS", "20000")
+    k2, c2 = ctx.canonical23_count(reads)
+    monkeypatch.delenv("AIX_CANONICAL23_PASS_KEYS")
+    assert k1.size > 30000  # > one pass: at least two ranges were needed
+    assert np.array_equal(k1, k2) and np.array_equal(c1, c2)
+    assert np.all(k2[1:] > k2[:-1])
