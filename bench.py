@@ -40,6 +40,19 @@ import numpy as np  # noqa: E402
 Q1_BYTES_PER_QUERY = 43       # 23 B in + 4 B out + 2 x 8 B checker
 Q1_BYTES_ONE_PROBE = 35       # what the canonical-first kernel really needs: 23 + 4 + 8
 C3_BYTES_PER_KMER = 9.09      # 151/138 B in + 4 B read + 4 B write
+# measured on this pool's B200 by profiles/atomic_roofline.cu (profiles/r01_atomic_roofline.txt)
+GATHER_PEAK_G = 50.1          # random 16-byte gathers/s (1 GiB table), G/s
+RED_PEAK_256M_G = 32.0        # random RED.ADD.U32 into a 256 MiB table (the north star's atomic roofline), G/s
+RED_PEAK_L2_G = 210.0         # the same into a 64 MiB (L2-resident) slice, G/s
+
+
+def _ncu_traffic(key, units, units_profiled):
+    """DRAM bytes per launch from the committed ncu capture, scaled if the run uses another size."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return d["bytes_per_launch"] * (units / units_profiled)
+    except Exception:
+        return None
 
 
 def parse_args():
@@ -391,7 +404,14 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_unit": Q1_BYTES_PER_QUERY, "units_per_launch": args.queries, "kernel_ms": k_ms,
                 "achieved_one_probe_bytes": args.queries * Q1_BYTES_ONE_PROBE / (k_ms / 1e3) / 1e9,
-                "traffic": None}
+                "traffic": _ncu_traffic("tf23_fixed_kernel_q1_100M", args.queries, 100_000_000),
+                "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
+                # the other denominators of this kernel (profiles/r01_atomic_roofline.txt):
+                # random 16-byte gathers from a 1 GiB table run at 50.1 G/s on this GPU (the index is 0.8 GB)
+                "random_access": {"achieved_gq_s": args.queries / (k_ms / 1e3) / 1e9, "peak_ggathers_s": GATHER_PEAK_G,
+                                  "frac": args.queries / (k_ms / 1e3) / 1e9 / GATHER_PEAK_G,
+                                  "note": "measured random-gather rate; above 1.0 is possible because the L2-resident "
+                                          "fingerprint tier answers misses without touching the HBM record"}}
 
     # ---- 13-mer counting (second half of the metric), per-GPU shard of C3 -------------------------
     extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries,
@@ -429,8 +449,10 @@ def run_ours(args):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record(stream)
         t0 = time.perf_counter()
+        l0 = ctx.launches
         for _ in range(args.steps):
             count_step()
+        count_launches = (ctx.launches - l0) / args.steps
         c1.record(stream)
         ctx.sync()
         barrier()
@@ -444,7 +466,13 @@ def run_ours(args):
         extra["count13"] = {"metric": "13-mer k-mers counted/s", "value": kps, "unit": "k-mers/s", "ms_per_step": c_ms,
                             "reads_per_gpu": args.count_reads, "kmers_per_gpu": n_kmers, "stats_ok": bool(ok),
                             "collective": "nccl reduce_scatter(sum) of the 4^13 u64 histogram" if world > 1 else None,
-                            "hbm_frac_9.09B": kps / world * C3_BYTES_PER_KMER / 1e9 / peak_gbs}
+                            "hbm_frac_9.09B": kps / world * C3_BYTES_PER_KMER / 1e9 / peak_gbs,
+                            "atomic_roofline": {"achieved_gred_s": kps / world / 1e9,
+                                                "frac_of_256MiB_table_red_rate": kps / world / 1e9 / RED_PEAK_256M_G,
+                                                "frac_of_L2_resident_red_rate": kps / world / 1e9 / RED_PEAK_L2_G,
+                                                "peaks_gred_s": {"256MiB_table": RED_PEAK_256M_G, "64MiB_slice": RED_PEAK_L2_G},
+                                                "source": "profiles/r01_atomic_roofline.txt"},
+                            "gpu_launches_per_step": int(count_launches)}
         extra["count13"]["wall_ms_per_step"] = extra_wall_ms
         if not args.no_e2e:
             # e2e: the shard starts in pinned host memory; H2D chunks overlap the count kernel
