@@ -543,7 +543,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "extra": extra,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -567,7 +567,7 @@ def run_reference(args):
     import torch
     from aindex_b200 import capi
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "index setup for config C2 needs the GPU builder (no GPU visible)"}))
+        _emit({"impl": "reference", "unavailable": "index setup for config C2 needs the GPU builder (no GPU visible)"})
         return
     dev = torch.device("cuda", 0)
     ctx = capi.Context(0)
@@ -598,10 +598,26 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": kind,
                              "sample": f"{sample} Q1 queries per step, {threads} std::threads over PHASH_MAP::get_freq (src/hash.hpp:123-140)"},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
+
+def _emit(line: dict):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
+_REAL_STDOUT = None
 
 if __name__ == "__main__":
+    # libraries (NCCL's version banner, torchrun) write to stdout: keep fd 1 for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
