@@ -72,6 +72,7 @@ SIGNATURES = {
     "aix_index23_load_prefix": (_i, [_vp, C.c_char_p, _pp, _pp]),
     "aix_index23_destroy": (None, [_vp, _vp]),
     "aix_index23_info": (_i, [_vp, _vp]),
+    "aix_index23_layout": (_i, [_vp, _vp]),
     "aix_index23_fill": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "aix_index23_fill_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "aix_tf23_batch": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
@@ -412,6 +413,12 @@ class Index23:
         a = np.zeros(2, dtype=np.uint64)
         self.ctx.check(lib().aix_index23_info(self._h, _p(a)))
         return {"n": int(a[0]), "canonical_only": bool(a[1])}
+
+    @property
+    def layout(self):
+        a = np.zeros(4, dtype=np.uint64)
+        self.ctx.check(lib().aix_index23_layout(self._h, _p(a)))
+        return {"fp_bits": int(a[0]), "fp_bytes": int(a[1]), "mphf_bytes": int(a[2]), "mphf_compact": bool(a[3])}
 
     def query(self, kmers, mode: int = Q_TF, out: Optional[np.ndarray] = None) -> np.ndarray:
         recs, lens = as_records(kmers)

@@ -16,13 +16,16 @@ struct aix_mphf {
     uint64_t n = 0, hash_domain = 0, seed = 0, bv_size = 0, n_words = 0, n_blocks = 0;
     std::vector<uint64_t> words;        // .pf order (host copy, for save / inspection)
     std::vector<uint64_t> block_ranks;  // .pf order
-    ulonglong2 *recs_dev = nullptr;     // B200 layout, see device_common.cuh
+    ulonglong2 *recs_dev = nullptr;     // B200 layout (wide records), see device_common.cuh
+    uint4 *crecs_dev = nullptr;         // B200 layout (compact records); exactly one of the two is set
+    uint64_t layout_bytes = 0;          // size of the device structure (L2 budget of the fingerprint tier)
     aix::MphfDev dev() const {
         aix::MphfDev d;
         d.n = n; d.hash_domain = hash_domain; d.seed = seed;
         // floor(2^64 / d); for d == 1 the quotient does not fit: 2^64-1 still gives q in {q_true-1, q_true}
         d.magic = hash_domain > 1 ? (uint64_t)((((unsigned __int128)1) << 64) / hash_domain) : ~0ULL;
         d.recs = recs_dev;
+        d.crecs = crecs_dev;
         return d;
     }
 };
@@ -33,9 +36,10 @@ struct aix_index23 {
     const aix_mphf *mphf = nullptr;
     uint4 *recs_dev = nullptr;  // {checker lo, checker hi, tf, 0}
     uint8_t *fp_dev = nullptr;  // fingerprint tier (may be null)
+    int fp_bits = 0;            // 8 or 4 when fp_dev is set
     aix::Index23Dev dev() const {
         aix::Index23Dev d;
-        d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev; d.fp = fp_dev;
+        d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev; d.fp = fp_dev; d.fp_bits = fp_bits;
         return d;
     }
 };

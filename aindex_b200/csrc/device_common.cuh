@@ -15,17 +15,22 @@ namespace aix {
 
 // ---------------------------------------------------------------------------------
 // B200 layout of the MPHF.  The reference stores words[] and a rank sample every 512
-// pairs, so rank() walks up to 16 words.  Here every 64-bit word of the bit-pair vector
-// is stored next to the rank of its first pair: one 16-byte load yields both the 2-bit
-// value and everything rank() needs, so a lookup is three independent 16-byte loads
-// (L2 resident: 0.46 B per key) and no dependent fourth access.
+// pairs, so rank() walks up to 16 words.  Here the bit-pair vector is cut into 16-byte
+// records that carry the rank of their first pair: one 16-byte load yields both the 2-bit
+// value and everything rank() needs, so a lookup is three independent 16-byte loads and no
+// dependent fourth access.  Two record shapes:
+//   compact (bv_size < 2^32, i.e. up to 1.16 G keys): 48 pairs + u32 rank   -> 0.41 B / key
+//   wide    (anything larger):                         32 pairs + u64 rank   -> 0.61 B / key
+// The compact form keeps the C2 structure (50 M keys) at 20.5 MB, which together with the
+// fingerprint tier stays inside the ~60 MB of L2 that random accesses from all SMs can use.
 // ---------------------------------------------------------------------------------
 struct MphfDev {
     uint64_t n;
     uint64_t hash_domain;
     uint64_t seed;
     uint64_t magic;     // floor(2^64 / hash_domain)
-    const ulonglong2 *recs;  // recs[w] = { words[w], rank of pair 32*w }
+    const ulonglong2 *recs;  // wide:    recs[w] = { words[w], rank of pair 32*w }
+    const uint4 *crecs;      // compact: crecs[r] = { pairs 48r..48r+47 (96 bits), rank of pair 48*r }; nullptr = wide
 };
 
 struct Index23Dev {
@@ -36,12 +41,17 @@ struct Index23Dev {
     // fingerprint differs cannot verify, so it never touches the HBM record: on miss-dominated
     // batches (the reference's own stress workload) 255/256 of the random HBM probes disappear.
     // Exact: fp mismatch => checker mismatch; a match is always confirmed on the full record.
-    const uint8_t *fp;  // nullptr = tier disabled (index too large to keep n bytes in L2)
+    const uint8_t *fp;  // nullptr = tier disabled (index too large to keep it in L2)
+    int fp_bits;        // 8: fp[h]; 4: nibble (h & 1) of fp[h >> 1] (half the L2 footprint, 1/16 false positives)
 };
 
 __device__ __host__ __forceinline__ uint32_t fingerprint8(uint64_t kmer) {
     uint32_t x = (uint32_t)kmer ^ (uint32_t)(kmer >> 23);
     return (x ^ (x >> 9)) & 0xFFu;
+}
+__device__ __host__ __forceinline__ uint32_t fingerprint4(uint64_t kmer) {
+    uint32_t x = fingerprint8(kmer);
+    return (x ^ (x >> 4)) & 0xFu;
 }
 
 // ---- cache-policy loads ---------------------------------------------------------------
@@ -72,11 +82,20 @@ __device__ __forceinline__ uint4 ld_evict_first_u32x4(const uint4 *p) {
     return v;
 }
 
-// exact h % d for any 64-bit h: q = mulhi(h, floor(2^64/d)) is q_true or q_true-1
+// exact h % d for any 64-bit h.  magic = floor(2^64/d) = (2^64 - r0)/d with r0 < d, so
+// h*magic/2^64 = h/d - h*r0/(d*2^64) > h/d - 1: q = mulhi(h, magic) is q_true or q_true-1 and
+// h - q*d lies in [0, 2d): one conditional subtraction.
 __device__ __forceinline__ uint64_t fastmod(uint64_t h, uint64_t d, uint64_t magic) {
     uint64_t q = __umul64hi(h, magic);
     uint64_t r = h - q * d;
     if (r >= d) r -= d;
+    return r;
+}
+// the same for d < 2^31: the remainder before correction is below 2d <= 2^32, so it can be
+// formed from the low halves alone (only the low 32 bits of the quotient are needed)
+__device__ __forceinline__ uint32_t fastmod32(uint64_t h, uint32_t d, uint64_t magic) {
+    uint32_t q = (uint32_t)__umul64hi(h, magic);
+    uint32_t r = (uint32_t)h - q * d;
     if (r >= d) r -= d;
     return r;
 }
@@ -139,7 +158,44 @@ __device__ __forceinline__ uint32_t nonzero_pairs64(uint64_t x) {
     return (uint32_t)__popcll(x);  // == the SWAR count of ranked_bitpair_vector.hpp:92-106
 }
 
+__device__ __forceinline__ uint32_t nonzero_pairs32(uint32_t x) { return (uint32_t)__popc((x | (x >> 1)) & 0x55555555u); }
+__device__ __forceinline__ uint4 ld_evict_last_u32x4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+
+// compact records: all node indices fit 32 bits (3 * hash_domain < 2^32)
+__device__ __forceinline__ uint64_t mphf_eval_compact(const MphfDev &m, uint64_t a, uint64_t b, uint64_t c) {
+    const uint32_t d = (uint32_t)m.hash_domain;
+    const uint32_t n0 = fastmod32(a, d, m.magic);
+    const uint32_t n1 = d + fastmod32(b, d, m.magic);
+    const uint32_t n2 = 2u * d + fastmod32(c, d, m.magic);
+    const uint32_t q0 = __umulhi(n0, 0xAAAAAAABu) >> 5, q1 = __umulhi(n1, 0xAAAAAAABu) >> 5,
+                   q2 = __umulhi(n2, 0xAAAAAAABu) >> 5;  // n / 48
+    const uint4 r0 = ld_evict_last_u32x4(&m.crecs[q0]);
+    const uint4 r1 = ld_evict_last_u32x4(&m.crecs[q1]);
+    const uint4 r2 = ld_evict_last_u32x4(&m.crecs[q2]);
+    const uint32_t p0 = n0 - q0 * 48u, p1 = n1 - q1 * 48u, p2 = n2 - q2 * 48u;  // pair inside the record
+    const uint32_t w0 = p0 < 16u ? r0.x : (p0 < 32u ? r0.y : r0.z);
+    const uint32_t w1 = p1 < 16u ? r1.x : (p1 < 32u ? r1.y : r1.z);
+    const uint32_t w2 = p2 < 16u ? r2.x : (p2 < 32u ? r2.y : r2.z);
+    const uint32_t s0 = (p0 & 15u) * 2u, s1 = (p1 & 15u) * 2u, s2 = (p2 & 15u) * 2u;
+    const uint32_t v = ((w0 >> s0) & 3u) + ((w1 >> s1) & 3u) + ((w2 >> s2) & 3u);
+    const uint32_t hidx = v % 3u;  // v <= 9
+    const uint4 r = hidx == 0 ? r0 : (hidx == 1 ? r1 : r2);
+    const uint32_t p = hidx == 0 ? p0 : (hidx == 1 ? p1 : p2);
+    const uint32_t w = hidx == 0 ? w0 : (hidx == 1 ? w1 : w2);
+    const uint32_t sh = hidx == 0 ? s0 : (hidx == 1 ? s1 : s2);
+    uint32_t rank = r.w + nonzero_pairs32(w & ((1u << sh) - 1u));  // sh <= 30
+    if (p >= 16u) rank += nonzero_pairs32(r.x);
+    if (p >= 32u) rank += nonzero_pairs32(r.y);
+    return (uint64_t)rank;
+}
+
 __device__ __forceinline__ uint64_t mphf_eval(const MphfDev &m, uint64_t a, uint64_t b, uint64_t c) {
+    if (m.crecs != nullptr) return mphf_eval_compact(m, a, b, c);
     const uint64_t d = m.hash_domain;
     uint64_t n0 = fastmod(a, d, m.magic);
     uint64_t n1 = d + fastmod(b, d, m.magic);
@@ -226,8 +282,13 @@ __device__ __forceinline__ bool probe23(const Index23Dev &ix, uint64_t h, uint64
     if (h >= ix.n) return false;
     if (ix.fp != nullptr) {
         uint32_t f;
-        asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(ix.fp + h), "l"(l2_policy_evict_last()));
-        if (f != fingerprint8(kmer)) return false;
+        if (ix.fp_bits == 8) {
+            asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(ix.fp + h), "l"(l2_policy_evict_last()));
+            if (f != fingerprint8(kmer)) return false;
+        } else {
+            asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(ix.fp + (h >> 1)), "l"(l2_policy_evict_last()));
+            if (((f >> (((uint32_t)h & 1u) * 4u)) & 0xFu) != fingerprint4(kmer)) return false;
+        }
     }
     uint4 r = ld_evict_first_u32x4(&ix.recs[h]);
     uint64_t chk = ((uint64_t)r.y << 32) | r.x;

@@ -19,10 +19,53 @@ __global__ void mphf_layout_kernel(const uint64_t *__restrict__ words, const uin
     recs[w] = make_ulonglong2(words[w], r);
 }
 
+// compact records: crecs[r] = { half-words 3r, 3r+1, 3r+2 of the bit-pair vector, rank of pair 48*r }
+__global__ void mphf_layout_compact_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ block_ranks,
+                                           uint64_t n_words, uint64_t n_recs, uint4 *__restrict__ crecs) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_recs) return;
+    const uint64_t j = 3 * r;  // first half-word
+    auto half = [&](uint64_t k) -> uint32_t {
+        uint64_t w = k >> 1;
+        if (w >= n_words) return 0u;
+        return (k & 1) ? (uint32_t)(words[w] >> 32) : (uint32_t)words[w];
+    };
+    const uint64_t w = j >> 1, blk = w >> 4;
+    uint64_t rank = w < n_words ? block_ranks[blk] : 0;
+    for (uint64_t i = blk << 4; i < w && i < n_words; ++i) rank += nonzero_pairs64(words[i]);
+    if (j & 1) rank += nonzero_pairs32(half(j - 1));
+    crecs[r] = make_uint4(half(j), half(j + 1), half(j + 2), (uint32_t)rank);
+}
+
+static bool mphf_force_wide() {
+    const char *e = getenv("AIX_MPHF_WIDE");  // test hook: exercise the wide records on small structures
+    return e && atoi(e) != 0;
+}
+
 int mphf_build_layout(aix_ctx *ctx, aix_mphf *m) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     uint64_t nw = m->n_words ? m->n_words : 1;
     uint64_t *words_dev = nullptr, *ranks_dev = nullptr;
+    const bool compact = m->bv_size < (1ull << 32) && m->hash_domain < (1ull << 31) && m->n < (1ull << 32) && !mphf_force_wide();
+    if (compact) {
+        const uint64_t n_recs = (2 * nw + 2) / 3 + 1;
+        m->layout_bytes = n_recs * sizeof(uint4);
+        AIX_CUDA(ctx, cudaMalloc(&m->crecs_dev, n_recs * sizeof(uint4)));
+        AIX_CUDA(ctx, cudaMemsetAsync(m->crecs_dev, 0, n_recs * sizeof(uint4), ctx->stream));
+        if (m->n_words) {
+            AIX_CUDA(ctx, cudaMalloc(&words_dev, m->n_words * 8));
+            AIX_CUDA(ctx, cudaMalloc(&ranks_dev, (m->n_blocks ? m->n_blocks : 1) * 8));
+            AIX_CUDA(ctx, cudaMemcpyAsync(words_dev, m->words.data(), m->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+            AIX_CUDA(ctx, cudaMemcpyAsync(ranks_dev, m->block_ranks.data(), m->n_blocks * 8, cudaMemcpyHostToDevice, ctx->stream));
+            mphf_layout_compact_kernel<<<aix_grid(n_recs, 256), 256, 0, ctx->stream>>>(words_dev, ranks_dev, m->n_words, n_recs, m->crecs_dev);
+            AIX_LAUNCH_CHECK(ctx);
+        }
+        AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (words_dev) cudaFree(words_dev);
+        if (ranks_dev) cudaFree(ranks_dev);
+        return AIX_OK;
+    }
+    m->layout_bytes = nw * sizeof(ulonglong2);
     AIX_CUDA(ctx, cudaMalloc(&m->recs_dev, nw * sizeof(ulonglong2)));
     AIX_CUDA(ctx, cudaMemsetAsync(m->recs_dev, 0, nw * sizeof(ulonglong2), ctx->stream));
     if (m->n_words) {
@@ -147,6 +190,7 @@ void aix_mphf_destroy(aix_ctx *ctx, aix_mphf *m) {
     if (!m) return;
     if (ctx) cudaSetDevice(ctx->device);
     if (m->recs_dev) cudaFree(m->recs_dev);
+    if (m->crecs_dev) cudaFree(m->crecs_dev);
     delete m;
 }
 

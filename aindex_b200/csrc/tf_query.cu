@@ -57,6 +57,89 @@ __global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, Mphf
     query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
 }
 
+
+// ---- K3 streaming form: persistent CTAs, one TMA ring per warp ------------------------------------
+// The fixed kernel above pays three dependent round trips per query (query bytes from HBM, MPHF
+// records, fingerprint / index record) and a CTA barrier between the first two.  Here every warp
+// owns a 3-slot ring of 32-query tiles (736 B) in shared memory that lane 0 fills with
+// cp.async.bulk (TMA, UBLKCP in SASS) two tiles ahead, completion signalled on one mbarrier per
+// slot: the query bytes are already on chip when a warp starts a tile, there is no CTA-wide
+// barrier, and the grid is sized to the resident CTAs of the 148 SMs (tiles are dealt round robin).
+constexpr int kStWarps = 8;
+constexpr int kStStages = 3;
+constexpr uint32_t kStTileBytes = 32u * 23u;  // 736 = 46 * 16: legal bulk-copy size, slots stay 16-byte aligned
+constexpr int kStSlot = 768;                  // the seventh word of lane 31 ends at byte 740
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+
+template <int kMode, bool kCanon, int kMinBlocks>
+__global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
+                                                                  uint64_t n_tiles, void *__restrict__ out) {
+    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kStSlot];
+    __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t total_warps = (uint64_t)gridDim.x * kStWarps;
+    const uint64_t gw = (uint64_t)blockIdx.x * kStWarps + wid;
+    const uint64_t policy = l2_policy_evict_first();
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStStages - 1; ++s) {
+            const uint64_t t = gw + (uint64_t)s * total_warps;
+            if (t < n_tiles) {
+                mbar_expect_tx(&bars[wid][s], kStTileBytes);
+                bulk_load(ring[wid][s], recs + t * kStTileBytes, kStTileBytes, &bars[wid][s], policy);
+            }
+        }
+    }
+    uint32_t it = 0, slot = 0, phase = 0;
+    for (uint64_t t = gw; t < n_tiles; t += total_warps, ++it) {
+        // refill the slot every lane finished reading in the previous iteration (the __syncwarp below)
+        const uint64_t tn = t + (uint64_t)(kStStages - 1) * total_warps;
+        if (lane == 0 && tn < n_tiles) {
+            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
+            mbar_expect_tx(&bars[wid][sn], kStTileBytes);
+            bulk_load(ring[wid][sn], recs + tn * kStTileBytes, kStTileBytes, &bars[wid][sn], policy);
+        }
+        mbar_wait(&bars[wid][slot], phase);
+        const uint32_t *tile = reinterpret_cast<const uint32_t *>(ring[wid][slot]);
+        const uint32_t base = lane * 23u;
+        const uint32_t w = base >> 2, sh = (base & 3u) * 8u;
+        uint32_t x0 = tile[w], x1 = tile[w + 1], x2 = tile[w + 2], x3 = tile[w + 3], x4 = tile[w + 4], x5 = tile[w + 5],
+                 x6 = tile[w + 6];
+        __syncwarp();
+        uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
+                 y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
+        uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
+                 r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
+        const uint64_t i = t * 32u + lane;
+        query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
+        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+    }
+}
+
 // K3, generic records (any stride, per-record lengths)
 template <int kMode, bool kCanon>
 __global__ void __launch_bounds__(kQBlock) tf23_generic_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
@@ -97,12 +180,19 @@ __global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__re
 
 // ---- index upload helpers ----------------------------------------------------------------
 __global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const uint32_t *__restrict__ tf, uint64_t n,
-                                    uint4 *__restrict__ recs, uint8_t *__restrict__ fp, int *__restrict__ non_canonical) {
+                                    uint4 *__restrict__ recs, uint8_t *__restrict__ fp, int fp_bits,
+                                    int *__restrict__ non_canonical) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t c = checker[i];
     recs[i] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), tf[i], 0u);
-    if (fp) fp[i] = (uint8_t)fingerprint8(c);
+    if (fp) {
+        if (fp_bits == 8) fp[i] = (uint8_t)fingerprint8(c);
+        else if ((i & 1) == 0) {  // one thread writes both nibbles of a byte
+            uint32_t lo = fingerprint4(c), hi = i + 1 < n ? fingerprint4(checker[i + 1]) : 0u;
+            fp[i >> 1] = (uint8_t)(lo | (hi << 4));
+        }
+    }
     if ((c >> 46) != 0 || c > revcomp23(c)) *non_canonical = 1;
 }
 
@@ -183,13 +273,56 @@ static size_t out_bytes23(int mode) {
     }
 }
 
+// 1: streaming kernel (default), 0: one CTA per 256 queries (AIX_TF23_KERNEL, kept for A/B runs)
+static int tf23_kernel_choice() {
+    const char *e = getenv("AIX_TF23_KERNEL");
+    return e ? atoi(e) : 1;
+}
+
+// register budget of the streaming kernel: 6 resident CTAs (40 registers, a few spilled words) or
+// whatever ptxas picks (46 registers, 5 CTAs); AIX_TF23_MINBLOCKS selects for A/B runs
+static int tf23_min_blocks() {
+    const char *e = getenv("AIX_TF23_MINBLOCKS");
+    return e ? atoi(e) : 6;
+}
+
+template <int kMode, bool kCanon, int kMinBlocks>
+static void launch_stream(const aix_ctx *ctx, cudaStream_t st, const Index23Dev &id, const MphfDev &md, const uint8_t *recs,
+                          uint64_t n_tiles, void *out) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tf23_stream_kernel<kMode, kCanon, kMinBlocks>, kStWarps * 32, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+    }
+    uint64_t want = (n_tiles + kStWarps - 1) / kStWarps, cap = (uint64_t)ctx->sm_count * per_sm;
+    tf23_stream_kernel<kMode, kCanon, kMinBlocks><<<(unsigned)(want < cap ? want : cap), kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out);
+}
+
+
 template <int kMode>
-static void launch23_mode(const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
-                          uint64_t q, void *out) {
+static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
+                          const uint8_t *lens, uint64_t q, void *out) {
     Index23Dev id = ix->dev();
     MphfDev md = ix->mphf->dev();
-    unsigned grid = aix_grid(q, kQBlock);
     const bool fixed = (stride == 23 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
+    if (fixed && tf23_kernel_choice() == 1 && q >= 32) {
+        const uint64_t n_tiles = q / 32;
+        if (ix->canonical_only) {
+            if (tf23_min_blocks() >= 6) launch_stream<kMode, true, 6>(ctx, st, id, md, recs, n_tiles, out);
+            else launch_stream<kMode, true, 1>(ctx, st, id, md, recs, n_tiles, out);
+        } else {
+            launch_stream<kMode, false, 6>(ctx, st, id, md, recs, n_tiles, out);
+        }
+        // the last q % 32 queries: the same per-query code through the block kernel (its tile start stays 16-byte aligned)
+        const uint64_t done = n_tiles * 32;
+        if (done == q) return;
+        recs += done * 23;
+        out = (char *)out + done * out_bytes23(kMode);
+        q -= done;
+    }
+    unsigned grid = aix_grid(q, kQBlock);
     if (fixed) {
         if (ix->canonical_only) tf23_fixed_kernel<kMode, true><<<grid, kQBlock, 0, st>>>(id, md, recs, q, out);
         else tf23_fixed_kernel<kMode, false><<<grid, kQBlock, 0, st>>>(id, md, recs, q, out);
@@ -203,12 +336,12 @@ int launch_tf23(aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint
                 const uint8_t *lens, uint64_t q, int mode, void *out) {
     if (q == 0) return AIX_OK;
     switch (mode) {
-        case AIX_Q_TF: launch23_mode<AIX_Q_TF>(ix, st, recs, stride, lens, q, out); break;
-        case AIX_Q_TOTAL: launch23_mode<AIX_Q_TOTAL>(ix, st, recs, stride, lens, q, out); break;
-        case AIX_Q_BOTH: launch23_mode<AIX_Q_BOTH>(ix, st, recs, stride, lens, q, out); break;
-        case AIX_Q_PFID: launch23_mode<AIX_Q_PFID>(ix, st, recs, stride, lens, q, out); break;
-        case AIX_Q_STRAND: launch23_mode<AIX_Q_STRAND>(ix, st, recs, stride, lens, q, out); break;
-        case AIX_Q_KID: launch23_mode<AIX_Q_KID>(ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_TF: launch23_mode<AIX_Q_TF>(ctx, ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_TOTAL: launch23_mode<AIX_Q_TOTAL>(ctx, ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_BOTH: launch23_mode<AIX_Q_BOTH>(ctx, ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_PFID: launch23_mode<AIX_Q_PFID>(ctx, ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_STRAND: launch23_mode<AIX_Q_STRAND>(ctx, ix, st, recs, stride, lens, q, out); break;
+        case AIX_Q_KID: launch23_mode<AIX_Q_KID>(ctx, ix, st, recs, stride, lens, q, out); break;
         default: return ctx->fail(AIX_ERR_ARG, "unknown query mode %d", mode);
     }
     AIX_LAUNCH_CHECK(ctx);
@@ -263,19 +396,32 @@ int aix_index23_upload_dev(aix_ctx *ctx, const aix_mphf *m, const uint64_t *chec
         aix_index23_destroy(ctx, ix);
         return ctx->fail(AIX_ERR_NOMEM, "index23 upload: %s", cudaGetErrorString(e));
     }
-    // fingerprint tier: n bytes that must stay in L2 next to the MPHF records (16 B per 32 nodes)
-    uint64_t fp_budget = 96ull << 20;
+    // fingerprint tier: must stay in L2 next to the MPHF records.  Random accesses from all SMs see
+    // about half of the 126 MB L2 (two partitions, lines replicated on the far side): 8-bit
+    // fingerprints when both structures fit in the budget, else 4-bit, else no tier.
+    uint64_t fp_budget = 72ull << 20;  // measured: C2 (50 M keys, 70.5 MB with 8-bit fingerprints) still runs best with 8 bits (profiles/r01_tf23_sweep.txt)
     if (const char *e = getenv("AIX_FP_TIER_MAX_BYTES")) fp_budget = strtoull(e, nullptr, 10);
-    if (n && n + m->n_words * 16 <= fp_budget) {
-        if (cudaMalloc(&ix->fp_dev, n) != cudaSuccess) {
+    uint64_t fp_bytes = 0;
+    if (n && n + m->layout_bytes <= fp_budget) { ix->fp_bits = 8; fp_bytes = n; }
+    else if (n && (n + 1) / 2 + m->layout_bytes <= fp_budget) { ix->fp_bits = 4; fp_bytes = (n + 1) / 2; }
+    if (const char *e = getenv("AIX_FP_TIER_BITS")) {  // test / experiment hook: 0, 4 or 8
+        int b = atoi(e);
+        ix->fp_bits = (b == 4 || b == 8) ? b : 0;
+        fp_bytes = ix->fp_bits == 8 ? n : (ix->fp_bits == 4 ? (n + 1) / 2 : 0);
+    }
+    if (fp_bytes) {
+        if (cudaMalloc(&ix->fp_dev, fp_bytes) != cudaSuccess) {
             cudaGetLastError();
             ix->fp_dev = nullptr;
+            ix->fp_bits = 0;
         }
+    } else {
+        ix->fp_bits = 0;
     }
     int flag = 0;
     cudaMemsetAsync(flag_dev, 0, sizeof(int), ctx->stream);
     if (n) {
-        index23_pack_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(checker_dev, tf_dev, n, ix->recs_dev, ix->fp_dev, flag_dev);
+        index23_pack_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(checker_dev, tf_dev, n, ix->recs_dev, ix->fp_dev, ix->fp_bits, flag_dev);
         ctx->launches++;
     }
     cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -343,6 +489,15 @@ int aix_index23_info(const aix_index23 *ix, uint64_t info[2]) {
     if (!ix || !info) return AIX_ERR_ARG;
     info[0] = ix->n;
     info[1] = (uint64_t)ix->canonical_only;
+    return AIX_OK;
+}
+
+int aix_index23_layout(const aix_index23 *ix, uint64_t info[4]) {
+    if (!ix || !info) return AIX_ERR_ARG;
+    info[0] = (uint64_t)ix->fp_bits;
+    info[1] = ix->fp_bits == 8 ? ix->n : (ix->fp_bits == 4 ? (ix->n + 1) / 2 : 0);
+    info[2] = ix->mphf->layout_bytes;
+    info[3] = ix->mphf->crecs_dev ? 1 : 0;
     return AIX_OK;
 }
 

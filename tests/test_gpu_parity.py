@@ -526,3 +526,38 @@ def test_canonical23_multi_pass_equals_single_pass(capi, ctx, monkeypatch):
     assert k1.size > 30000  # > one pass: at least two ranges were needed
     assert np.array_equal(k1, k2) and np.array_equal(c1, c2)
     assert np.all(k2[1:] > k2[:-1])
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+@pytest.mark.parametrize("fp_bits", [0, 4, 8])
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_tf23_layout_and_kernel_variants(capi, oracle, ctx, oidx23, monkeypatch, wide, fp_bits, kernel):
+    """Every HBM/L2 layout (compact / wide MPHF records, no / 4-bit / 8-bit fingerprint tier) and both
+    fixed-stride kernels (TMA-ring streaming kernel, one-CTA-per-256 kernel) give the oracle's
+    answers in every mode, including ragged batch sizes around the 32-query tile."""
+    monkeypatch.setenv("AIX_MPHF_WIDE", str(wide))
+    monkeypatch.setenv("AIX_FP_TIER_BITS", str(fp_bits))
+    monkeypatch.setenv("AIX_TF23_KERNEL", str(kernel))
+    m = capi.Mphf.from_arrays(ctx, oidx23.mphf.n, oidx23.mphf.hash_domain, oidx23.mphf.seed, oidx23.mphf.words,
+                              oidx23.mphf.block_ranks)
+    ix = capi.Index23.upload(ctx, m, oidx23.checker, oidx23.tf)
+    lay = ix.layout
+    assert lay["fp_bits"] == fp_bits and lay["mphf_compact"] == (wide == 0)
+    rng = np.random.default_rng(100 + 10 * wide + fp_bits + kernel)
+    # raw mphf ids (keys and non-keys) must not depend on the record shape
+    q = _mixed_queries(rng, oidx23, 3000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    assert np.array_equal(m.lookup(q), oidx23.mphf.lookup_batch(recs, lens))
+    for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH),
+                        (capi.Q_PFID, oracle.MODE_PFID), (capi.Q_STRAND, oracle.MODE_STRAND), (capi.Q_KID, oracle.MODE_KID)):
+        assert np.array_equal(ix.query(q, mode), oidx23.batch(recs, lens, omode)), f"generic mode {mode}"
+    for nq in (1, 31, 32, 33, 8191, 8192, 20011):
+        qq = [x for x in _mixed_queries(rng, oidx23, 2 * nq) if len(x) == 23][:nq]
+        r23 = np.frombuffer(b"".join(qq), dtype=np.uint8).reshape(len(qq), 23).copy()
+        for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH),
+                            (capi.Q_PFID, oracle.MODE_PFID), (capi.Q_STRAND, oracle.MODE_STRAND), (capi.Q_KID, oracle.MODE_KID)):
+            assert np.array_equal(ix.query(r23, mode), oidx23.batch(r23, None, omode)), f"fixed mode {mode} nq {nq}"
+    cov_in = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "idx23.reads"), dtype=np.uint8)[:3000]
+    assert np.array_equal(ix.coverage(cov_in), oidx23.coverage(cov_in))
+    ix.close()
+    m.close()
