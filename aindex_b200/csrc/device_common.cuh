@@ -183,7 +183,7 @@ __device__ __forceinline__ uint64_t mphf_eval_compact(const MphfDev &m, uint64_t
     const uint32_t w2 = p2 < 16u ? r2.x : (p2 < 32u ? r2.y : r2.z);
     const uint32_t s0 = (p0 & 15u) * 2u, s1 = (p1 & 15u) * 2u, s2 = (p2 & 15u) * 2u;
     const uint32_t v = ((w0 >> s0) & 3u) + ((w1 >> s1) & 3u) + ((w2 >> s2) & 3u);
-    const uint32_t hidx = v % 3u;  // v <= 9
+    const uint32_t hidx = (0x24924u >> (2u * v)) & 3u;  // v % 3 for v <= 9, two bits per entry
     const uint4 r = hidx == 0 ? r0 : (hidx == 1 ? r1 : r2);
     const uint32_t p = hidx == 0 ? p0 : (hidx == 1 ? p1 : p2);
     const uint32_t w = hidx == 0 ? w0 : (hidx == 1 ? w1 : w2);
@@ -261,6 +261,23 @@ __device__ __forceinline__ void ascii_words13_from_rc(uint32_t rc_of_kmer, uint6
     uint32_t x = ~rc_of_kmer;
     w0 = ascii8_from_codes_le(x & 0xFFFF);
     w1 = ascii8_from_codes_le((x >> 16) & 0x3FF) & 0x000000FFFFFFFFFFULL;  // 5 bytes
+}
+
+// ASCII words of the reverse complement of a VALID (upper-case ACGT) 23-byte string given as
+// ASCII words: complement per byte (A^T = 0x15, C^G = 0x04, bit 1 tells which) and byte reversal by
+// one PRMT per output word (byte j = in byte 22-j: the alignment is the same for every word).
+__device__ __forceinline__ uint32_t ascii_complement4(uint32_t w) {
+    return w ^ 0x15151515u ^ (((w >> 1) & 0x01010101u) * 0x11u);
+}
+__device__ __forceinline__ void rc_ascii_words23(uint64_t e0, uint64_t e1, uint64_t e2, uint64_t &f0, uint64_t &f1, uint64_t &f2) {
+    const uint32_t c0 = ascii_complement4((uint32_t)e0), c1 = ascii_complement4((uint32_t)(e0 >> 32)),
+                   c2 = ascii_complement4((uint32_t)e1), c3 = ascii_complement4((uint32_t)(e1 >> 32)),
+                   c4 = ascii_complement4((uint32_t)e2), c5 = ascii_complement4((uint32_t)(e2 >> 32));
+    const uint32_t o0 = __byte_perm(c4, c5, 0x3456), o1 = __byte_perm(c3, c4, 0x3456), o2 = __byte_perm(c2, c3, 0x3456),
+                   o3 = __byte_perm(c1, c2, 0x3456), o4 = __byte_perm(c0, c1, 0x3456), o5 = __byte_perm(0u, c0, 0x3456);
+    f0 = ((uint64_t)o1 << 32) | o0;
+    f1 = ((uint64_t)o3 << 32) | o2;
+    f2 = ((uint64_t)o5 << 32) | o4;
 }
 
 // MPHF id of a packed 23-mer u given its reverse complement r (hashes the ASCII string of u)

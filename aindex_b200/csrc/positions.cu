@@ -140,12 +140,10 @@ static int exclusive_scan(aix_ctx *ctx, cudaStream_t st, F f, uint64_t n, unsign
 __device__ __forceinline__ uint64_t bucket23(const Index23Dev &ix, const MphfDev &m, const uint8_t *p) {
     uint64_t r0, r1, r2;
     load_window23(p, r0, r1, r2);
-    uint64_t all48 = ((uint64_t)codes_be_from_ascii8(r0) << 32) | ((uint64_t)codes_be_from_ascii8(r1) << 16) |
-                     codes_be_from_ascii8(r2);
-    uint64_t u = all48 >> 2, r = revcomp23(u), e0, e1, e2;
-    ascii_words23_from_rc(r, e0, e1, e2);
-    if (e0 == r0 && e1 == r1 && e2 == r2) {
-        Hit h = lookup_packed23<true>(ix, m, u, r, true, e0, e1, e2);  // one probe of min(u, r)
+    bool all_acgt;
+    uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
+    if (all_acgt) {
+        Hit h = lookup_packed23<true>(ix, m, u, r, true, r0, r1, r2);  // one probe of min(u, r)
         return h.strand ? h.h : kNoBucket;
     }
 #pragma unroll

@@ -22,6 +22,28 @@ __device__ __forceinline__ uint32_t codes_be_from_ascii8(uint64_t w) {
     return (pl << 8) | ph;
 }
 
+// 2-bit value of a 23-byte string (words zero padded past byte 22) AND whether every byte is an
+// upper-case ACGT letter: the letter code of each byte selects the one byte value that is valid
+// for it ("ACGT"[code], by PRMT) and the word is compared with that expectation.
+__device__ __forceinline__ uint32_t expect_acgt4(uint32_t c4) {  // c4: letter code in bits 1:0 of each byte
+    const uint32_t t = c4 | (c4 >> 4);
+    return __byte_perm(0x54474341u, 0u, __byte_perm(t, 0u, 0x4420));
+}
+__device__ __forceinline__ uint64_t encode_validate23(uint64_t r0, uint64_t r1, uint64_t r2, bool &all_acgt) {
+    const uint32_t w[6] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32), (uint32_t)r2, (uint32_t)(r2 >> 32)};
+    uint32_t p[6], bad = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const uint32_t c4 = ((w[j] >> 1) ^ (w[j] >> 2)) & 0x03030303u;
+        p[j] = (c4 * 0x40100401u) >> 24;  // c0<<6 | c1<<4 | c2<<2 | c3
+        const uint32_t diff = expect_acgt4(c4) ^ w[j];
+        bad |= j == 5 ? (diff & 0x00FFFFFFu) : diff;  // byte 23 is padding
+    }
+    all_acgt = bad == 0;
+    const uint64_t all48 = ((uint64_t)((p[0] << 8) | p[1]) << 32) | ((uint64_t)((p[2] << 8) | p[3]) << 16) | ((p[4] << 8) | p[5]);
+    return all48 >> 2;  // 23 codes; the 24th byte is padding
+}
+
 // strict encoder of get_dna23_bitset (kmers.cpp:12-25): non-ACGT (and missing) bytes -> 0
 __device__ __forceinline__ uint64_t encode23_strict(uint64_t r0, uint64_t r1, uint64_t r2) {
     uint64_t u = 0;
@@ -51,7 +73,11 @@ __device__ __forceinline__ Hit lookup_packed23(const Index23Dev &ix, const MphfD
         // every stored k-mer is canonical: only min(u, r) can be present, and the reference's
         // forward probe of a non-canonical u can never verify -> one probe, same answer.
         const bool fwd = u <= r;
-        if (!(fwd && have_asc_u)) ascii_words23_from_rc(fwd ? r : u, e0, e1, e2);
+        if (have_asc_u) {
+            if (!fwd) rc_ascii_words23(e0, e1, e2, e0, e1, e2);
+        } else {
+            ascii_words23_from_rc(fwd ? r : u, e0, e1, e2);
+        }
         jenkins_short(m.seed, e0, e1, e2, 23u, a, b, c);
         uint64_t h = mphf_eval(m, a, b, c);
         uint32_t tf;
@@ -94,14 +120,12 @@ __device__ __forceinline__ int cmp_words23(uint64_t a0, uint64_t a1, uint64_t a2
 template <int kMode, bool kCanon>
 __device__ __forceinline__ void query23(const Index23Dev &ix, const MphfDev &m, uint64_t r0, uint64_t r1, uint64_t r2,
                                         uint32_t len, const uint8_t *p, uint64_t i, void *out) {
-    // fast encode + validate by round trip
-    uint64_t all48 = ((uint64_t)codes_be_from_ascii8(r0) << 32) | ((uint64_t)codes_be_from_ascii8(r1) << 16) |
-                     codes_be_from_ascii8(r2);
-    uint64_t u = all48 >> 2;  // 23 codes; the 24th byte is padding
+    // fast encode + validate (a valid query's ASCII words are the raw words themselves)
+    bool all_acgt;
+    uint64_t u = encode_validate23(r0, r1, r2, all_acgt);
     uint64_t r = revcomp23(u);
-    uint64_t e0, e1, e2;
-    ascii_words23_from_rc(r, e0, e1, e2);
-    const bool valid = (len == 23u) && e0 == r0 && e1 == r1 && e2 == r2;
+    const uint64_t e0 = r0, e1 = r1, e2 = r2;
+    const bool valid = (len == 23u) && all_acgt;
 
     Hit hit = {0, 0, 0};
     uint64_t ustrict = u, rstrict = r;
@@ -188,13 +212,10 @@ __device__ __forceinline__ void query23(const Index23Dev &ix, const MphfDev &m, 
 template <bool kCanon>
 __device__ __forceinline__ Hit find23_window(const Index23Dev &ix, const MphfDev &m, uint64_t r0, uint64_t r1,
                                              uint64_t r2) {
-    uint64_t all48 = ((uint64_t)codes_be_from_ascii8(r0) << 32) | ((uint64_t)codes_be_from_ascii8(r1) << 16) |
-                     codes_be_from_ascii8(r2);
-    uint64_t u = all48 >> 2;
+    bool all_acgt;
+    uint64_t u = encode_validate23(r0, r1, r2, all_acgt);
     uint64_t r = revcomp23(u);
-    uint64_t e0, e1, e2;
-    ascii_words23_from_rc(r, e0, e1, e2);
-    if (e0 == r0 && e1 == r1 && e2 == r2) return lookup_packed23<kCanon>(ix, m, u, r, true, e0, e1, e2);
+    if (all_acgt) return lookup_packed23<kCanon>(ix, m, u, r, true, r0, r1, r2);
     // window with a non-ACGT byte: raw bytes forward, decoded reverse complement backward
     Hit hit = {0, 0, 0};
     uint64_t us = encode23_strict(r0, r1, r2), rs = revcomp23(us), a, b, c;

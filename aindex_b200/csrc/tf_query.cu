@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, Mphf
 // records, fingerprint / index record) and a CTA barrier between the first two.  Here every warp
 // owns a 3-slot ring of 32-query tiles (736 B) in shared memory that lane 0 fills with
 // cp.async.bulk (TMA, UBLKCP in SASS) two tiles ahead, completion signalled on one mbarrier per
-// slot: the query bytes are already on chip when a warp starts a tile, there is no CTA-wide
-// barrier, and the grid is sized to the resident CTAs of the 148 SMs (tiles are dealt round robin).
+// slot: the query bytes are already on chip when a warp starts a tile and there is no CTA-wide
+// barrier.
 constexpr int kStWarps = 8;
 constexpr int kStStages = 3;
 constexpr uint32_t kStTileBytes = 32u * 23u;  // 736 = 46 * 16: legal bulk-copy size, slots stay 16-byte aligned
@@ -89,53 +89,75 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
 }
 
+// tiles per warp and CTA: a CTA owns kStWarps * kStTilesPerWarp consecutive tiles (4096 queries), warp w takes
+// tiles w, w + 8, ...  Small enough that the hardware scheduler evens out SM speed differences (one wave of
+// resident CTAs per launch left a quarter of the warp slots idle at the tail), long enough that the two
+// exposed loads of the ring prologue are amortised.
+constexpr int kStTilesPerWarp = 16;
+constexpr int kStTilesPerCta = kStWarps * kStTilesPerWarp;
+
 template <int kMode, bool kCanon, int kMinBlocks>
 __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
-                                                                  uint64_t n_tiles, void *__restrict__ out) {
+                                                                              uint64_t n_tiles, void *__restrict__ out) {
     __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kStSlot];
     __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    const uint64_t total_warps = (uint64_t)gridDim.x * kStWarps;
-    const uint64_t gw = (uint64_t)blockIdx.x * kStWarps + wid;
+    __syncwarp();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;  // this warp's first tile
+    if (tile0 >= n_tiles) return;
+    const uint64_t left = n_tiles - tile0;                                // tiles from tile0 on
+    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
     const uint64_t policy = l2_policy_evict_first();
+    constexpr uint32_t kStride = kStWarps * kStTileBytes;                 // bytes between a warp's consecutive tiles
+    const uint8_t *src = recs + tile0 * kStTileBytes;                     // next tile to fetch
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStStages - 1; ++s) {
-            const uint64_t t = gw + (uint64_t)s * total_warps;
-            if (t < n_tiles) {
-                mbar_expect_tx(&bars[wid][s], kStTileBytes);
-                bulk_load(ring[wid][s], recs + t * kStTileBytes, kStTileBytes, &bars[wid][s], policy);
+            if ((uint32_t)s < my_tiles) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(kStTileBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(ring0 + (uint32_t)kStSlot * s), "l"(src + (uint64_t)kStride * s), "r"(kStTileBytes), "r"(bar0 + 8u * s), "l"(policy) : "memory");
             }
         }
     }
-    uint32_t it = 0, slot = 0, phase = 0;
-    for (uint64_t t = gw; t < n_tiles; t += total_warps, ++it) {
+    src += (uint64_t)kStride * (kStStages - 1);
+    uint64_t i = tile0 * 32u + lane;  // query index of this lane in the current tile
+    uint32_t slot = 0, phase = 0;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
         // refill the slot every lane finished reading in the previous iteration (the __syncwarp below)
-        const uint64_t tn = t + (uint64_t)(kStStages - 1) * total_warps;
-        if (lane == 0 && tn < n_tiles) {
+        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
             const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
-            mbar_expect_tx(&bars[wid][sn], kStTileBytes);
-            bulk_load(ring[wid][sn], recs + tn * kStTileBytes, kStTileBytes, &bars[wid][sn], policy);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
         }
-        mbar_wait(&bars[wid][slot], phase);
-        const uint32_t *tile = reinterpret_cast<const uint32_t *>(ring[wid][slot]);
+        src += kStride;
+        {
+            uint32_t done;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
+            } while (!done);
+        }
         const uint32_t base = lane * 23u;
-        const uint32_t w = base >> 2, sh = (base & 3u) * 8u;
-        uint32_t x0 = tile[w], x1 = tile[w + 1], x2 = tile[w + 2], x3 = tile[w + 3], x4 = tile[w + 4], x5 = tile[w + 5],
-                 x6 = tile[w + 6];
+        const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
+        uint32_t x0, x1, x2, x3, x4, x5, x6;
+        asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
+                     "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
+                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
         __syncwarp();
         uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
                  y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
         uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
                  r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
-        const uint64_t i = t * 32u + lane;
         query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
+        i += (uint64_t)kStWarps * 32u;
         if (++slot == kStStages) { slot = 0; phase ^= 1u; }
     }
 }
@@ -279,25 +301,21 @@ static int tf23_kernel_choice() {
     return e ? atoi(e) : 1;
 }
 
-// register budget of the streaming kernel: 6 resident CTAs (40 registers, a few spilled words) or
-// whatever ptxas picks (46 registers, 5 CTAs); AIX_TF23_MINBLOCKS selects for A/B runs
+// register budget of the streaming kernel: what ptxas picks (56 registers, 4 resident CTAs, no spills;
+// default) or 6 resident CTAs (40 registers, two spilled words).  The kernel is ALU-pipe bound, not
+// latency bound: the unconstrained build is 8 % faster (profiles/r01_tf23_sweep.txt).
+// AIX_TF23_MINBLOCKS selects for A/B runs.
 static int tf23_min_blocks() {
     const char *e = getenv("AIX_TF23_MINBLOCKS");
-    return e ? atoi(e) : 6;
+    return e ? atoi(e) : 1;
 }
 
 template <int kMode, bool kCanon, int kMinBlocks>
 static void launch_stream(const aix_ctx *ctx, cudaStream_t st, const Index23Dev &id, const MphfDev &md, const uint8_t *recs,
                           uint64_t n_tiles, void *out) {
-    static int per_sm = 0;
-    if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tf23_stream_kernel<kMode, kCanon, kMinBlocks>, kStWarps * 32, 0) != cudaSuccess || per_sm < 1) {
-            cudaGetLastError();
-            per_sm = 4;
-        }
-    }
-    uint64_t want = (n_tiles + kStWarps - 1) / kStWarps, cap = (uint64_t)ctx->sm_count * per_sm;
-    tf23_stream_kernel<kMode, kCanon, kMinBlocks><<<(unsigned)(want < cap ? want : cap), kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out);
+    (void)ctx;
+    const uint64_t grid = (n_tiles + kStTilesPerCta - 1) / kStTilesPerCta;
+    tf23_stream_kernel<kMode, kCanon, kMinBlocks><<<(unsigned)grid, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out);
 }
 
 
