@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -137,6 +138,33 @@ struct aix_ctx {
             return (ctx)->fail(AIX_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,      \
                                cudaGetErrorString(e__));                                         \
     } while (0)
+
+// AIX_TRACE=1: per-phase wall times of the multi-kernel host routines on stderr (synchronises the
+// stream at every mark, so only for diagnosis -- profiles/ keeps the outputs that DESIGN.md quotes)
+struct AixTrace {
+    bool on;
+    cudaStream_t st;
+    const char *what;
+    double t_last;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + ts.tv_nsec * 1e-9;
+    }
+    AixTrace(cudaStream_t s, const char *w) : on(getenv("AIX_TRACE") != nullptr), st(s), what(w), t_last(0) {
+        if (on) {
+            cudaStreamSynchronize(st);
+            t_last = now();
+        }
+    }
+    void mark(const char *phase) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        double t = now();
+        fprintf(stderr, "[aix trace] %s: %-70s %9.3f ms\n", what, phase, (t - t_last) * 1e3);
+        t_last = t;
+    }
+};
 
 static inline unsigned aix_grid(uint64_t work_items, unsigned block) {
     uint64_t g = (work_items + block - 1) / block;

@@ -176,19 +176,22 @@ __device__ __forceinline__ uint64_t bucket13(const MphfDev &m, const uint8_t *p)
     return h < AIX_TOTAL_13MERS ? h : kNoBucket;
 }
 
-// phase 0: occ[h]++ ; phase 1: tmp[off[h] + cursor[h]++] = i + 1 (if below cap[h] when clip)
-template <int K, int kPhase>
-__global__ void __launch_bounds__(256) positions_scan_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ reads,
+// phase 1: tmp[off[h] + cursor[h]++] = i + 1 (every occurrence, general path)
+// phase 2: the optimistic single pass -- positions[indices[h] + cursor[h]++] = i + 1 while the slot is
+//          below tf[h]; cursor[h] ends as the true occurrence count, so a bucket with more occurrences
+//          than tf is detected afterwards (classify) and only then the general path runs
+template <int K, int kPhase, typename F>
+__global__ void __launch_bounds__(256) positions_scan_kernel(Index23Dev ix, MphfDev m, F tf, const uint8_t *__restrict__ reads,
                                                            uint64_t start, uint64_t n_win_end /* len-k+1 */,
-                                                           uint32_t *__restrict__ occ_or_cursor,
+                                                           uint32_t *__restrict__ cursor,
                                                            const unsigned long long *__restrict__ off,
                                                            unsigned long long *__restrict__ dst) {
     uint64_t i = start + (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_win_end) return;
     uint64_t h = K == 23 ? bucket23(ix, m, reads + i) : bucket13(m, reads + i);
     if (h == kNoBucket) return;
-    uint32_t slot = atomicAdd(occ_or_cursor + h, 1u);
-    if (kPhase == 1) dst[off[h] + slot] = i + 1;
+    uint32_t slot = atomicAdd(cursor + h, 1u);
+    if (kPhase == 1 || (uint64_t)slot < tf(h)) dst[off[h] + slot] = i + 1;
 }
 
 // any bucket with more occurrences than tf?  also classifies buckets by size for the sort
@@ -373,6 +376,7 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
             return ctx->fail(AIX_ERR_CUDA, "positions build %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
         }                                                                                               \
     } while (0)
+    AixTrace trace(st, "positions build");
     const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile + 1;
     PB_CUDA(cudaMalloc(&indices, (n + 1) * 8));
     PB_CUDA(cudaMalloc(&tiles, n_tiles * 8));
@@ -387,22 +391,23 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         const uint64_t n_win_end = len - K + 1;
         if (start < n_win_end) {
             PB_CUDA(cudaMalloc(&occ, n * 4));
-            PB_CUDA(cudaMalloc(&cursor, n * 4));
             PB_CUDA(cudaMalloc(&medium, n * 4));
             PB_CUDA(cudaMalloc(&large, n * 4));
             PB_CUDA(cudaMalloc(&over, sizeof(int)));
             PB_CUDA(cudaMalloc(&cls, 2 * sizeof(unsigned int)));
             PB_CUDA(cudaMemsetAsync(occ, 0, n * 4, st));
-            PB_CUDA(cudaMemsetAsync(cursor, 0, n * 4, st));
             PB_CUDA(cudaMemsetAsync(over, 0, sizeof(int), st));
             PB_CUDA(cudaMemsetAsync(cls, 0, 2 * sizeof(unsigned int), st));
+            trace.mark("prefix sum + allocations");
             // grids are limited to 2^31-1 CTAs: scan the image in launches of <= 2^38 windows
             const uint64_t kLaunchWin = 1ull << 38;
+            // optimistic single pass straight into the final layout (occ doubles as the cursor)
             for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
                 const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
-                positions_scan_kernel<K, 0><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, reads_dev, w0, w1, occ, nullptr, nullptr);
+                positions_scan_kernel<K, 2><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, tf, reads_dev, w0, w1, occ, indices, positions);
                 ctx->launches++;
             }
+            trace.mark("scatter pass (lookup + cursor atomic + 8-byte store per window)");
             classify_kernel<<<aix_grid(n, 256), 256, 0, st>>>(tf, occ, n, over, medium, large, cls, kSmallMax, kMediumMax);
             ctx->launches++;
             int h_over = 0;
@@ -410,9 +415,11 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
             PB_CUDA(cudaMemcpyAsync(&h_over, over, sizeof(int), cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaMemcpyAsync(h_cls, cls, sizeof h_cls, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
+            trace.mark("classify");
             unsigned long long *data = positions;
             const unsigned long long *off = indices;
-            if (h_over) {  // some bucket overflows its tf: sort everything aside, then clip
+            if (h_over) {  // some bucket overflows its tf: scatter everything aside, sort, then clip
+                PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
                 PB_CUDA(cudaMalloc(&tmp_off, (n + 1) * 8));
                 rc = exclusive_scan(ctx, st, TfFromU32{occ}, n, tmp_off, tiles);
                 if (rc != AIX_OK) { cleanup(); return rc; }
@@ -420,13 +427,16 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
                 PB_CUDA(cudaMemcpyAsync(&tmp_total, tmp_off + n, 8, cudaMemcpyDeviceToHost, st));
                 PB_CUDA(cudaStreamSynchronize(st));
                 PB_CUDA(cudaMalloc(&tmp, (tmp_total ? tmp_total : 1) * 8));
+                PB_CUDA(cudaMalloc(&cursor, n * 4));
+                PB_CUDA(cudaMemsetAsync(cursor, 0, n * 4, st));
                 data = tmp;
                 off = tmp_off;
-            }
-            for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
-                const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
-                positions_scan_kernel<K, 1><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, reads_dev, w0, w1, cursor, off, data);
-                ctx->launches++;
+                for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
+                    const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
+                    positions_scan_kernel<K, 1><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, tf, reads_dev, w0, w1, cursor, off, data);
+                    ctx->launches++;
+                }
+                trace.mark("general path: second scatter");
             }
             sort_small_kernel<<<aix_grid(n, 256), 256, 0, st>>>(data, off, occ, n, kSmallMax);
             ctx->launches++;
@@ -462,11 +472,13 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
                 clip_copy_kernel<<<aix_grid(n, 256), 256, 0, st>>>(tf, tmp, tmp_off, occ, indices, n, positions);
                 ctx->launches++;
             }
+            trace.mark("per-bucket sort (+ clip)");
         }
     }
     PB_CUDA(cudaStreamSynchronize(st));
 #undef PB_CUDA
     cleanup_tmp();
+    trace.mark("free scratch");
     *indices_dev = indices;
     *positions_dev = positions;
     *total_out = total;

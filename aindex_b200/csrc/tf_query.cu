@@ -231,6 +231,58 @@ __device__ __forceinline__ uint32_t comp13_char(uint32_t c) {
     return c == 'A' ? 'T' : (c == 'T' ? 'A' : (c == 'G' ? 'C' : (c == 'C' ? 'G' : c)));
 }
 
+// one 13-mer query; w0 = bytes 0..7, w1 = bytes 8..12 of the record (zero padded), len = record length
+template <int kMode>
+__device__ __forceinline__ void query13(const MphfDev &m, const uint64_t *__restrict__ tf_mphf, const uint64_t *__restrict__ tf_direct,
+                                        uint64_t w0, uint64_t w1, uint32_t len, uint64_t i, void *__restrict__ out) {
+    // SIMD encode + validity (upper-case ACGT only), as encode_validate23
+    const uint32_t a[4] = {(uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)};
+    uint32_t p[4], bad = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t c4 = ((a[j] >> 1) ^ (a[j] >> 2)) & 0x03030303u;
+        p[j] = j == 3 ? (c4 & 3u) : ((c4 * 0x40100401u) >> 24);
+        const uint32_t diff = expect_acgt4(c4) ^ a[j];
+        bad |= j == 3 ? (diff & 0xFFu) : diff;
+    }
+    const bool valid = len == 13u && bad == 0;
+    const uint32_t v = (p[0] << 18) | (p[1] << 10) | (p[2] << 2) | p[3];
+    if (kMode == AIX_Q_TF) {
+        // :482-503 / :938-980: len == 13 and upper-case ACGT only, value narrowed to u32
+        ((uint32_t *)out)[i] = valid ? (uint32_t)__ldg(tf_direct + v) : 0u;
+        return;
+    }
+    uint64_t fwd = 0, rev = 0;
+    if (len == 13u) {
+        if (valid) {
+            fwd = __ldg(tf_direct + v);
+            rev = __ldg(tf_direct + revcomp13(v));
+        } else {
+            // :533-542: no validity check -- the raw bytes are hashed; an id of 4^13 (possible
+            // for non-keys) is out of bounds in the reference and defined as 0 here
+            uint64_t x0 = 0, x1 = 0, ha, hb, hc;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+                const int k = 12 - j;  // python_wrapper.cpp:505-517: reverse, complement ACGT, keep the rest
+                const uint64_t g = comp13_char((uint32_t)((k < 8 ? w0 >> (8 * k) : w1 >> (8 * (k - 8))) & 0xFFu));
+                if (j < 8) x0 |= g << (8 * j);
+                else x1 |= g << (8 * (j - 8));
+            }
+            jenkins_short(m.seed, w0, w1, 0, 13u, ha, hb, hc);
+            uint64_t id = mphf_eval(m, ha, hb, hc);
+            fwd = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
+            jenkins_short(m.seed, x0, x1, 0, 13u, ha, hb, hc);
+            id = mphf_eval(m, ha, hb, hc);
+            rev = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
+        }
+    }
+    if (kMode == AIX_Q_TOTAL) ((uint64_t *)out)[i] = fwd + rev;
+    else {
+        ((uint64_t *)out)[2 * i] = fwd;
+        ((uint64_t *)out)[2 * i + 1] = rev;
+    }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kQBlock) tf13_kernel(MphfDev m, const uint64_t *__restrict__ tf_mphf,
                                                      const uint64_t *__restrict__ tf_direct, const uint8_t *__restrict__ recs,
@@ -241,50 +293,77 @@ __global__ void __launch_bounds__(kQBlock) tf13_kernel(MphfDev m, const uint64_t
     uint32_t len = lens ? lens[i] : stride;
     if (len > stride) len = stride;
     const uint8_t *p = recs + i * stride;
-    uint32_t ch[13];
-    bool valid = len == 13u;
-    uint32_t v = 0;
+    uint64_t w0 = 0, w1 = 0;
     if (len == 13u) {
 #pragma unroll
         for (int j = 0; j < 13; ++j) {
-            ch[j] = __ldg(p + j);
-            valid = valid && is_acgt_upper(ch[j]);
-            v = (v << 2) | base_code_strict(ch[j]);
+            const uint64_t ch = __ldg(p + j);
+            if (j < 8) w0 |= ch << (8 * j);
+            else w1 |= ch << (8 * (j - 8));
         }
     }
-    if (kMode == AIX_Q_TF) {
-        // :482-503 / :938-980: len == 13 and upper-case ACGT only, value narrowed to u32
-        ((uint32_t *)out)[i] = valid ? (uint32_t)tf_direct[v] : 0u;
-        return;
-    }
-    uint64_t fwd = 0, rev = 0;
-    if (len == 13u) {
-        if (valid) {
-            fwd = tf_direct[v];
-            rev = tf_direct[revcomp13(v)];
-        } else {
-            // :533-542: no validity check -- the raw bytes are hashed; an id of 4^13 (possible
-            // for non-keys) is out of bounds in the reference and defined as 0 here
-            uint64_t w0 = 0, w1 = 0, x0 = 0, x1 = 0, a, b, c;
+    query13<kMode>(m, tf_mphf, tf_direct, w0, w1, len, i, out);
+}
+
+// K4 streaming form for uint8[q, 13] batches: the TMA ring of tf23_stream_kernel with 416-byte tiles
+// (32 x 13 = 26 x 16).  The per-query work is an encode and one 8-byte gather, so staging the records
+// (13 single-byte loads per thread in the generic kernel) is what bounds it.
+constexpr uint32_t kSt13TileBytes = 32u * 13u;
+constexpr int kSt13Slot = 448;
+
+template <int kMode>
+__global__ void __launch_bounds__(kStWarps * 32) tf13_stream_kernel(MphfDev m, const uint64_t *__restrict__ tf_mphf,
+                                                                  const uint64_t *__restrict__ tf_direct,
+                                                                  const uint8_t *__restrict__ recs, uint64_t n_tiles,
+                                                                  void *__restrict__ out) {
+    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kSt13Slot];
+    __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
+    if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < 13; ++j) {
-                uint64_t f = ch[j], g = comp13_char(ch[12 - j]);
-                if (j < 8) { w0 |= f << (8 * j); x0 |= g << (8 * j); }
-                else { w1 |= f << (8 * (j - 8)); x1 |= g << (8 * (j - 8)); }
+        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;
+    if (tile0 >= n_tiles) return;
+    const uint64_t left = n_tiles - tile0;
+    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
+    const uint64_t policy = l2_policy_evict_first();
+    constexpr uint32_t kStride = kStWarps * kSt13TileBytes;
+    const uint8_t *src = recs + tile0 * kSt13TileBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStStages - 1; ++s)
+            if ((uint32_t)s < my_tiles) {
+                mbar_expect_tx(&bars[wid][s], kSt13TileBytes);
+                bulk_load(&ring[wid][s][0], src + (uint64_t)kStride * s, kSt13TileBytes, &bars[wid][s], policy);
             }
-            jenkins_short(m.seed, w0, w1, 0, 13u, a, b, c);
-            uint64_t id = mphf_eval(m, a, b, c);
-            fwd = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
-            jenkins_short(m.seed, x0, x1, 0, 13u, a, b, c);
-            id = mphf_eval(m, a, b, c);
-            rev = id < AIX_TOTAL_13MERS ? tf_mphf[id] : 0;
+    }
+    src += (uint64_t)kStride * (kStStages - 1);
+    uint64_t i = tile0 * 32u + lane;
+    uint32_t slot = 0, phase = 0;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
+            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
+            mbar_expect_tx(&bars[wid][sn], kSt13TileBytes);
+            bulk_load(&ring[wid][sn][0], src, kSt13TileBytes, &bars[wid][sn], policy);
         }
+        src += kStride;
+        mbar_wait(&bars[wid][slot], phase);
+        const uint32_t base = lane * 13u;
+        const uint32_t *t = reinterpret_cast<const uint32_t *>(&ring[wid][slot][base & ~3u]);
+        const uint32_t sh = (base & 3u) * 8u;
+        const uint32_t x0 = t[0], x1 = t[1], x2 = t[2], x3 = t[3];  // bytes base .. base+12 end inside the fourth word
+        __syncwarp();
+        const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
+                       y3 = (x3 >> sh) & 0xFFu;
+        query13<kMode>(m, tf_mphf, tf_direct, ((uint64_t)y1 << 32) | y0, ((uint64_t)y3 << 32) | y2, 13u, i, out);
+        i += (uint64_t)kStWarps * 32u;
+        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
     }
-    if (kMode == AIX_Q_TOTAL) ((uint64_t *)out)[i] = fwd + rev;
-    else {
-        ((uint64_t *)out)[2 * i] = fwd;
-        ((uint64_t *)out)[2 * i + 1] = rev;
-    }
+    (void)ring0; (void)bar0;
 }
 
 static size_t out_bytes23(int mode) {
@@ -366,15 +445,31 @@ int launch_tf23(aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint
     return AIX_OK;
 }
 
+template <int kMode>
+static void launch13_mode(const aix_index13 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
+                          uint64_t q, void *out, size_t out_bytes) {
+    MphfDev md = ix->mphf->dev();
+    const bool fixed = (stride == 13 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
+    if (fixed && tf23_kernel_choice() == 1 && q >= 32) {
+        const uint64_t n_tiles = q / 32;
+        const uint64_t grid = (n_tiles + kStTilesPerCta - 1) / kStTilesPerCta;
+        tf13_stream_kernel<kMode><<<(unsigned)grid, kStWarps * 32, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, n_tiles, out);
+        const uint64_t done = n_tiles * 32;
+        if (done == q) return;
+        recs += done * 13;
+        out = (char *)out + done * out_bytes;
+        q -= done;
+    }
+    tf13_kernel<kMode><<<aix_grid(q, kQBlock), kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out);
+}
+
 int launch_tf13(aix_ctx *ctx, const aix_index13 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
                 const uint8_t *lens, uint64_t q, int mode, void *out) {
     if (q == 0) return AIX_OK;
-    MphfDev md = ix->mphf->dev();
-    unsigned grid = aix_grid(q, kQBlock);
     switch (mode) {
-        case AIX_Q_TF: tf13_kernel<AIX_Q_TF><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
-        case AIX_Q_TOTAL: tf13_kernel<AIX_Q_TOTAL><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
-        case AIX_Q_BOTH: tf13_kernel<AIX_Q_BOTH><<<grid, kQBlock, 0, st>>>(md, ix->tf_mphf_dev, ix->tf_direct_dev, recs, stride, lens, q, out); break;
+        case AIX_Q_TF: launch13_mode<AIX_Q_TF>(ix, st, recs, stride, lens, q, out, 4); break;
+        case AIX_Q_TOTAL: launch13_mode<AIX_Q_TOTAL>(ix, st, recs, stride, lens, q, out, 8); break;
+        case AIX_Q_BOTH: launch13_mode<AIX_Q_BOTH>(ix, st, recs, stride, lens, q, out, 16); break;
         default: return ctx->fail(AIX_ERR_ARG, "unknown 13-mer query mode %d", mode);
     }
     AIX_LAUNCH_CHECK(ctx);

@@ -362,6 +362,7 @@ def main():
     torch.cuda.set_device(dev)
     ctx = capi.Context(0)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    torch.cuda.set_stream(stream)  # one stream for torch and the library: allocator reuse stays ordered
     lines = []
     for name in args.configs.split(","):
         fn = {"c1": run_c1, "c4": run_c4, "c5": run_c5}[name.strip().lower()]

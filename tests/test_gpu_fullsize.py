@@ -1,0 +1,186 @@
+"""GPU parity at BASELINE.json's full sizes, through size-independent properties (bit-exact integer
+work) plus the compiled reference on bounded samples.  The generators are bench.py's, so these are
+the very inputs the headline numbers are measured on.
+
+  C2  100 M random + 20 M half-hit 23-mer queries on the 50 M-key index
+  C3  one GPU's shard of the 13-mer counting job: 25 M x 150 bp reads (3.45 G windows)
+  C4  coverage of 1 M x 10 kb sequences;  C5  positions index over 50 M reads (profiles/bench_configs.py)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "profiles"))
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import bench
+    from aindex_b200 import capi
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    ctx = capi.Context(0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    # torch work (data generation, checks) and the library's kernels share ONE stream: the caching
+    # allocator hands freed blocks out again in stream order, so a second stream would race with it
+    prev = torch.cuda.current_stream(dev)
+    torch.cuda.set_stream(stream)
+    yield types.SimpleNamespace(torch=torch, bench=bench, capi=capi, dev=dev, ctx=ctx, stream=stream)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(prev)
+    ctx.close()
+    torch.cuda.empty_cache()
+
+
+def _revcomp_records(torch, q):
+    comp = torch.zeros(256, device=q.device, dtype=torch.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    return comp[q.long()].flip(1).contiguous()
+
+
+def test_c2_full_size_properties(env):
+    t, capi, ctx = env.torch, env.capi, env.ctx
+    reads = env.bench.make_reads(t, env.dev, 50_000_000, 10_000_000, 150, 1, 2)
+    mphf, index, checker_t, tf_t, n = env.bench.build_index(t, capi, ctx, reads)
+    assert index.info["canonical_only"] is True and 49_000_000 < n < 50_000_001
+    # checksum of checksums: querying every stored k-mer returns the tf array, in order
+    keys = t.empty((n, 23), device=env.dev, dtype=t.uint8)
+    lib = capi.lib()
+    # decode on the device through the C-ABI host path would copy 1.1 GB: build ASCII with torch instead
+    lut = t.tensor(list(b"ACGT"), device=env.dev, dtype=t.uint8)
+    for j in range(23):
+        keys[:, j] = lut[(checker_t >> (2 * (22 - j))) & 3]
+    out = t.empty(n, device=env.dev, dtype=t.int32)
+    index.query_dev(keys.data_ptr(), 23, None, n, capi.Q_TF, out.data_ptr())
+    ctx.sync()
+    assert t.equal(out, tf_t)
+    assert int(tf_t.sum().item()) == 10_000_000 * 128  # every window of every read is counted once
+    kid = t.empty(n, device=env.dev, dtype=t.int64)
+    index.query_dev(keys.data_ptr(), 23, None, n, capi.Q_PFID, kid.data_ptr())
+    ctx.sync()
+    assert t.equal(kid, t.arange(n, device=env.dev))  # the MPHF is minimal and perfect on its keys
+    del keys, kid, out
+    # Q2: half substrings of the reads (either strand), half random
+    q2 = t.cat([env.bench.make_hit_queries(t, env.dev, reads, 10_000_000, 4), env.bench.make_queries(t, env.dev, 10_000_000, 5)])
+    del reads
+    t.cuda.empty_cache()
+    o2 = t.empty(q2.shape[0], device=env.dev, dtype=t.int32)
+    index.query_dev(q2.data_ptr(), 23, None, q2.shape[0], capi.Q_TF, o2.data_ptr())
+    ctx.sync()
+    assert bool((o2[:10_000_000] > 0).all().item())          # a window of a read is always in the index
+    # Q1: 100 M uniform-random queries; reverse-complement invariance, total == 2 x tf, batch splitting
+    q = env.bench.make_queries(t, env.dev, 100_000_000, 3)
+    o = t.empty(100_000_000, device=env.dev, dtype=t.int32)
+    index.query_dev(q.data_ptr(), 23, None, 100_000_000, capi.Q_TF, o.data_ptr())
+    ctx.sync()
+    for lo in range(0, 100_000_000, 25_000_000):
+        rc = _revcomp_records(t, q[lo:lo + 25_000_000])
+        orc = t.empty(25_000_000, device=env.dev, dtype=t.int32)
+        index.query_dev(rc.data_ptr(), 23, None, 25_000_000, capi.Q_TF, orc.data_ptr())
+        ctx.sync()
+        assert t.equal(orc, o[lo:lo + 25_000_000])
+        del rc, orc
+    tot = t.empty(20_000_000, device=env.dev, dtype=t.int64)
+    index.query_dev(q2.data_ptr(), 23, None, 20_000_000, capi.Q_TOTAL, tot.data_ptr())
+    ctx.sync()
+    assert t.equal(tot, 2 * o2.to(t.int64))
+    # an odd split point (not a multiple of the 32-query tile, unaligned sub-batch start) gives the same answers
+    cut = 33_333_331
+    o_b = t.empty(100_000_000 - cut, device=env.dev, dtype=t.int32)
+    index.query_dev(q.data_ptr() + cut * 23, 23, None, 100_000_000 - cut, capi.Q_TF, o_b.data_ptr())
+    ctx.sync()
+    assert t.equal(o_b, o[cut:])
+    # the host-buffer C-ABI call and the unmodified reference on a sample
+    qs = q[:3_000_000].cpu().numpy()
+    assert np.array_equal(index.query(qs), o[:3_000_000].cpu().numpy().view(np.uint32))
+    import tempfile, shutil
+    tmp = tempfile.mkdtemp(prefix="aix_t_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        prefix = env.bench.write_index_files(tmp, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
+        mix = np.concatenate([qs[:1_000_000], q2[:1_000_000].cpu().numpy(), q2[-1_000_000:].cpu().numpy()])
+        kind, secs, res = env.bench.cpu_query_runs(prefix, mix, os.cpu_count() or 1, 1)
+        assert np.array_equal(res, index.query(mix)), f"differs from the CPU {kind}"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_c3_full_size_shard_properties(env):
+    t, capi, ctx = env.torch, env.capi, env.ctx
+    lib = capi.lib()
+    n_reads = 25_000_000
+    reads = env.bench.make_reads(t, env.dev, 100_000_000, n_reads, 150, 11, 12)
+    flat = reads.reshape(-1)
+
+    def count(lo, hi):
+        ctx.check(lib.aix_count13_begin(ctx.handle))
+        ctx.check(lib.aix_count13_add_dev(ctx.handle, flat.data_ptr() + lo * 151, (hi - lo) * 151, capi.FMT_PLAIN))
+        ctx.check(lib.aix_count13_flush(ctx.handle))
+        st = capi.CountStats()
+        ctx.check(lib.aix_count13_stats(ctx.handle, st))
+        h = env.bench._wrap_device_i64(t, lib.aix_count13_hist_dev(ctx.handle), 1 << 26, env.dev).clone()
+        return h, st.as_dict()
+
+    whole, st = count(0, n_reads)
+    assert st == {"sequences": n_reads, "windows": n_reads * 138, "valid": n_reads * 138, "invalid": 0}
+    assert int(whole.sum().item()) == n_reads * 138
+    # linearity: the histogram of the shard is the sum of the histograms of its parts (any cut at a line start)
+    cut = 9_999_937
+    a, sa = count(0, cut)
+    b, sb = count(cut, n_reads)
+    assert t.equal(a + b, whole) and sa["valid"] + sb["valid"] == st["valid"]
+    # reverse-complementing every read reverse-complements the histogram: hist'[rc(v)] == hist[v]
+    v = t.arange(1 << 26, device=env.dev, dtype=t.int64)
+    rcv = t.zeros_like(v)
+    for j in range(13):
+        rcv |= (3 - ((v >> (2 * j)) & 3)) << (2 * (12 - j))
+    sub = reads[:2_000_000]
+    comp = t.zeros(256, device=env.dev, dtype=t.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    rsub = sub.clone()
+    rsub[:, :150] = comp[sub[:, :150].long()].flip(1)
+    ctx.check(lib.aix_count13_begin(ctx.handle))
+    ctx.check(lib.aix_count13_add_dev(ctx.handle, rsub.data_ptr(), rsub.numel(), capi.FMT_PLAIN))
+    ctx.check(lib.aix_count13_flush(ctx.handle))
+    hr = env.bench._wrap_device_i64(t, lib.aix_count13_hist_dev(ctx.handle), 1 << 26, env.dev).clone()
+    hs, _ = count(0, 2_000_000)
+    assert t.equal(hr[rcv], hs)
+    ctx.check(lib.aix_count13_end(ctx.handle))
+    # the reference binary on a 300 k-read sample (MPHF-order tf.bin, 512 MiB): byte-equal
+    pf = os.path.join(ROOT, "oracle", "_ref", "data", "all_13mers.pf")
+    if os.path.exists(pf) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "count_kmers13")):
+        import tempfile, shutil
+        tmp = tempfile.mkdtemp(prefix="aix_t_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            sample = reads[:300_000].cpu().numpy()
+            kind, secs, nk, tf_ref, _ = env.bench.cpu_count_run(sample, os.cpu_count() or 1, tmp)
+            m13 = capi.Mphf.load(ctx, pf)
+            tf_gpu, stats = ctx.count13(m13, sample.reshape(-1), capi.FMT_PLAIN)
+            assert np.array_equal(tf_ref, tf_gpu) and stats["valid"] == nk
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+@pytest.mark.parametrize("config", ["c4", "c5"])
+def test_c4_c5_full_size(env, config):
+    """profiles/bench_configs.py at scale 1.0: every full-size property and every comparison with the
+    oracle / the compiled reference must hold (the timings it also takes are not asserted)."""
+    import bench_configs
+    env.torch.cuda.empty_cache()
+    args = types.SimpleNamespace(scale=1.0)
+    line = {"c4": bench_configs.run_c4, "c5": bench_configs.run_c5}[config](env.ctx, env.stream, env.dev, args)
+    assert all(line["checks"].values()), line["checks"]
+    cb = line["cpu_baseline"]
+    if cb is not None:
+        assert all(v for k, v in cb.items() if k.endswith("equal") or k.startswith("results_equal") or "_equal" in k), cb
+    if "e2e" in line:
+        assert line["e2e"]["matches_device_path"]
+    env.torch.cuda.empty_cache()

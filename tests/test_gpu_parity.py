@@ -375,6 +375,17 @@ def test_tf13_vs_oracle_odd_queries(capi, oracle, ctx, m13, g13):
     recs, lens = oracle.pack_queries(q, stride=16)
     for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH)):
         assert np.array_equal(ix.query(q, mode), oix.batch(recs, lens, omode))
+    # uint8[q, 13] batches take the TMA-ring kernel: ragged sizes around the 32-query tile, odd bytes included
+    for nq in (1, 31, 32, 33, 4095, 4096, 4097, 10007):
+        r13 = rng.choice(ACGT, size=(nq, 13))
+        hit = rng.random(nq) < 0.5
+        pd = g13["plain_data"]
+        st = rng.integers(0, pd.size - 13, size=int(hit.sum()))
+        r13[hit] = pd[st[:, None] + np.arange(13)[None, :]]  # windows of the counted reads (some span a newline)
+        odd = rng.random(nq) < 0.1
+        r13[odd, rng.integers(0, 13, size=int(odd.sum()))] = rng.choice(np.frombuffer(b"NnacgtX~\x00\xff", dtype=np.uint8), size=int(odd.sum()))
+        for mode, omode in ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH)):
+            assert np.array_equal(ix.query(r13, mode), oix.batch(r13, None, omode)), f"13-mer fixed mode {mode} nq {nq}"
     # coverage, k = 13 (aindex.py:314-322 over get_tf_value_13mer)
     seq = g13["plain_data"][:3000].tobytes().replace(b"\n", b"")
     for cutoff in (0, 2):
