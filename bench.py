@@ -399,7 +399,7 @@ def run_ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = float(np.mean(kernel_ms))
     achieved = args.queries * Q1_BYTES_PER_QUERY / (k_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tf23_fixed_kernel<AIX_Q_TF, canonical>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "tf23_stream_kernel<AIX_Q_TF, canonical>", "achieved": achieved,
                 "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_unit": Q1_BYTES_PER_QUERY, "units_per_launch": args.queries, "kernel_ms": k_ms,

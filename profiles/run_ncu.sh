@@ -14,7 +14,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --count-rea
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:tf23_fixed -s 3 -c 1 -o gpurun_out/${TAG}_tf23 -f $CMD > gpurun_out/${TAG}_ncu_tf23.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tf23_stream -s 3 -c 1 -o gpurun_out/${TAG}_tf23 -f $CMD > gpurun_out/${TAG}_ncu_tf23.log 2>&1
 $CMD > gpurun_out/${TAG}_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:count13_kernel -s 8 -c 4 -o gpurun_out/${TAG}_count13 -f $CMD > gpurun_out/${TAG}_ncu_count13.log 2>&1
 ls -la gpurun_out/
