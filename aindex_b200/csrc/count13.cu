@@ -325,6 +325,185 @@ __global__ void __launch_bounds__(kCntBlock) fastq_mask_kernel(uint8_t *__restri
     }
 }
 
+
+// ---- FASTA: concatenate the lines of a record, drop header lines (count_kmers13.cpp:211-235) ----------
+// Output byte stream (counted as plain text afterwards): sequence-line bytes without their newlines, and
+// one '\n' for every header line (it ends the record before it; empty records are empty lines, which the
+// plain reader skips).  A byte is a line start iff the byte before it is '\n' (or it is the first byte);
+// a line is a header iff its first byte is '>'.  Three kernels: per-tile summary (header state leaving
+// the tile, kept-byte count for either entering state), one single-block scan over tiles, compaction.
+__device__ __forceinline__ uint32_t last_nonzero_scan_warp(uint32_t v) {  // inclusive: last non-zero value at or before the lane
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= (unsigned)o && v == 0) v = y;
+    }
+    return v;
+}
+
+// per-thread walk over its 16 bytes.  state_in: 0 sequence line, 1 header line.  Returns the state after
+// the last byte; *ls = 2 + header flag of the last line start in the chunk (0 if none); kept bytes are
+// appended to out (when not null) and counted.
+__device__ __forceinline__ uint32_t fasta_walk16(uint4 own, uint32_t n_bytes, uint32_t prev, uint32_t state_in, uint32_t *ls,
+                                                 uint32_t *count, uint8_t *out) {
+    const uint32_t w[4] = {own.x, own.y, own.z, own.w};
+    uint32_t state = state_in, last = 0, cnt = 0;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        if ((uint32_t)b < n_bytes) {
+            const uint32_t c = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+            const bool line_start = prev == '\n';
+            if (line_start) {
+                state = c == '>' ? 1u : 0u;
+                last = 2u + state;
+            }
+            if (state) {
+                if (line_start) {
+                    if (out) out[cnt] = '\n';
+                    ++cnt;
+                }
+            } else if (c != '\n') {
+                if (out) out[cnt] = (uint8_t)c;
+                ++cnt;
+            }
+            prev = c;
+        }
+    }
+    *ls = last;
+    *count = cnt;
+    return state;
+}
+
+// state entering every thread relative to the tile: 0 = inherits the tile's entering state, else 2 + header flag
+__device__ __forceinline__ uint32_t fasta_block_prefix_state(uint32_t my_last, uint32_t *smem /* >= 32 */, uint32_t *tile_last) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t incl = last_nonzero_scan_warp(my_last);
+    if (lane == 31) smem[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < nw ? smem[lane] : 0u;
+        t = last_nonzero_scan_warp(t);
+        smem[lane] = t;
+    }
+    __syncthreads();
+    uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0) excl = 0;
+    const uint32_t warp_in = wid ? smem[wid - 1] : 0u;
+    *tile_last = smem[nw - 1];
+    __syncthreads();
+    return excl ? excl : warp_in;
+}
+
+__device__ __forceinline__ uint32_t fasta_prev_byte(const uint8_t *base, uint64_t pos) { return pos ? base[pos - 1] : (uint32_t)'\n'; }
+
+struct FastaTile {
+    uint32_t last;   // 0: no line start in the tile, else 2 + header flag of its last line start
+    uint32_t cnt[2];  // kept bytes if the tile is entered in state 0 / 1
+};
+
+__global__ void __launch_bounds__(kCntBlock) fasta_summary_kernel(const uint8_t *__restrict__ base, uint64_t len,
+                                                                FastaTile *__restrict__ tiles) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t sums[2];
+    if (threadIdx.x < 2) sums[threadIdx.x] = 0;
+    const uint64_t pos = ((uint64_t)blockIdx.x * kCntBlock + threadIdx.x) * 16;
+    const uint4 own = load_own16(base, pos, len);
+    const uint32_t nb = pos < len ? (uint32_t)(len - pos < 16 ? len - pos : 16) : 0u;
+    const uint32_t prev = pos < len ? fasta_prev_byte(base, pos) : 0u;
+    uint32_t ls0, ls1, c0, c1;
+    fasta_walk16(own, nb, prev, 0u, &ls0, &c0, nullptr);
+    fasta_walk16(own, nb, prev, 1u, &ls1, &c1, nullptr);  // ls1 == ls0: line starts do not depend on the state
+    uint32_t tile_last;
+    const uint32_t in = fasta_block_prefix_state(ls0, sm, &tile_last);
+    // entered through an earlier line start of this tile: the count is fixed; otherwise it depends on the tile's state
+    const uint32_t k0 = in ? ((in & 1u) ? c1 : c0) : c0, k1 = in ? ((in & 1u) ? c1 : c0) : c1;
+    const uint32_t w0 = __reduce_add_sync(0xFFFFFFFFu, k0), w1 = __reduce_add_sync(0xFFFFFFFFu, k1);
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(&sums[0], w0);
+        atomicAdd(&sums[1], w1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        FastaTile t;
+        t.last = tile_last; t.cnt[0] = sums[0]; t.cnt[1] = sums[1];
+        tiles[blockIdx.x] = t;
+    }
+}
+
+// single block: entering state and output offset of every tile; total[0] = kept bytes
+__global__ void fasta_scan_kernel(const FastaTile *__restrict__ tiles, uint32_t n_tiles, uint32_t *__restrict__ tile_state,
+                                  unsigned long long *__restrict__ tile_off, unsigned long long *__restrict__ total) {
+    __shared__ uint32_t sm[33];
+    __shared__ unsigned long long carry_off;
+    __shared__ uint32_t carry_state;
+    if (threadIdx.x == 0) { carry_off = 0; carry_state = 0; }  // the file starts on a sequence-or-header line start
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ unsigned long long wsum[33];
+    for (uint32_t i0 = 0; i0 < n_tiles; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        FastaTile t = {0u, {0u, 0u}};
+        if (i < n_tiles) t = tiles[i];
+        uint32_t tile_last;
+        uint32_t in = fasta_block_prefix_state(t.last, sm, &tile_last);
+        const uint32_t st = in ? (in & 1u) : carry_state;
+        unsigned long long c = i < n_tiles ? t.cnt[st] : 0ull, x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long v = lane < nw ? wsum[lane] : 0ull;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= (unsigned)o) v += y;
+            }
+            wsum[lane] = v;
+        }
+        __syncthreads();
+        const unsigned long long off = carry_off + (wid ? wsum[wid - 1] : 0ull) + x - c;
+        if (i < n_tiles) {
+            tile_state[i] = st;
+            tile_off[i] = off;
+        }
+        const unsigned long long batch_total = wsum[nw - 1];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry_off += batch_total;
+            if (tile_last) carry_state = tile_last & 1u;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = carry_off;
+}
+
+__global__ void __launch_bounds__(kCntBlock) fasta_compact_kernel(const uint8_t *__restrict__ base, uint64_t len,
+                                                                const uint32_t *__restrict__ tile_state,
+                                                                const unsigned long long *__restrict__ tile_off,
+                                                                uint8_t *__restrict__ out) {
+    __shared__ uint32_t sm[33];
+    const uint64_t pos = ((uint64_t)blockIdx.x * kCntBlock + threadIdx.x) * 16;
+    const uint4 own = load_own16(base, pos, len);
+    const uint32_t nb = pos < len ? (uint32_t)(len - pos < 16 ? len - pos : 16) : 0u;
+    const uint32_t prev = pos < len ? fasta_prev_byte(base, pos) : 0u;
+    uint32_t ls, cnt;
+    fasta_walk16(own, nb, prev, 0u, &ls, &cnt, nullptr);
+    uint32_t tile_last;
+    const uint32_t in = fasta_block_prefix_state(ls, sm, &tile_last);
+    const uint32_t st = in ? (in & 1u) : tile_state[blockIdx.x];
+    uint8_t local[16];
+    fasta_walk16(own, nb, prev, st, &ls, &cnt, local);
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(cnt, sm, total);
+    uint8_t *dst = out + tile_off[blockIdx.x] + ex;
+    for (uint32_t b = 0; b < cnt; ++b) dst[b] = local[b];
+}
+
 }  // namespace aix
 
 using namespace aix;
@@ -390,28 +569,41 @@ static int launch_count(aix_ctx *ctx, cudaStream_t st, const uint8_t *base, uint
     return AIX_OK;
 }
 
-// host-side FASTA normalisation to plain text (one record per line).  Parsing only; the
-// counting itself stays on the device.  TODO(round 2): device stream compaction.
-static void fasta_to_plain(const uint8_t *bytes, uint64_t len, std::vector<uint8_t> &out) {
-    out.clear();
-    out.reserve(len + 1);
-    uint64_t pos = 0;
-    bool open = false;
-    while (pos < len) {
-        const uint8_t *nl = (const uint8_t *)memchr(bytes + pos, '\n', len - pos);
-        uint64_t e = nl ? (uint64_t)(nl - bytes) : len;
-        if (e > pos) {
-            if (bytes[pos] == '>') {
-                if (open) out.push_back('\n');
-                open = false;
-            } else {
-                out.insert(out.end(), bytes + pos, bytes + e);
-                open = true;
-            }
-        }
-        pos = e + 1;
+// FASTA image in HBM (16-byte aligned) -> plain-text image in *out_dev (caller frees), *out_len bytes
+static int fasta_compact_dev(aix_ctx *ctx, cudaStream_t st, const uint8_t *in_dev, uint64_t len, uint8_t **out_dev, uint64_t *out_len) {
+    *out_dev = nullptr;
+    *out_len = 0;
+    const uint32_t n_tiles = (uint32_t)((len + kTileBytes - 1) / kTileBytes);
+    FastaTile *tiles = nullptr;
+    uint32_t *tstate = nullptr;
+    unsigned long long *toff = nullptr, *total = nullptr;
+    uint8_t *out = nullptr;
+    auto cleanup = [&]() { cudaFree(tiles); cudaFree(tstate); cudaFree(toff); cudaFree(total); };
+    cudaError_t e = cudaMalloc(&tiles, (size_t)n_tiles * sizeof(FastaTile));
+    if (e == cudaSuccess) e = cudaMalloc(&tstate, (size_t)n_tiles * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&toff, (size_t)n_tiles * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&total, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&out, len + 64);  // every input byte yields at most one output byte
+    if (e != cudaSuccess) {
+        cudaGetLastError(); cleanup(); cudaFree(out);
+        return ctx->fail(AIX_ERR_NOMEM, "FASTA staging (%llu bytes): %s", (unsigned long long)len, cudaGetErrorString(e));
     }
-    if (open) out.push_back('\n');
+    fasta_summary_kernel<<<n_tiles, kCntBlock, 0, st>>>(in_dev, len, tiles);
+    fasta_scan_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, tstate, toff, total);
+    fasta_compact_kernel<<<n_tiles, kCntBlock, 0, st>>>(in_dev, len, tstate, toff, out);
+    ctx->launches += 3;
+    unsigned long long h_total = 0;
+    e = cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out + h_total, '\n', 64, st);  // the last record ends here
+    cleanup();
+    if (e != cudaSuccess) {
+        cudaGetLastError(); cudaFree(out);
+        return ctx->fail(AIX_ERR_CUDA, "FASTA compaction: %s", cudaGetErrorString(e));
+    }
+    *out_dev = out;
+    *out_len = h_total + 1;
+    return AIX_OK;
 }
 
 static int detect_format_host(const uint8_t *b, uint64_t len) {  // count_kmers13.cpp:194-206
@@ -434,20 +626,29 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
         else first = src[0];
         fmt = detect_format_host(&first, 1);
     }
-    std::vector<uint8_t> plain;
-    std::vector<uint8_t> host_copy;
+    uint8_t *fasta_in = nullptr, *fasta_out = nullptr;  // device staging of a FASTA image (freed on return)
+    struct Free2 {
+        uint8_t *&a, *&b;
+        ~Free2() { cudaFree(a); cudaFree(b); }
+    } free2{fasta_in, fasta_out};
     if (fmt == AIX_FMT_FASTA) {
-        if (src_is_device) {
-            host_copy.resize(len);
-            AIX_CUDA(ctx, cudaMemcpy(host_copy.data(), src, len, cudaMemcpyDeviceToHost));
-            src = host_copy.data();
-            src_is_device = false;
+        // records are concatenated on the device; the plain-text image is then counted in place
+        const uint8_t *in_dev = src;
+        if (!src_is_device || ((uintptr_t)src & 15) != 0) {
+            cudaError_t e = cudaMalloc(&fasta_in, len + 64);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return ctx->fail(AIX_ERR_NOMEM, "FASTA image (%llu bytes): %s", (unsigned long long)len, cudaGetErrorString(e));
+            }
+            AIX_CUDA(ctx, cudaMemcpyAsync(fasta_in, src, len, cudaMemcpyDefault, ctx->stream));
+            in_dev = fasta_in;
         }
-        fasta_to_plain(src, len, plain);
-        src = plain.data();
-        len = plain.size();
+        uint64_t plain_len = 0;
+        AIX_TRY(fasta_compact_dev(ctx, ctx->stream, in_dev, len, &fasta_out, &plain_len));
+        src = fasta_out;
+        len = plain_len;
+        src_is_device = true;
         fmt = AIX_FMT_PLAIN;
-        if (len == 0) return AIX_OK;
     }
     if (fmt != AIX_FMT_PLAIN && fmt != AIX_FMT_FASTQ) return ctx->fail(AIX_ERR_ARG, "unknown format %d", fmt);
 
@@ -475,6 +676,7 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
             AIX_TRY(launch_count(ctx, ctx->stream, src, done, done + n));
             done += n;
         }
+        if (fasta_out) AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffers are released on return
         return AIX_OK;
     }
 

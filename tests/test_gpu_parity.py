@@ -347,6 +347,53 @@ def test_count13_vs_oracle_and_chunking(capi, oracle, ctx, m13, variant, monkeyp
     assert int(tf.sum()) == wst["valid"]
 
 
+def _random_fasta(rng, n_records, alphabet=b"ACGTacgtN"):
+    """multi-line records of ragged widths, empty lines, empty records, adjacent headers, CRLF, '>' inside lines"""
+    letters = np.frombuffer(alphabet, dtype=np.uint8)
+    out = []
+    for i in range(n_records):
+        out.append(b">rec%d some description > with a bracket" % i)
+        if rng.random() < 0.05:
+            continue  # empty record
+        for _ in range(int(rng.integers(1, 12))):
+            ln = rng.choice(letters, size=int(rng.integers(0, 90))).tobytes()
+            if rng.random() < 0.03:
+                ln = ln[:5] + b">" + ln[5:]      # '>' not at a line start is an ordinary (invalid) character
+            if rng.random() < 0.03:
+                ln += b"\r"
+            out.append(ln)
+    return b"\n".join(out)
+
+
+@pytest.mark.parametrize("trailing_newline", [True, False])
+def test_count13_fasta_device_concatenation(capi, oracle, ctx, m13, trailing_newline):
+    """FASTA records are concatenated on the device (header state scan + stream compaction): windows span
+    the line breaks of a record and never a header; compared with the oracle reader (count_kmers13.cpp:211-235)."""
+    rng = np.random.default_rng(37 + int(trailing_newline))
+    for n_rec in (1, 3, 40, 2500):   # the last one spans ~250 4-KiB tiles
+        data = _random_fasta(rng, n_rec) + (b"\n" if trailing_newline else b"")
+        arr = np.frombuffer(data, dtype=np.uint8)
+        want, wst = oracle.count13_direct(arr, oracle.FMT_FASTA)
+        tf, st = ctx.count13(m13, arr, capi.FMT_FASTA)
+        assert st == wst, (n_rec, st, wst)
+        assert np.array_equal(tf[m13.perm13().astype(np.int64)], want)
+        tf2, st2 = ctx.count13(m13, arr, capi.FMT_DETECT)
+        assert st2 == wst and np.array_equal(tf2, tf)
+    # an image already in HBM at an odd address takes the aligned staging copy
+    import torch
+    buf = torch.zeros(arr.size + 3, dtype=torch.uint8, device="cuda:0")
+    buf[3:] = torch.from_numpy(arr.copy()).cuda()
+    torch.cuda.synchronize()
+    lib = capi.lib()
+    ctx.check(lib.aix_count13_begin(ctx.handle))
+    ctx.check(lib.aix_count13_add_dev(ctx.handle, buf.data_ptr() + 3, arr.size, capi.FMT_FASTA))
+    st3 = capi.CountStats()
+    tf3 = np.zeros(1 << 26, dtype=np.uint64)
+    ctx.check(lib.aix_count13_finish(ctx.handle, m13._h, 0, 1 << 26, tf3.ctypes.data, st3))
+    ctx.check(lib.aix_count13_end(ctx.handle))
+    assert st3.as_dict() == wst and np.array_equal(tf3, tf)
+
+
 def test_tf13_golden(capi, ctx, m13, g13):
     tf = np.zeros(1 << 26, dtype=np.uint64)
     tf[g13["plain_ids"]] = g13["plain_counts"]
