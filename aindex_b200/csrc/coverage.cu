@@ -69,22 +69,29 @@ __device__ __forceinline__ uint64_t find_seq(const unsigned long long *__restric
     return lo;
 }
 
+// cta_seq[b] = sequence that holds output b * 256 (one thread per CTA of the main kernel, b = 0 .. n_ctas;
+// the last entry is n_seq - 1).  Doing these ~20-step searches here, all in parallel, instead of by two threads
+// of every CTA in front of a barrier removed the largest stall of the first version (profiles/r01_c4c5_ncu.txt:
+// barrier 9.5 of 24 stall cycles per issue).
+__global__ void coverage_cta_seq_kernel(const unsigned long long *__restrict__ out_offs, uint64_t n_seq, uint64_t total_out,
+                                        uint64_t n_ctas, uint32_t *__restrict__ cta_seq) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_ctas) return;
+    unsigned long long o = b * kCovBlock;
+    cta_seq[b] = (b == n_ctas || o >= total_out) ? (uint32_t)(n_seq - 1) : (uint32_t)find_seq(out_offs, 0, n_seq - 1, o);
+}
+
 template <int K, bool kCanon>
 __global__ void __launch_bounds__(kCovBlock) coverage_kernel(Index23Dev ix, MphfDev m, const uint64_t *__restrict__ tf13_direct,
                                                            const uint8_t *__restrict__ seqs, const int64_t *__restrict__ offs,
-                                                           const unsigned long long *__restrict__ out_offs, uint64_t n_seq,
-                                                           uint64_t total_out, uint32_t cutoff, uint32_t *__restrict__ out) {
-    __shared__ uint64_t s_range[2];
-    const uint64_t o0 = (uint64_t)blockIdx.x * kCovBlock;
-    if (threadIdx.x < 2) {
-        unsigned long long o = threadIdx.x == 0 ? o0 : (o0 + kCovBlock - 1 < total_out ? o0 + kCovBlock - 1 : total_out - 1);
-        s_range[threadIdx.x] = find_seq(out_offs, 0, n_seq - 1, o);
-    }
-    __syncthreads();
-    const uint64_t o = o0 + threadIdx.x;
+                                                           const unsigned long long *__restrict__ out_offs,
+                                                           const uint32_t *__restrict__ cta_seq, uint64_t total_out, uint32_t cutoff,
+                                                           uint32_t *__restrict__ out) {
+    const uint64_t o = (uint64_t)blockIdx.x * kCovBlock + threadIdx.x;
     if (o >= total_out) return;
-    const uint64_t s = find_seq(out_offs, s_range[0], s_range[1], o);
-    const uint8_t *p = seqs + offs[s] + (o - out_offs[s]);
+    const uint64_t s_lo = __ldg(cta_seq + blockIdx.x), s_hi = __ldg(cta_seq + blockIdx.x + 1);
+    const uint64_t s = s_lo == s_hi ? s_lo : find_seq(out_offs, s_lo, s_hi, o);
+    const uint8_t *p = seqs + __ldg(offs + s) + (o - __ldg(out_offs + s));
     uint32_t tf;
     if (K == 23) {
         uint64_t r0, r1, r2;
@@ -121,22 +128,32 @@ int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *i
     if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
     if (n_seq == 0 || total_out == 0) return AIX_OK;
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_seq >= (1ull << 32)) return ctx->fail(AIX_ERR_ARG, "coverage: at most 2^32-1 sequences per call");
+    const uint64_t n_ctas = (total_out + kCovBlock - 1) / kCovBlock;
     void *oo;
-    AIX_TRY(ctx->reserve(SCR_TMP1, (n_seq + 1) * 8, &oo));
+    const size_t oo_bytes = ((n_seq + 1) * 8 + 255) & ~(size_t)255;
+    AIX_TRY(ctx->reserve(SCR_TMP1, oo_bytes + (n_ctas + 1) * 4, &oo));
+    uint32_t *cta_seq = reinterpret_cast<uint32_t *>((char *)oo + oo_bytes);
     coverage_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(offs_dev, n_seq, k, (unsigned long long *)oo);
     AIX_LAUNCH_CHECK(ctx);
-    unsigned grid = aix_grid(total_out, kCovBlock);
+    coverage_cta_seq_kernel<<<aix_grid(n_ctas + 1, 256), 256, 0, ctx->stream>>>((unsigned long long *)oo, n_seq, total_out, n_ctas, cta_seq);
+    AIX_LAUNCH_CHECK(ctx);
+    unsigned grid = (unsigned)n_ctas;
     Index23Dev id = {};
     MphfDev md = {};
     if (k == 23) {
         id = ix23->dev();
         md = ix23->mphf->dev();
+        // coverage is hit-dominated (sequences of the indexed organism): the fingerprint tier would add a
+        // dependent L2 round trip in front of nearly every HBM record load.  AIX_COVERAGE_TIER=1 keeps it.
+        const char *e = getenv("AIX_COVERAGE_TIER");
+        if (!(e && atoi(e) != 0)) id.fp = nullptr;
         if (ix23->canonical_only)
-            coverage_kernel<23, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+            coverage_kernel<23, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
         else
-            coverage_kernel<23, false><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+            coverage_kernel<23, false><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
     } else {
-        coverage_kernel<13, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, ix13->tf_direct_dev, seqs_dev, offs_dev, (unsigned long long *)oo, n_seq, total_out, cutoff, out_dev);
+        coverage_kernel<13, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, ix13->tf_direct_dev, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
     }
     AIX_LAUNCH_CHECK(ctx);
     return AIX_OK;

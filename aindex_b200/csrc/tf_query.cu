@@ -6,12 +6,13 @@
 // 13-mer queries python_wrapper.cpp:482-608, :938-980, loaders hash.cpp:367-450,
 // python_wrapper.cpp:404-437.
 //
-// Kernel shape (K3): one query per thread, 256 queries per CTA.  The 23-byte records of a
-// CTA are contiguous, so they are staged into shared memory with coalesced 16-byte
-// streaming loads and re-read per thread as 7 aligned words + funnel shifts.  A query is
-// then ~450 integer instructions, three independent 16-byte L2 loads (MPHF record) and one
-// 16-byte HBM load ({checker, tf} record).  Latency is hidden by occupancy, not by
-// intra-thread pipelining: the loads of a query depend on its hash.
+// Kernel shape (K3): one query per thread.  Fixed 23-byte records take tf23_stream_kernel (a TMA ring
+// of 32-query tiles per warp, see below); tf23_fixed_kernel is its predecessor (256 queries per CTA
+// staged with 16-byte streaming loads behind a CTA barrier) and serves the last q mod 32 queries.
+// Either way the bytes of a query are re-read from shared memory as 7 aligned words + funnel shifts,
+// and a query is ~400 integer instructions, three independent 16-byte L2 loads (MPHF record), one
+// L2 byte (fingerprint) and one 16-byte HBM load ({checker, tf} record) when the fingerprint matches.
+// Latency is hidden by occupancy, not by intra-thread pipelining: the loads of a query depend on its hash.
 #include "aix_internal.cuh"
 #include "batch_pipeline.cuh"
 #include "query23.cuh"
@@ -319,7 +320,6 @@ __global__ void __launch_bounds__(kStWarps * 32) tf13_stream_kernel(MphfDev m, c
     __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kSt13Slot];
     __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
@@ -363,7 +363,6 @@ __global__ void __launch_bounds__(kStWarps * 32) tf13_stream_kernel(MphfDev m, c
         i += (uint64_t)kStWarps * 32u;
         if (++slot == kStStages) { slot = 0; phase ^= 1u; }
     }
-    (void)ring0; (void)bar0;
 }
 
 static size_t out_bytes23(int mode) {
