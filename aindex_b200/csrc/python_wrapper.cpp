@@ -123,6 +123,42 @@ Records pack_records(const std::vector<std::string> &kmers) {
     return r;
 }
 
+// list of str (or bytes) -> records without building a std::vector<std::string> first: the UTF-8 view of an
+// ASCII str is the object's own buffer, so a 23-mer costs one memcpy instead of a heap allocation and two copies.
+// Must be called with the GIL held.
+Records pack_records_py(const py::list &kmers) {
+    Records r;
+    r.q = (uint64_t)kmers.size();
+    std::vector<const char *> ptr(r.q);
+    std::vector<Py_ssize_t> len(r.q);
+    size_t mx = 1;
+    for (uint64_t i = 0; i < r.q; ++i) {
+        PyObject *o = PyList_GET_ITEM(kmers.ptr(), (Py_ssize_t)i);
+        if (PyUnicode_Check(o)) {
+            ptr[i] = PyUnicode_AsUTF8AndSize(o, &len[i]);
+            if (!ptr[i]) throw py::error_already_set();
+        } else if (PyBytes_Check(o)) {
+            char *b = nullptr;
+            if (PyBytes_AsStringAndSize(o, &b, &len[i]) != 0) throw py::error_already_set();
+            ptr[i] = b;
+        } else {
+            throw py::type_error("k-mers must be str or bytes");
+        }
+        mx = std::max(mx, (size_t)len[i]);
+    }
+    if (mx > 255) throw std::invalid_argument("query strings longer than 255 characters are not supported");
+    r.stride = (uint32_t)mx;
+    for (uint64_t i = 0; i < r.q; ++i)
+        if ((size_t)len[i] != mx) { r.uniform = false; break; }
+    r.bytes.assign((size_t)r.q * r.stride, 0);
+    if (!r.uniform) r.lens.resize(r.q);
+    for (uint64_t i = 0; i < r.q; ++i) {
+        memcpy(r.bytes.data() + i * r.stride, ptr[i], (size_t)len[i]);
+        if (!r.uniform) r.lens[i] = (uint8_t)len[i];
+    }
+    return r;
+}
+
 struct Interval {  // python_wrapper.cpp:44-53 (end is stored as end+1, :271)
     uint64_t rid, start, end;
 };
@@ -220,6 +256,23 @@ private:
     }
 
 public:
+    // the batch form of get_tf_values: list in, list out, no per-string C++ objects in between
+    py::list tf_values_list(const py::list &kmers) const {
+        Records r = pack_records_py(kmers);
+        std::vector<uint32_t> out(r.q);
+        if (r.q) {
+            py::gil_scoped_release nogil;
+            if (is_13mer_mode) check(aix_tf13_batch(ctx, ix13, r.bytes.data(), r.stride, r.lens_ptr(), r.q, AIX_Q_TF, out.data()));
+            else {
+                if (!ix23) throw std::runtime_error("23-mer index not loaded");
+                check(aix_tf23_batch(ctx, ix23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, AIX_Q_TF, out.data()));
+            }
+        }
+        py::list res(r.q);
+        for (uint64_t i = 0; i < r.q; ++i) PyList_SET_ITEM(res.ptr(), (Py_ssize_t)i, PyLong_FromUnsignedLong(out[i]));
+        return res;
+    }
+
     // ------------------------------------------------------------------ loaders
     // load / load_hash_file (python_wrapper.cpp:228-259) -> load_hash (hash.cpp:367-450)
     void load(std::string hash_filename, std::string tf_file, std::string kmers_bin_filename,
@@ -792,6 +845,7 @@ PYBIND11_MODULE(aindex_cpp, m) {
         .def("load_from_prefix_13mer", &AindexWrapper::load_from_prefix_13mer, py::arg("prefix"), py::arg("reads_file") = "")
         .def("load_aindex_from_prefix_13mer", &AindexWrapper::load_aindex_from_prefix_13mer, py::arg("prefix"),
              py::arg("reads_file") = "")
+        .def("get_tf_values", &AindexWrapper::tf_values_list, "list[str] -> list[int] (python_wrapper.cpp:653-664)")
         .def("get_tf_values", &AindexWrapper::get_tf_values)
         .def("get_tf_values", &AindexWrapper::get_tf_values_array, "uint8[q, k] records -> uint32[q] (no per-string objects)")
         .def("get_tf_value", &AindexWrapper::get_tf_value)

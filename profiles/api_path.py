@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""The drop-in boundary as a user of the reference meets it: AindexWrapper.get_tf_values on the golden
+23-mer index through (a) list[str] (the reference signature) and (b) the uint8[q, 23] overload, for this
+module, and (c) list[str] through the UNMODIFIED reference module (oracle/_ref, run in a subprocess so the
+two same-named extension modules never share a process).  Prints one JSON line."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PREFIX = os.path.join(ROOT, "tests", "golden", "idx23")
+N = 2_000_000
+
+
+def queries():
+    rng = np.random.default_rng(3)
+    kb = np.fromfile(PREFIX + ".kmers.bin", dtype=np.uint64)
+    arr = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(N, 23))
+    hit = rng.random(N) < 0.5
+    v = kb[rng.integers(0, kb.size, size=int(hit.sum()))]
+    sh = (2 * (22 - np.arange(23))).astype(np.uint64)
+    arr[hit] = np.frombuffer(b"ACGT", dtype=np.uint8)[((v[:, None] >> sh[None, :]) & np.uint64(3)).astype(np.int64)]
+    return arr
+
+
+def time_list(w, strs, reps=3):
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = w.get_tf_values(strs)
+        best = min(best, time.perf_counter() - t0)
+    return best, np.asarray(out, dtype=np.uint32)
+
+
+if __name__ == "__main__":
+    arr = queries()
+    strs = [r.tobytes().decode() for r in arr]
+    if len(sys.argv) > 1 and sys.argv[1] == "--reference":
+        from oracle import oracle as O
+        m = O.ref_module()
+        w = m.AindexWrapper()
+        w.load(PREFIX + ".pf", PREFIX + ".tf.bin", PREFIX + ".kmers.bin", "")
+        dt, out = time_list(w, strs)
+        print(json.dumps({"qps": N / dt, "sum": int(out.sum())}))
+        sys.exit(0)
+    from aindex_b200.core import aindex_cpp
+    w = aindex_cpp.AindexWrapper()
+    w.load(PREFIX + ".pf", PREFIX + ".tf.bin", PREFIX + ".kmers.bin", "")
+    dt_list, out_list = time_list(w, strs)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out_arr = np.asarray(w.get_tf_values(arr))
+        best = min(best, time.perf_counter() - t0)
+    line = {"queries": N, "hit_fraction": float((out_list > 0).mean()),
+            "ours_list_str_qps": N / dt_list, "ours_ndarray_qps": N / best,
+            "ndarray_equals_list": bool(np.array_equal(out_arr, out_list))}
+    r = subprocess.run([sys.executable, __file__, "--reference"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    if r.returncode == 0 and r.stdout.strip():
+        ref = json.loads(r.stdout.strip().splitlines()[-1])
+        line["reference_list_str_qps"] = ref["qps"]
+        line["reference_sum_equal"] = ref["sum"] == int(out_list.sum())
+    print(json.dumps(line))
