@@ -71,6 +71,7 @@ struct aix_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     DevBuf scratch[8];                  // grow-only device scratch, indexed by role
+    void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
     uint64_t *c13_hist64 = nullptr;     // u64[4^13]

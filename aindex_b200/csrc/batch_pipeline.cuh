@@ -6,6 +6,8 @@
 
 namespace aix {
 
+constexpr size_t kSmallBatchBytes = 32u << 10;  // per region (records / lengths / results); +64 bytes of slack inside
+
 // launch(stream, recs_dev, lens_dev_or_null, nq, out_dev) must enqueue the kernel(s) on `stream`.
 template <typename Launch>
 int run_record_batches(aix_ctx *ctx, const uint8_t *recs, uint32_t stride, const uint8_t *lens,
@@ -13,6 +15,30 @@ int run_record_batches(aix_ctx *ctx, const uint8_t *recs, uint32_t stride, const
     if (q == 0) return AIX_OK;
     if (!recs || !out || stride == 0) return ctx->fail(AIX_ERR_ARG, "null buffer or zero stride");
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    // small batches (a single get_tf_value call is a batch of one): no staged copies at all.  The records are
+    // placed in a pinned, device-mapped buffer owned by the ctx, the kernel reads them and writes its results
+    // through the mapping, and the host waits once: one launch + one synchronisation instead of three
+    // synchronous pageable copies around the launch.
+    if (q * (uint64_t)stride + 64 <= kSmallBatchBytes && q * out_bytes_per_rec <= kSmallBatchBytes) {
+        if (!ctx->small_host) {
+            cudaError_t e = cudaHostAlloc(&ctx->small_host, 3 * kSmallBatchBytes, cudaHostAllocMapped);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->small_host = nullptr;
+            }
+        }
+        if (ctx->small_host) {
+            uint8_t *h_in = (uint8_t *)ctx->small_host, *h_len = h_in + kSmallBatchBytes, *h_out = h_len + kSmallBatchBytes;
+            memcpy(h_in, recs, q * stride);
+            memset(h_in + q * stride, 0, 64);  // the fixed-stride kernels read whole 16-byte vectors
+            if (lens) memcpy(h_len, lens, q);
+            int rc = launch(ctx->stream, h_in, lens ? h_len : nullptr, q, h_out);
+            if (rc != AIX_OK) return rc;
+            AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            memcpy(out, h_out, q * out_bytes_per_rec);
+            return AIX_OK;
+        }
+    }
     const uint64_t target_bytes = 64ull << 20;
     uint64_t qc = target_bytes / stride;
     qc = (qc + 4095) & ~4095ull;

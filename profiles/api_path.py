@@ -28,6 +28,15 @@ def queries():
     return arr
 
 
+def time_single(w, strs, n=20000):
+    """one Python call per k-mer (index[kmer] / get_tf_value): launch latency, not throughput"""
+    t0 = time.perf_counter()
+    acc = 0
+    for k in strs[:n]:
+        acc += w.get_tf_value(k)
+    return n / (time.perf_counter() - t0), acc
+
+
 def time_list(w, strs, reps=3):
     best = 1e9
     for _ in range(reps):
@@ -46,7 +55,8 @@ if __name__ == "__main__":
         w = m.AindexWrapper()
         w.load(PREFIX + ".pf", PREFIX + ".tf.bin", PREFIX + ".kmers.bin", "")
         dt, out = time_list(w, strs)
-        print(json.dumps({"qps": N / dt, "sum": int(out.sum())}))
+        sq, acc = time_single(w, strs)
+        print(json.dumps({"qps": N / dt, "sum": int(out.sum()), "single_qps": sq, "single_sum": acc}))
         sys.exit(0)
     from aindex_b200.core import aindex_cpp
     w = aindex_cpp.AindexWrapper()
@@ -57,7 +67,17 @@ if __name__ == "__main__":
         t0 = time.perf_counter()
         out_arr = np.asarray(w.get_tf_values(arr))
         best = min(best, time.perf_counter() - t0)
-    line = {"queries": N, "hit_fraction": float((out_list > 0).mean()),
+    sq, acc = time_single(w, strs)
+    # sequence coverage, one call per 150 bp sequence (the reference's "sequences/s" usage pattern) vs one batch call
+    from aindex_b200.core.aindex import AIndex
+    ai = AIndex.load_from_prefix(PREFIX)
+    reads = [l for l in open(PREFIX + ".reads").read().split("\n") if len(l) >= 100][:5000]
+    t0 = time.perf_counter()
+    tot = 0
+    for r in reads:
+        tot += int(np.sum(ai.get_sequence_coverage(r)))
+    cov_single = len(reads) / (time.perf_counter() - t0)
+    line = {"queries": N, "ours_single_call_qps": sq, "ours_coverage_calls_per_s": cov_single, "hit_fraction": float((out_list > 0).mean()),
             "ours_list_str_qps": N / dt_list, "ours_ndarray_qps": N / best,
             "ndarray_equals_list": bool(np.array_equal(out_arr, out_list))}
     r = subprocess.run([sys.executable, __file__, "--reference"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,4 +85,6 @@ if __name__ == "__main__":
         ref = json.loads(r.stdout.strip().splitlines()[-1])
         line["reference_list_str_qps"] = ref["qps"]
         line["reference_sum_equal"] = ref["sum"] == int(out_list.sum())
+        line["reference_single_call_qps"] = ref["single_qps"]
+        line["single_sum_equal"] = ref["single_sum"] == acc
     print(json.dumps(line))
