@@ -634,7 +634,8 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
     if (fmt == AIX_FMT_FASTA) {
         // records are concatenated on the device; the plain-text image is then counted in place
         const uint8_t *in_dev = src;
-        if (!src_is_device || ((uintptr_t)src & 15) != 0) {
+        // in place only when every 16-byte vector of the image lies inside the caller's buffer
+        if (!src_is_device || ((uintptr_t)src & 15) != 0 || (len & 15) != 0) {
             cudaError_t e = cudaMalloc(&fasta_in, len + 64);
             if (e != cudaSuccess) {
                 cudaGetLastError();
@@ -666,18 +667,23 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
         return AIX_OK;
     };
 
-    // resident plain text: count in place, no copy
+    // resident plain text: count in place, no copy.  Only whole 16-byte vectors are read in place; a ragged
+    // tail (len % 16 bytes) goes through the staged path below with its 16 bytes of lookback, so nothing past
+    // the caller's buffer is ever touched.
+    uint64_t done = 0;
     if (src_is_device && fmt == AIX_FMT_PLAIN && ((uintptr_t)src & 15) == 0) {
-        uint64_t done = 0;
+        const uint64_t whole = len & ~15ull;
         const uint64_t step = 1ull << 31;  // keep each launch below the flush threshold
-        while (done < len) {
-            uint64_t n = len - done < step ? len - done : step;
+        while (done < whole) {
+            uint64_t n = whole - done < step ? whole - done : step;
             AIX_TRY(account(n, ctx->stream));
             AIX_TRY(launch_count(ctx, ctx->stream, src, done, done + n));
             done += n;
         }
-        if (fasta_out) AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffers are released on return
-        return AIX_OK;
+        if (done == len) {
+            if (fasta_out) AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffers are released on return
+            return AIX_OK;
+        }
     }
 
     // staged path: chunk c holds [16 lookback bytes][chunk bytes] (the first chunk has no lookback)
@@ -686,7 +692,7 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
         uint64_t v = strtoull(e, nullptr, 10);
         if (v >= 64) chunk = v & ~15ull;
     }
-    if (chunk > len) chunk = (len + 15) & ~15ull;
+    if (chunk > len - done) chunk = (len - done + 15) & ~15ull;
     const uint32_t max_tiles = (uint32_t)((chunk + kTileBytes - 1) / kTileBytes) + 1;
     void *buf[2] = {nullptr, nullptr}, *tcnt[2] = {nullptr, nullptr}, *tbase[2] = {nullptr, nullptr};
     for (int s = 0; s < 2; ++s) {
@@ -695,14 +701,13 @@ static int c13_add_impl(aix_ctx *ctx, const uint8_t *src, uint64_t len, int fmt,
             AIX_TRY(ctx->reserve(SCR_LEN0 + s, (size_t)max_tiles * 4, &tcnt[s]));
             AIX_TRY(ctx->reserve(SCR_OUT0 + s, (size_t)max_tiles * 8, &tbase[s]));
         }
-        if (len <= chunk) break;
+        if (len - done <= chunk) break;
     }
     unsigned long long *line_base = (unsigned long long *)(ctx->c13_stats_dev + 4);
     if (fmt == AIX_FMT_FASTQ) AIX_CUDA(ctx, cudaMemsetAsync(line_base, 0, 8, ctx->stream));
     AIX_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer[0], ctx->ev[0], 0));
     AIX_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer[1], ctx->ev[0], 0));
-    uint64_t done = 0;
     int c = 0;
     while (done < len) {
         uint64_t n = len - done < chunk ? len - done : chunk;

@@ -213,6 +213,7 @@ int aix_count13_end(aix_ctx *ctx);
 int aix_coverage(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13,
                  const uint8_t *seqs, const int64_t *offs, uint64_t n_seq, int k, uint32_t cutoff,
                  uint32_t *out);
+/* device form: seqs_dev must be readable for 8 bytes past total_bytes (aligned word loads of the last window) */
 int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13,
                      const uint8_t *seqs_dev, const int64_t *offs_dev, uint64_t n_seq,
                      uint64_t total_bytes, uint64_t total_out, int k, uint32_t cutoff,

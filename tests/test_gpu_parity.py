@@ -394,6 +394,28 @@ def test_count13_fasta_device_concatenation(capi, oracle, ctx, m13, trailing_new
     assert st3.as_dict() == wst and np.array_equal(tf3, tf)
 
 
+def test_count13_device_inplace_ragged_tail(capi, oracle, ctx, m13):
+    """A resident plain-text image whose length is not a multiple of 16: whole vectors are counted in place, the
+    ragged tail through the staged path with lookback -- windows across the seam are counted exactly once."""
+    import torch
+    rng = np.random.default_rng(53)
+    data = _random_reads(rng, 3000, 150, b"ACGT", n_rate=0.001)
+    lib = capi.lib()
+    for cut in (data.size, data.size - 1, data.size - 7, data.size - 151 - 9, 16 * 1000 + 3, 15, 40):
+        part = np.ascontiguousarray(data[:cut])
+        want, wst = oracle.count13_direct(part, oracle.FMT_PLAIN)
+        buf = torch.from_numpy(part.copy()).cuda()   # exact size: nothing readable is promised past the end
+        torch.cuda.synchronize()
+        ctx.check(lib.aix_count13_begin(ctx.handle))
+        ctx.check(lib.aix_count13_add_dev(ctx.handle, buf.data_ptr(), part.size, capi.FMT_PLAIN))
+        st = capi.CountStats()
+        tf = np.zeros(1 << 26, dtype=np.uint64)
+        ctx.check(lib.aix_count13_finish(ctx.handle, m13._h, 0, 1 << 26, tf.ctypes.data, st))
+        ctx.check(lib.aix_count13_end(ctx.handle))
+        assert st.as_dict() == wst, (cut, st.as_dict(), wst)
+        assert np.array_equal(tf[m13.perm13().astype(np.int64)], want)
+
+
 def test_tf13_golden(capi, ctx, m13, g13):
     tf = np.zeros(1 << 26, dtype=np.uint64)
     tf[g13["plain_ids"]] = g13["plain_counts"]
