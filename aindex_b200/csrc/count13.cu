@@ -89,13 +89,16 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // smask/sval: multi-pass mode -- only k-mers whose byte offset satisfies (off & smask) == sval
 // are counted in this launch, so the histogram slice being updated stays L2 resident
 // (smask = 0: single pass).  kStats: accumulate the count_kmers13 statistics (first pass only).
-// kVariant: 0 one RED per window, 1 thread-local run-length merge, 2 warp match_any merge.
+// kVariant: 0 one RED per window + warp merge of low-complexity windows (default), 1 thread-local run-length
+// merge, 2 warp match_any merge of every window, 3 one RED per window, nothing merged.
 template <bool kStats, int kVariant>
 __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__restrict__ base, uint64_t own_begin,
                                                           uint64_t own_end, uint32_t *__restrict__ hist,
                                                           unsigned long long *__restrict__ stats, uint32_t smask,
                                                           uint32_t sval) {
     __shared__ uint2 edge[kCntBlock / 32];
+    __shared__ uint32_t lc_cnt[16], lc_off[16];  // low-complexity windows of the CTA (variant 0)
+    if (kVariant == 0 && threadIdx.x < 16) lc_cnt[threadIdx.x] = 0;  // visible after the barrier below
     const uint64_t t = (uint64_t)blockIdx.x * kCntBlock + threadIdx.x;
     const uint64_t pos = own_begin + t * 16;
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -131,26 +134,62 @@ __global__ void __launch_bounds__(kCntBlock) count13_kernel(const uint8_t *__res
     // byte offsets into the histogram: (prev:own codes) << 2, window s at bits [2(16-s)+2 ...]
     const uint32_t lo2 = own.codes << 2, hi2 = __funnelshift_l(own.codes, prev.codes, 2);
     constexpr uint32_t kOffMask = kMask26 << 2;
+    // Low-complexity windows (period 1 or 2: poly-A, (CA)n ... -- 16 k-mers that real genomes hit millions of
+    // times) would serialise on a handful of L2 counters.  They are found per thread with a few 64-bit operations
+    // on the 29 codes (code[q] == code[q-2] for 11 consecutive q) and counted in 16 shared-memory counters per CTA
+    // that are flushed with at most 16 REDs; warps of uniform-random reads never enter that path.
+    uint32_t lowc = 0;  // bit (32 - 2s): window s has period <= 2
+    if (kVariant == 0) {
+        const uint64_t w64 = ((uint64_t)(prev.codes & kMask26) << 32) | own.codes;  // position p at bits [57-2p, 56-2p]
+        const uint64_t d = w64 ^ (w64 >> 4);
+        const uint64_t z = ~(d | (d >> 1)) & 0x0015555555555555ULL;  // field q (>= 2): code[q] == code[q-2]
+        const uint64_t r1 = z & (z >> 2), r2 = r1 & (r1 >> 4), r3 = r2 & (r2 >> 8);
+        lowc = (uint32_t)(r3 & (r1 >> 16) & (z >> 20));  // field q: the 11 comparisons q-10 .. q all hold
+    }
     uint32_t pend_off = 0, pend_c = 0;
+    // warp-uniform choice: warps without a low-complexity window (all of them on random reads) run the plain loop
+    if (kVariant == 0 && __any_sync(0xFFFFFFFFu, lowc != 0)) {
 #pragma unroll
-    for (int s = 1; s <= 16; ++s) {
-        const uint32_t off = __funnelshift_r(lo2, hi2, 2 * (16 - s)) & kOffMask;
-        const bool ok = ((wvalid >> s) & 1u) && ((off & smask) == sval);
-        if (kVariant == 0) {
-            if (ok) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
-        } else if (kVariant == 1) {
-            if (ok && pend_c && off == pend_off) { ++pend_c; continue; }
-            if (pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
-            pend_c = ok ? 1u : 0u;
-            pend_off = off;
-        } else {
-            const uint32_t key = ok ? off : 0xFFFFFFFFu;
-            const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-            if (ok && lane == (unsigned)(__ffs(peers) - 1))
-                atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), (uint32_t)__popc(peers));
+        for (int s = 1; s <= 16; ++s) {
+            const uint32_t off = __funnelshift_r(lo2, hi2, 2 * (16 - s)) & kOffMask;
+            const bool ok = ((wvalid >> s) & 1u) && ((off & smask) == sval);
+            const bool sp = (lowc >> (32 - 2 * s)) & 1u;
+            if (ok && !sp) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
+            if (ok && sp) {
+                // a period-<=2 13-mer is determined by its last two bases: 16 CTA-level counters in shared memory
+                const uint32_t cls = (off >> 2) & 15u;
+                atomicAdd(&lc_cnt[cls], 1u);
+                lc_off[cls] = off;  // every writer stores the same value
+            }
+        }
+    } else {
+#pragma unroll
+        for (int s = 1; s <= 16; ++s) {
+            const uint32_t off = __funnelshift_r(lo2, hi2, 2 * (16 - s)) & kOffMask;
+            const bool ok = ((wvalid >> s) & 1u) && ((off & smask) == sval);
+            if (kVariant == 0 || kVariant == 3) {
+                if (ok) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
+            } else if (kVariant == 1) {
+                if (ok && pend_c && off == pend_off) { ++pend_c; continue; }
+                if (pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
+                pend_c = ok ? 1u : 0u;
+                pend_off = off;
+            } else {
+                const uint32_t key = ok ? off : 0xFFFFFFFFu;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+                if (ok && lane == (unsigned)(__ffs(peers) - 1))
+                    atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), (uint32_t)__popc(peers));
+            }
         }
     }
     if (kVariant == 1 && pend_c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + pend_off), pend_c);
+    if (kVariant == 0) {
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const uint32_t c = lc_cnt[threadIdx.x];
+            if (c) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + lc_off[threadIdx.x]), c);
+        }
+    }
     if (kStats) {
         // count_kmers13 statistics: per thread <= 16 of each kind, so one packed 32-bit REDUX per
         // warp, one shared-memory word per warp and three global atomics per CTA on one of
@@ -531,7 +570,8 @@ static int c13_flush_on(aix_ctx *ctx, cudaStream_t st) {
     return AIX_OK;
 }
 
-// 0 one RED per window (default), 1 + thread-local run-length merge, 2 warp match_any merge
+// 0 one RED per window, low-complexity windows merged across the warp (default), 1 thread-local run-length merge,
+// 2 warp match_any merge of every window, 3 nothing merged (profiles/r01_count13_sweep.txt)
 static int count_variant() {
     const char *e = getenv("AIX_COUNT13_VARIANT");
     return e ? atoi(e) : 0;
@@ -557,10 +597,12 @@ static int launch_count(aix_ctx *ctx, cudaStream_t st, const uint8_t *base, uint
         if (p == 0) {
             if (variant == 1) AIX_C13_LAUNCH(true, 1);
             else if (variant == 2) AIX_C13_LAUNCH(true, 2);
+            else if (variant == 3) AIX_C13_LAUNCH(true, 3);
             else AIX_C13_LAUNCH(true, 0);
         } else {
             if (variant == 1) AIX_C13_LAUNCH(false, 1);
             else if (variant == 2) AIX_C13_LAUNCH(false, 2);
+            else if (variant == 3) AIX_C13_LAUNCH(false, 3);
             else AIX_C13_LAUNCH(false, 0);
         }
 #undef AIX_C13_LAUNCH

@@ -322,7 +322,7 @@ def _random_reads(rng, n_reads, read_len, alphabet=b"ACGT", n_rate=0.0):
     return a.reshape(-1)
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
 def test_count13_vs_oracle_and_chunking(capi, oracle, ctx, m13, variant, monkeypatch):
     """2 MB of reads against the oracle; the same input through the multi-chunk streaming path
     (forced small chunks) and through every atomics variant must give the same histogram."""
@@ -392,6 +392,35 @@ def test_count13_fasta_device_concatenation(capi, oracle, ctx, m13, trailing_new
     ctx.check(lib.aix_count13_finish(ctx.handle, m13._h, 0, 1 << 26, tf3.ctypes.data, st3))
     ctx.check(lib.aix_count13_end(ctx.handle))
     assert st3.as_dict() == wst and np.array_equal(tf3, tf)
+
+
+@pytest.mark.parametrize("passes_log2", ["0", "2"])
+def test_count13_low_complexity_merge(capi, oracle, ctx, m13, monkeypatch, passes_log2):
+    """Period-1 / period-2 windows (poly-A, (CA)n ...) are merged across the warp before they reach L2: tracts of
+    every phase and length, broken by N / lower case / newlines, next to random sequence, against the oracle."""
+    monkeypatch.setenv("AIX_COUNT13_PASSES_LOG2", passes_log2)
+    rng = np.random.default_rng(59)
+    lines = []
+    units = [b"A", b"C", b"G", b"T", b"AC", b"CA", b"AG", b"GT", b"TA", b"AT", b"CG", b"GC", b"TG", b"ct", b"ACG", b"AAC", b"ACAG"]
+    for i in range(6000):
+        parts = []
+        for _ in range(int(rng.integers(1, 5))):
+            r = rng.random()
+            if r < 0.6:
+                u = units[int(rng.integers(0, len(units)))]
+                parts.append((u * 200)[int(rng.integers(0, 3)):][:int(rng.integers(1, 180))])
+            else:
+                parts.append(rng.choice(ACGT, size=int(rng.integers(1, 60))).tobytes())
+            if rng.random() < 0.1:
+                parts.append(b"N")
+        lines.append(b"".join(parts))
+    lines += [b"A" * 13, b"A" * 12, b"AC" * 6 + b"A", b"AC" * 6, b"A" * 5000, b"TG" * 3000, b""]
+    data = np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+    want, wst = oracle.count13_direct(data, oracle.FMT_PLAIN)
+    tf, st = ctx.count13(m13, data, capi.FMT_PLAIN)
+    assert st == wst
+    assert np.array_equal(tf[m13.perm13().astype(np.int64)], want)
+    assert int(want.max()) > 10000  # the hot counters really are hot in this input
 
 
 def test_count13_device_inplace_ragged_tail(capi, oracle, ctx, m13):
