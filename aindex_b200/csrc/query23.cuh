@@ -9,19 +9,6 @@
 
 namespace aix {
 
-// ---------------------------------------------------------------------------------------
-// 2-bit codes of 8 ASCII bytes, first byte most significant (16 bits).  Uses the
-// branch-free letter code ((c>>1)^(c>>2))&3, which is only meaningful for ACGT letters;
-// callers validate by re-expanding to ASCII and comparing with the raw bytes.
-__device__ __forceinline__ uint32_t codes_be_from_ascii8(uint64_t w) {
-    uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-    uint32_t cl = ((lo >> 1) ^ (lo >> 2)) & 0x03030303u;
-    uint32_t ch = ((hi >> 1) ^ (hi >> 2)) & 0x03030303u;
-    uint32_t pl = (cl * 0x40100401u) >> 24;  // c0<<6 | c1<<4 | c2<<2 | c3
-    uint32_t ph = (ch * 0x40100401u) >> 24;
-    return (pl << 8) | ph;
-}
-
 // 2-bit value of a 23-byte string (words zero padded past byte 22) AND whether every byte is an
 // upper-case ACGT letter: the letter code of each byte selects the one byte value that is valid
 // for it ("ACGT"[code], by PRMT) and the word is compared with that expectation.

@@ -508,7 +508,7 @@ def run_ours(args):
         tmpdir = tempfile.mkdtemp(prefix="aix_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
             prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
-            sample = args.cpu_sample or min(args.queries, 2_000_000 * threads)
+            sample = args.cpu_sample or min(args.queries, 6_250_000 * threads)  # 16 threads: the whole 100 M batch (~4 s per pass)
             if q_host is None:
                 raise RuntimeError("cpu baseline needs the host copy of the queries")
             qs = np.ascontiguousarray(q_host[:sample])
