@@ -191,6 +191,17 @@ __global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__re
     uint64_t lo = k & ((1ULL << 46) - 1);
     uint64_t rl = revcomp23(lo);
     uint32_t res = 0, tf;
+    if (kCanon) {
+        // every stored value is canonical and below 2^46: the forward probe can only verify k == lo <= rl, the
+        // reverse probe only rl < lo -- one probe of min(lo, rl), same answer
+        const bool fwd = lo <= rl;
+        if (!fwd || k == lo) {
+            const uint64_t h = mphf_lookup23(m, fwd ? rl : lo);  // hashes the ASCII string of min(lo, rl)
+            if (probe23(ix, h, fwd ? lo : rl, tf)) res = tf;
+        }
+        out[i] = res;
+        return;
+    }
     uint64_t h1 = mphf_lookup23(m, rl);
     if (probe23(ix, h1, k, tf)) res = tf;
     else {
@@ -636,7 +647,8 @@ int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, 
     MphfDev md = ix->mphf->dev();
     return run_record_batches(ctx, (const uint8_t *)ukmers, 8, nullptr, q, out, 4,
                               [&](cudaStream_t st, const uint8_t *r, const uint8_t *, uint64_t nq, void *o) {
-                                  get_freq23_kernel<false><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, (const uint64_t *)r, nq, (uint32_t *)o);
+                                  if (ix->canonical_only) get_freq23_kernel<true><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, (const uint64_t *)r, nq, (uint32_t *)o);
+                                  else get_freq23_kernel<false><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, (const uint64_t *)r, nq, (uint32_t *)o);
                                   AIX_LAUNCH_CHECK(ctx);
                                   return AIX_OK;
                               });

@@ -162,6 +162,14 @@ def test_tf23_fixed_stride_fast_path(capi, oracle, idx23, oidx23):
                             (capi.Q_STRAND, oracle.MODE_STRAND)):
             assert np.array_equal(idx23.query(recs, mode), oidx23.batch(recs, None, omode))
     assert np.array_equal(idx23.get_freq(oidx23.checker[:500]), oidx23.tf[:500])
+    # PHASH_MAP::get_freq(uint64_t): stored k-mers, their reverse complements, random values, values with bits above 46
+    pick = oidx23.checker[rng.integers(0, oidx23.n, size=4000)]
+    rcs = np.array([oracle.reverse_dna23(int(x)) for x in pick[:1000]], dtype=np.uint64)
+    rnd = rng.integers(0, 1 << 46, size=2000, dtype=np.uint64)
+    high = pick[:500] | (np.uint64(1) << np.uint64(50))
+    high_rc = rcs[:500] | (np.uint64(3) << np.uint64(46))
+    u = np.concatenate([pick, rcs, rnd, high, high_rc])
+    assert np.array_equal(idx23.get_freq(u), np.array([oidx23.get_freq(int(x)) for x in u], dtype=np.uint32))
     assert idx23.query(np.zeros((0, 23), dtype=np.uint8)).size == 0
 
 
