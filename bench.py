@@ -558,7 +558,11 @@ def run_ours(args):
         line = {
             "metric": "23-mer batch tf queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "vs_baseline_note": "BASELINE.json.published is empty; the reference README quotes 2.3 M q/s for 1 M random queries through "
+                                "the Python list API on unstated hardware (README.md:14) -- another config, so no ratio is formed; "
+                                "the reference is timed on this box instead (cpu_baseline, --impl reference, profiles/r01_api_path.json)",
+            "dtype": "u64", "data": "synthetic",
             "config": {"workload": "C2: 23-mer index over 10M synthetic 150bp reads; 100M random batch tf queries (Q1, ~100% miss) per GPU",
                        "reads": args.reads, "genome_bp": args.genome, "queries_per_gpu": args.queries, "index_keys": n_keys,
                        "parallelism": f"replicated index, queries sharded x{world}",
