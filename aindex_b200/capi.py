@@ -92,6 +92,10 @@ SIGNATURES = {
     "aix_count13_finish": (_i, [_vp, _vp, _u64, _u64, _vp, C.POINTER(CountStats)]),
     "aix_count13_finish_dev": (_i, [_vp, _vp, _u64, _u64, _vp]),
     "aix_count13_end": (_i, [_vp]),
+    "aix_count13_ipc_export": (_i, [_vp, _vp]),
+    "aix_count13_peers_open": (_i, [_vp, _vp, _i, _i]),
+    "aix_count13_reduce_peers_dev": (_i, [_vp, _u64, _u64, _vp]),
+    "aix_count13_peers_close": (_i, [_vp]),
     "aix_coverage": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _u32, _vp]),
     "aix_coverage_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _u64, _i, _u32, _vp]),
     "aix_positions_total23": (_i, [_vp, _vp, _vp]),

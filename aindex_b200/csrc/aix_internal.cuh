@@ -78,6 +78,8 @@ struct aix_ctx {
     uint64_t *c13_stats_dev = nullptr;  // statistics slots, layout in count13.cu (kStatBase)
     uint64_t c13_pending_windows = 0;   // upper bound of increments not yet flushed
     bool c13_active = false;
+    void *c13_peer[16][3] = {};         // IPC-mapped {hist32, hist64, stats} of every rank (own entries = own buffers)
+    int c13_n_peers = 0, c13_my_rank = 0;
     aix_count_stats c13_range_invalid = {0, 0, 0, 0};
     // canonical23 result kept between the two passes
     uint64_t *c23_kmers_dev = nullptr;

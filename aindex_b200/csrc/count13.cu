@@ -21,6 +21,7 @@ constexpr uint32_t kMask26 = (1u << 26) - 1;
 // statistics buffer (u64): [3] out-of-range ids, [4] FASTQ line counter, [kStatBase + 3*slot + j] =
 // sequences / windows / valid of slot `slot` (summed on the host in aix_count13_stats)
 constexpr uint32_t kStatBase = 8, kStatSlots = 64, kStatWords = kStatBase + 3 * kStatSlots;
+constexpr uint32_t kStatFlushed = 5;  // non-zero once part of the counts has been moved to the u64 histogram
 
 // ---- SIMD classification of 16 input bytes -------------------------------------------------
 // codes: 16 two-bit codes, byte 0 in bits 31:30 ... byte 15 in bits 1:0 (A0 C1 G2 T3 via
@@ -365,6 +366,38 @@ __global__ void __launch_bounds__(kCntBlock) fastq_mask_kernel(uint8_t *__restri
 }
 
 
+// ---- histogram combine over NVLink peer memory (one rank per GPU) ---------------------------------------
+// Rank r owns the k-mer range [v_begin, v_end).  Instead of widening its whole 256 MiB u32 histogram to u64
+// and handing 512 MiB to an NCCL reduce-scatter, every rank reads its range straight out of the u32 histograms
+// of all ranks (peer loads through NVLink / NVSwitch, 16 bytes per lane), adds them up in u64 and writes its
+// slice: widen + reduce-scatter in one kernel, a quarter of the bytes on the wire.  A peer that already moved
+// counts to its u64 histogram (flag word) contributes that slice too.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    const uint32_t *h32[kMaxPeers];
+    const unsigned long long *h64[kMaxPeers];
+    const unsigned long long *stats[kMaxPeers];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) count13_reduce_peers_kernel(PeerTable t, uint32_t v_begin, uint32_t count,
+                                                                 unsigned long long *__restrict__ out) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i >= count) return;  // count is a multiple of 4 (4^13 / world)
+    unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int p = 0; p < t.n; ++p) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(t.h32[p] + v_begin + i);
+        a0 += x.x; a1 += x.y; a2 += x.z; a3 += x.w;
+        if (t.stats[p][kStatFlushed]) {
+            const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(t.h64[p] + v_begin + i);
+            const ulonglong2 y1 = *reinterpret_cast<const ulonglong2 *>(t.h64[p] + v_begin + i + 2);
+            a0 += y0.x; a1 += y0.y; a2 += y1.x; a3 += y1.y;
+        }
+    }
+    *reinterpret_cast<ulonglong2 *>(out + i) = make_ulonglong2(a0, a1);
+    *reinterpret_cast<ulonglong2 *>(out + i + 2) = make_ulonglong2(a2, a3);
+}
+
 // ---- FASTA: concatenate the lines of a record, drop header lines (count_kmers13.cpp:211-235) ----------
 // Output byte stream (counted as plain text afterwards): sequence-line bytes without their newlines, and
 // one '\n' for every header line (it ends the record before it; empty records are empty lines, which the
@@ -566,6 +599,7 @@ static int c13_alloc(aix_ctx *ctx) {
 static int c13_flush_on(aix_ctx *ctx, cudaStream_t st) {
     flush_hist_kernel<<<aix_grid(AIX_TOTAL_13MERS, 256), 256, 0, st>>>(ctx->c13_hist32, ctx->c13_hist64);
     AIX_LAUNCH_CHECK(ctx);
+    AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_stats_dev + kStatFlushed, 1, 8, st));
     ctx->c13_pending_windows = 0;
     return AIX_OK;
 }
@@ -871,6 +905,80 @@ int aix_count13_finish(aix_ctx *ctx, const aix_mphf *m, uint64_t v_begin, uint64
         stats->valid -= oor;  // count_kmers13.cpp:153-156
         stats->invalid += oor;
     }
+    return AIX_OK;
+}
+
+
+// ---- peer-memory combine: handles are exchanged by the caller (any transport), 3 x 64 bytes per rank --------
+int aix_count13_ipc_export(aix_ctx *ctx, void *handles_out) {
+    if (!ctx || !handles_out) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_TRY(c13_alloc(ctx));
+    cudaIpcMemHandle_t h[3];
+    AIX_CUDA(ctx, cudaIpcGetMemHandle(&h[0], ctx->c13_hist32));
+    AIX_CUDA(ctx, cudaIpcGetMemHandle(&h[1], ctx->c13_hist64));
+    AIX_CUDA(ctx, cudaIpcGetMemHandle(&h[2], ctx->c13_stats_dev));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles_out, h, sizeof h);
+    return AIX_OK;
+}
+
+int aix_count13_peers_close(aix_ctx *ctx) {
+    if (!ctx) return AIX_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    for (int p = 0; p < ctx->c13_n_peers; ++p) {
+        if (p == ctx->c13_my_rank) continue;
+        for (int k = 0; k < 3; ++k)
+            if (ctx->c13_peer[p][k]) cudaIpcCloseMemHandle(ctx->c13_peer[p][k]);
+    }
+    memset(ctx->c13_peer, 0, sizeof ctx->c13_peer);
+    ctx->c13_n_peers = 0;
+    return AIX_OK;
+}
+
+int aix_count13_peers_open(aix_ctx *ctx, const void *handles, int n_ranks, int my_rank) {
+    if (!ctx || !handles || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_TRY(c13_alloc(ctx));
+    aix_count13_peers_close(ctx);
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+    ctx->c13_n_peers = n_ranks;
+    ctx->c13_my_rank = my_rank;
+    for (int p = 0; p < n_ranks; ++p) {
+        if (p == my_rank) {
+            ctx->c13_peer[p][0] = ctx->c13_hist32; ctx->c13_peer[p][1] = ctx->c13_hist64; ctx->c13_peer[p][2] = ctx->c13_stats_dev;
+            continue;
+        }
+        for (int k = 0; k < 3; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&ctx->c13_peer[p][k], h[3 * p + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->c13_peer[p][k] = nullptr;
+                aix_count13_peers_close(ctx);
+                return ctx->fail(AIX_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+            }
+        }
+    }
+    return AIX_OK;
+}
+
+int aix_count13_reduce_peers_dev(aix_ctx *ctx, uint64_t v_begin, uint64_t v_end, uint64_t *out_dev) {
+    if (!ctx || !out_dev) return AIX_ERR_ARG;
+    if (!ctx->c13_active) return ctx->fail(AIX_ERR_STATE, "count13 not active");
+    if (ctx->c13_n_peers < 1) return ctx->fail(AIX_ERR_STATE, "aix_count13_peers_open not called");
+    if (v_begin > v_end || v_end > AIX_TOTAL_13MERS || ((v_end - v_begin) & 3) || (v_begin & 3)) return ctx->fail(AIX_ERR_ARG, "bad k-mer range");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (v_end == v_begin) return AIX_OK;
+    PeerTable t;
+    t.n = ctx->c13_n_peers;
+    for (int p = 0; p < t.n; ++p) {
+        t.h32[p] = (const uint32_t *)ctx->c13_peer[p][0];
+        t.h64[p] = (const unsigned long long *)ctx->c13_peer[p][1];
+        t.stats[p] = (const unsigned long long *)ctx->c13_peer[p][2];
+    }
+    const uint32_t count = (uint32_t)(v_end - v_begin);
+    count13_reduce_peers_kernel<<<aix_grid(count / 4, 256), 256, 0, ctx->stream>>>(t, (uint32_t)v_begin, count, (unsigned long long *)out_dev);
+    AIX_LAUNCH_CHECK(ctx);
     return AIX_OK;
 }
 

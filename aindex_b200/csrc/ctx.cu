@@ -56,6 +56,7 @@ void aix_ctx_destroy(aix_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto &b : ctx->scratch)
         if (b.p) cudaFree(b.p);
+    aix_count13_peers_close(ctx);
     if (ctx->small_host) cudaFreeHost(ctx->small_host);
     if (ctx->c13_hist32) cudaFree(ctx->c13_hist32);
     if (ctx->c13_hist64) cudaFree(ctx->c13_hist64);

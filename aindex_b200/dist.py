@@ -93,6 +93,54 @@ def reduce_scatter_hist(hist, group=None):
     return out
 
 
+class PeerHistogram:
+    """The fused form of `flush + reduce_scatter_hist` for one-node runs: every rank maps the u32 histograms of
+    all ranks (CUDA IPC over NVLink / NVSwitch) and sums its k-mer range out of them in one kernel
+    (aix_count13_reduce_peers_dev).  The two stream-ordered barriers around the kernel are tiny NCCL all-reduces.
+
+        ph = PeerHistogram(ctx, group)            # once; raises RuntimeError if peer mapping is not possible
+        ... aix_count13_begin / add ...
+        mine = ph.reduce(stream)                  # int64[4^13 / world], this rank's range, summed over ranks
+    """
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.ctx, self.group, self.lib = ctx, group, capi.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        mine = (C.c_uint8 * 192)()
+        ctx.check(self.lib.aix_count13_ipc_export(ctx.handle, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t, group=group)
+        blob = bytes(torch.cat(parts).cpu().numpy().tobytes())
+        rc = self.lib.aix_count13_peers_open(ctx.handle, blob, self.world, self.rank)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks agree on the path
+        if int(ok.item()) == 0:
+            self.lib.aix_count13_peers_close(ctx.handle)
+            raise RuntimeError("peer mapping of the 13-mer histograms failed on some rank")
+        self.lo, self.hi = kmer_range(self.rank, self.world)
+        self.out = torch.empty(self.hi - self.lo, dtype=torch.int64, device=self.dev)
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    def reduce(self, stream):
+        """Enqueue barrier -> gather-reduce kernel -> barrier on `stream` (the library's stream); returns the slice."""
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.stream(stream):
+            dist.all_reduce(self._token, group=self.group)   # every rank has finished counting
+            self.ctx.check(self.lib.aix_count13_reduce_peers_dev(self.ctx.handle, self.lo, self.hi, self.out.data_ptr()))
+            dist.all_reduce(self._token, group=self.group)   # nobody clears its histogram while a peer still reads it
+        return self.out
+
+    def close(self):
+        self.lib.aix_count13_peers_close(self.ctx.handle)
+
+
 def sum_to_rank0(t, group=None):
     """Element-wise sum of a tensor onto rank 0 (the scattered MPHF-order partial results)."""
     import torch.distributed as dist

@@ -451,6 +451,10 @@ def run_ours(args):
         def count_step():
             ctx.check(lib.aix_count13_begin(ctx.handle))
             ctx.check(lib.aix_count13_add_dev(ctx.handle, creads.data_ptr(), n_bytes, capi.FMT_PLAIN))
+            if peer is not None:
+                # widen + reduce-scatter fused into one kernel over NVLink peer memory (aindex_b200/dist.py)
+                peer.reduce(stream)
+                return
             ctx.check(lib.aix_count13_flush(ctx.handle))
             if world > 1:
                 # per-GPU 4^13 histograms -> NCCL reduce-scatter over k-mer ranges (rank r owns
@@ -459,6 +463,14 @@ def run_ours(args):
                 with torch.cuda.stream(stream):
                     dist.reduce_scatter_tensor(rs_out, hist_tensor, op=dist.ReduceOp.SUM)
 
+        peer = None
+        if world > 1 and os.environ.get("AIX_COUNT13_COLLECTIVE", "peer") == "peer":
+            from aindex_b200 import dist as D
+            try:
+                peer = D.PeerHistogram(ctx)
+            except Exception as e:  # IPC not available between these processes: NCCL reduce-scatter instead
+                sys.stderr.write(f"[bench] peer-memory combine unavailable ({e}); using NCCL reduce-scatter\n")
+                peer = None
         if world > 1:
             import ctypes as C
             ctx.check(lib.aix_count13_begin(ctx.handle))
@@ -488,7 +500,9 @@ def run_ours(args):
         kps = world * n_kmers / (c_ms / 1e3)
         extra["count13"] = {"metric": "13-mer k-mers counted/s", "value": kps, "unit": "k-mers/s", "ms_per_step": c_ms,
                             "reads_per_gpu": args.count_reads, "kmers_per_gpu": n_kmers, "stats_ok": bool(ok),
-                            "collective": "nccl reduce_scatter(sum) of the 4^13 u64 histogram" if world > 1 else None,
+                            "collective": (None if world == 1 else
+                                           "fused widen + gather-reduce over NVLink peer memory (CUDA IPC), NCCL barriers" if peer is not None
+                                           else "nccl reduce_scatter(sum) of the 4^13 u64 histogram"),
                             "hbm_frac_9.09B": kps / world * C3_BYTES_PER_KMER / 1e9 / peak_gbs,
                             "atomic_roofline": {"achieved_gred_s": kps / world / 1e9,
                                                 "frac_of_256MiB_table_red_rate": kps / world / 1e9 / RED_PEAK_256M_G,

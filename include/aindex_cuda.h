@@ -205,6 +205,16 @@ int aix_count13_finish(aix_ctx *ctx, const aix_mphf *m, uint64_t v_begin, uint64
 int aix_count13_finish_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t v_begin, uint64_t v_end,
                            uint64_t *tf_out_dev);
 int aix_count13_end(aix_ctx *ctx);
+/* Histogram combine over NVLink peer memory instead of widen + NCCL reduce-scatter (one rank per GPU, one node):
+ *   export (3 x 64-byte CUDA IPC handles) -> the caller all-gathers the handles -> peers_open(all, n, my_rank)
+ *   begin -> add ... -> [caller: barrier on the stream] -> reduce_peers_dev(my range) -> [caller: barrier] -> ...
+ * reduce_peers_dev writes out_dev[v - v_begin] = sum over ranks of their counts of k-mer v (u64, direct-address
+ * order): what aix_count13_flush + reduce-scatter + slicing would give.  No flush is needed before it. */
+int aix_count13_ipc_export(aix_ctx *ctx, void *handles_out /* 192 bytes */);
+int aix_count13_peers_open(aix_ctx *ctx, const void *handles /* n_ranks x 192 bytes */, int n_ranks,
+                           int my_rank);
+int aix_count13_reduce_peers_dev(aix_ctx *ctx, uint64_t v_begin, uint64_t v_end, uint64_t *out_dev);
+int aix_count13_peers_close(aix_ctx *ctx);
 
 /* ---- coverage: aindex/core/aindex.py:314-322 ------------------------------------- */
 /* n_seq sequences concatenated in `seqs`, sequence s = seqs[offs[s] .. offs[s+1]).

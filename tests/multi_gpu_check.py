@@ -38,6 +38,36 @@ def main():
         want, wst = ctx.count13(m13, data, capi.FMT_PLAIN)
         ok = bool(np.array_equal(tf, want)) and st == wst
         print(f"count13 x{world}: equal={ok} valid={st['valid']} md5={hashlib.md5(tf.tobytes()).hexdigest()}")
+    # the fused combine over peer memory must give the slices the NCCL reduce-scatter gives
+    lib = capi.lib()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    try:
+        peer = D.PeerHistogram(ctx)
+    except RuntimeError as ex:
+        peer = None
+        if rank == 0:
+            print(f"peer combine unavailable: {ex}")
+    if peer is not None:
+        for force_flush in (False, True):
+            ctx.check(lib.aix_count13_begin(ctx.handle))
+            half = ((e - b) // 2 // 101) * 101
+            ctx.check(lib.aix_count13_add(ctx.handle, data[b:b + half].ctypes.data, half, capi.FMT_PLAIN))
+            if force_flush and rank % 2 == 0:
+                ctx.check(lib.aix_count13_flush(ctx.handle))  # some ranks hold part of their counts in the u64 histogram
+            ctx.check(lib.aix_count13_add(ctx.handle, data[b + half:e].ctypes.data, e - b - half, capi.FMT_PLAIN))
+            mine = peer.reduce(stream).clone()
+            stream.synchronize()
+            ctx.check(lib.aix_count13_flush(ctx.handle))
+            hist = D.wrap_device_i64(lib.aix_count13_hist_dev(ctx.handle), 1 << 26, torch.device("cuda", local))
+            with torch.cuda.stream(stream):
+                ref = D.reduce_scatter_hist(hist)
+            stream.synchronize()
+            same = bool(torch.equal(mine, ref))
+            ok = ok and same
+            ctx.check(lib.aix_count13_end(ctx.handle))
+            if rank == 0:
+                print(f"peer combine (flush on even ranks={force_flush}): equal={same}")
+        peer.close()
     # sharded queries
     q = ctx.decode(np.fromfile(os.path.join(g, "idx23.kmers.bin"), dtype=np.uint64)[:5000], 23)
     q[::3] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(len(q[::3]), 23))
