@@ -496,6 +496,18 @@ def run_ours(args):
         extra_wall_ms = wall * 1e3 / args.steps
         st = capi.CountStats()
         ctx.check(lib.aix_count13_stats(ctx.handle, st))
+        peer_equal = None
+        if peer is not None:
+            # untimed: the fused combine must give exactly the slice the NCCL reduce-scatter gives
+            with torch.cuda.stream(stream):
+                mine = peer.out.clone()
+            ctx.check(lib.aix_count13_flush(ctx.handle))
+            with torch.cuda.stream(stream):
+                dist.reduce_scatter_tensor(rs_out, hist_tensor, op=dist.ReduceOp.SUM)
+                same = torch.tensor([1 if torch.equal(mine, rs_out) else 0], device=dev, dtype=torch.int32)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ctx.sync()
+            peer_equal = bool(int(same.item()))
         ok = st.valid == n_kmers and st.sequences == args.count_reads
         kps = world * n_kmers / (c_ms / 1e3)
         extra["count13"] = {"metric": "13-mer k-mers counted/s", "value": kps, "unit": "k-mers/s", "ms_per_step": c_ms,
@@ -509,7 +521,7 @@ def run_ours(args):
                                                 "frac_of_L2_resident_red_rate": kps / world / 1e9 / RED_PEAK_L2_G,
                                                 "peaks_gred_s": {"256MiB_table": RED_PEAK_256M_G, "64MiB_slice": RED_PEAK_L2_G},
                                                 "source": "profiles/r01_atomic_roofline.txt"},
-                            "gpu_launches_per_step": int(count_launches)}
+                            "gpu_launches_per_step": int(count_launches), "fused_combine_equals_nccl_reduce_scatter": peer_equal}
         extra["count13"]["wall_ms_per_step"] = extra_wall_ms
         if not args.no_e2e:
             # e2e: the shard starts in pinned host memory; H2D chunks overlap the count kernel

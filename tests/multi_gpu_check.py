@@ -55,7 +55,9 @@ def main():
             if force_flush and rank % 2 == 0:
                 ctx.check(lib.aix_count13_flush(ctx.handle))  # some ranks hold part of their counts in the u64 histogram
             ctx.check(lib.aix_count13_add(ctx.handle, data[b + half:e].ctypes.data, e - b - half, capi.FMT_PLAIN))
-            mine = peer.reduce(stream).clone()
+            out = peer.reduce(stream)
+            with torch.cuda.stream(stream):  # everything that touches the library's buffers stays on its stream
+                mine = out.clone()
             stream.synchronize()
             ctx.check(lib.aix_count13_flush(ctx.handle))
             hist = D.wrap_device_i64(lib.aix_count13_hist_dev(ctx.handle), 1 << 26, torch.device("cuda", local))
