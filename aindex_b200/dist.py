@@ -111,13 +111,15 @@ class PeerHistogram:
         self.ctx, self.group, self.lib = ctx, group, capi.lib()
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        # no rank may leave this constructor early: every failure is carried to the agreement all-reduce below
         mine = (C.c_uint8 * 192)()
-        ctx.check(self.lib.aix_count13_ipc_export(ctx.handle, mine))
+        rc = self.lib.aix_count13_ipc_export(ctx.handle, mine)
         t = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
         parts = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(parts, t, group=group)
         blob = bytes(torch.cat(parts).cpu().numpy().tobytes())
-        rc = self.lib.aix_count13_peers_open(ctx.handle, blob, self.world, self.rank)
+        if rc == 0:
+            rc = self.lib.aix_count13_peers_open(ctx.handle, blob, self.world, self.rank)
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks agree on the path
         if int(ok.item()) == 0:
