@@ -98,16 +98,24 @@ __global__ void __launch_bounds__(kCovBlock) coverage_kernel(Index23Dev ix, Mphf
         load_window23(p, r0, r1, r2);
         tf = find23_window<kCanon>(ix, m, r0, r1, r2).tf;
     } else {
-        // get_tf_value_13mer: upper-case ACGT only, u64 count narrowed to u32
-        uint32_t v = 0;
-        bool valid = true;
+        // get_tf_value_13mer: upper-case ACGT only, u64 count narrowed to u32.  13 bytes at any alignment are
+        // inside four aligned words (offset <= 3, so the last byte is at most byte 15); SIMD encode + validity as in the batch query kernel
+        const uintptr_t a = (uintptr_t)p;
+        const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8u;
+        const uint32_t x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3);
+        const uint32_t y[4] = {__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                               (x3 >> sh) & 0xFFu};
+        uint32_t pk[4], bad = 0;
 #pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            uint32_t ch = __ldg(p + j);
-            valid = valid && is_acgt_upper(ch);
-            v = (v << 2) | base_code_strict(ch);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c4 = ((y[j] >> 1) ^ (y[j] >> 2)) & 0x03030303u;
+            pk[j] = j == 3 ? (c4 & 3u) : ((c4 * 0x40100401u) >> 24);
+            const uint32_t diff = expect_acgt4(c4) ^ y[j];
+            bad |= j == 3 ? (diff & 0xFFu) : diff;
         }
-        tf = valid ? (uint32_t)__ldg(tf13_direct + v) : 0u;
+        const uint32_t v = (pk[0] << 18) | (pk[1] << 10) | (pk[2] << 2) | pk[3];
+        tf = bad == 0 ? (uint32_t)__ldg(tf13_direct + v) : 0u;
     }
     __stcs(out + o, tf >= cutoff ? tf : 0u);
 }
