@@ -282,12 +282,12 @@ __global__ void positions_query_kernel(Index23Dev ix, MphfDev m, const unsigned 
                                        const uint8_t *__restrict__ lens, uint64_t q, unsigned long long *__restrict__ counts,
                                        const unsigned long long *__restrict__ out_off, unsigned long long *__restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q) return;
-    uint32_t len = lens ? lens[i] : stride;
+    const bool active = i < q;  // inactive lanes of the last warp still take part in the warp-wide slice scans
+    uint32_t len = active ? (lens ? lens[i] : stride) : 0u;
     if (len > stride) len = stride;
-    const uint8_t *p = recs + i * stride;
+    const uint8_t *p = recs + (active ? i : 0) * stride;
     uint64_t h = kNoBucket;
-    if (len == (uint32_t)K) {
+    if (active && len == (uint32_t)K) {
         if (K == 23) {
             // get_pfid (hash.hpp:150-170): single probe of the lexicographically smaller string
             uint64_t w[3] = {0, 0, 0};
@@ -308,20 +308,35 @@ __global__ void positions_query_kernel(Index23Dev ix, MphfDev m, const unsigned 
             h = bucket13(m, p);  // python_wrapper.cpp:1076-1087: upper-case ACGT only
         }
     }
-    unsigned long long cnt = 0;
+    // bucket slices are scanned by the whole warp, one query (lane) after the other: coalesced 256-byte reads and
+    // writes, zeros squeezed out in order with a ballot (python_wrapper.cpp:816-820: skip 0, store pos - 1)
+    unsigned long long b = 0, e = 0;
     if (h != kNoBucket && h + 1 < n_indices) {
-        unsigned long long b = indices[h], e = indices[h + 1];
+        b = indices[h];
+        e = indices[h + 1];
         if (e > n_positions) e = n_positions;  // python_wrapper.cpp:1092
-        unsigned long long w = out ? out_off[i] : 0;
-        for (unsigned long long j = b; j < e; ++j) {
-            unsigned long long v = positions[j];
-            if (v) {
-                if (out) out[w + cnt] = v - 1;
-                ++cnt;
-            }
-        }
+        if (e < b) e = b;
     }
-    if (counts) counts[i] = cnt;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long w = (out && e > b) ? out_off[i] : 0;
+    unsigned long long cnt = 0;
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, e > b);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned long long sb = __shfl_sync(0xFFFFFFFFu, b, src), se = __shfl_sync(0xFFFFFFFFu, e, src);
+        const unsigned long long sw = __shfl_sync(0xFFFFFFFFu, w, src);
+        unsigned long long done = 0;
+        for (unsigned long long j0 = sb; j0 < se; j0 += 32) {
+            const unsigned long long j = j0 + lane;
+            const unsigned long long v = j < se ? __ldg(positions + j) : 0ull;
+            const unsigned nz = __ballot_sync(0xFFFFFFFFu, v != 0);
+            if (out && v) out[sw + done + __popc(nz & ((1u << lane) - 1u))] = v - 1;
+            done += __popc(nz);
+        }
+        if ((int)lane == src) cnt = done;
+    }
+    if (counts && active) counts[i] = cnt;
 }
 
 }  // namespace aix
