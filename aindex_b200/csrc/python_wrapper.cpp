@@ -234,9 +234,8 @@ private:
     }
 
     template <typename T>
-    std::vector<T> query23(const std::vector<std::string> &kmers, int mode, size_t per = 1) const {
+    std::vector<T> run23(const Records &r, int mode, size_t per = 1) const {
         require23();
-        Records r = pack_records(kmers);
         std::vector<T> out(r.q * per);
         if (r.q) {
             py::gil_scoped_release nogil;
@@ -245,14 +244,21 @@ private:
         return out;
     }
     template <typename T>
-    std::vector<T> query13(const std::vector<std::string> &kmers, int mode, size_t per = 1) const {
-        Records r = pack_records(kmers);
+    std::vector<T> run13(const Records &r, int mode, size_t per = 1) const {
         std::vector<T> out(r.q * per);
         if (r.q) {
             py::gil_scoped_release nogil;
             check(aix_tf13_batch(ctx, ix13, r.bytes.data(), r.stride, r.lens_ptr(), r.q, mode, out.data()));
         }
         return out;
+    }
+    template <typename T>
+    std::vector<T> query23(const std::vector<std::string> &kmers, int mode, size_t per = 1) const {
+        return run23<T>(pack_records(kmers), mode, per);
+    }
+    template <typename T>
+    std::vector<T> query13(const std::vector<std::string> &kmers, int mode, size_t per = 1) const {
+        return run13<T>(pack_records(kmers), mode, per);
     }
 
 public:
@@ -392,6 +398,18 @@ public:
     }
 
     // ------------------------------------------------------------------ tf queries
+    // list overloads of the batch calls: the str buffers are read in place (pack_records_py), registered in front of
+    // the std::vector<std::string> forms, which stay for other sequences
+    std::vector<uint32_t> tf_values_23mer_list(const py::list &kmers) { return run23<uint32_t>(pack_records_py(kmers), AIX_Q_TF); }
+    std::vector<uint64_t> total_tf_values_23mer_list(const py::list &kmers) { return run23<uint64_t>(pack_records_py(kmers), AIX_Q_TOTAL); }
+    std::vector<uint32_t> tf_values_13mer_list(const py::list &kmers) {
+        if (!is_13mer_mode) return std::vector<uint32_t>(kmers.size(), 0);
+        return run13<uint32_t>(pack_records_py(kmers), AIX_Q_TF);
+    }
+    std::vector<uint64_t> total_tf_values_13mer_list(const py::list &kmers) {
+        if (!is_13mer_mode) return std::vector<uint64_t>(kmers.size(), 0);
+        return run13<uint64_t>(pack_records_py(kmers), AIX_Q_TOTAL);
+    }
     std::vector<uint32_t> get_tf_values_23mer(const std::vector<std::string> &kmers) { return query23<uint32_t>(kmers, AIX_Q_TF); }
     uint32_t get_tf_value_23mer(const std::string &kmer) { return query23<uint32_t>({kmer}, AIX_Q_TF)[0]; }
 
@@ -872,6 +890,7 @@ PYBIND11_MODULE(aindex_cpp, m) {
         .def("debug_kmer_tf_values", &AindexWrapper::debug_kmer_tf_values)
         .def("get_index_info", &AindexWrapper::get_index_info)
         .def("get_total_tf_value_13mer", &AindexWrapper::get_total_tf_value_13mer)
+        .def("get_total_tf_values_13mer", &AindexWrapper::total_tf_values_13mer_list)
         .def("get_total_tf_values_13mer", &AindexWrapper::get_total_tf_values_13mer)
         .def("get_tf_both_directions_13mer", &AindexWrapper::get_tf_both_directions_13mer)
         .def("get_tf_both_directions_13mer_batch", &AindexWrapper::get_tf_both_directions_13mer_batch)
@@ -879,9 +898,12 @@ PYBIND11_MODULE(aindex_cpp, m) {
         .def("get_13mer_statistics", &AindexWrapper::get_13mer_statistics)
         .def("get_13mer_tf_array", &AindexWrapper::get_13mer_tf_array)
         .def("get_tf_by_index_13mer", &AindexWrapper::get_tf_by_index_13mer)
+        .def("get_tf_values_13mer", &AindexWrapper::tf_values_13mer_list)
         .def("get_tf_values_13mer", &AindexWrapper::get_tf_values_13mer)
+        .def("get_tf_values_23mer", &AindexWrapper::tf_values_23mer_list)
         .def("get_tf_values_23mer", &AindexWrapper::get_tf_values_23mer)
         .def("get_total_tf_value_23mer", &AindexWrapper::get_total_tf_value_23mer)
+        .def("get_total_tf_values_23mer", &AindexWrapper::total_tf_values_23mer_list)
         .def("get_total_tf_values_23mer", &AindexWrapper::get_total_tf_values_23mer)
         .def("get_tf_both_directions_23mer", &AindexWrapper::get_tf_both_directions_23mer)
         .def("get_tf_both_directions_23mer_batch", &AindexWrapper::get_tf_both_directions_23mer_batch)
