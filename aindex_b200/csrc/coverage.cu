@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t find_seq(const unsigned long long *__restric
 
 // cta_seq[b] = sequence that holds output b * 256 (one thread per CTA of the main kernel, b = 0 .. n_ctas;
 // the last entry is n_seq - 1).  Doing these ~20-step searches here, all in parallel, instead of by two threads
-// of every CTA in front of a barrier removed the largest stall of the first version (profiles/r01_c4c5_ncu.txt:
+// of every CTA in front of a barrier removed the largest stall of the first version (profiles/r01_c4_ncu_before.txt:
 // barrier 9.5 of 24 stall cycles per issue).
 __global__ void coverage_cta_seq_kernel(const unsigned long long *__restrict__ out_offs, uint64_t n_seq, uint64_t total_out,
                                         uint64_t n_ctas, uint32_t *__restrict__ cta_seq) {
