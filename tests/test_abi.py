@@ -61,3 +61,28 @@ def test_product_does_not_import_oracle():
                 if re.search(r"(from|import)\s+oracle\b|oracle/|liboracle|aindex_oracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_bench_contract_without_gpu():
+    """bench.py on a box without a GPU: our arm refuses loudly (no CPU fallback), the reference arm prints the
+    one-line JSON the contract asks for, and nothing else reaches stdout."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible: this is the no-GPU contract")
+    except ImportError:
+        pytest.skip("torch missing")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and "unavailable" in d
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=300)
+    assert r.returncode != 0 and r.stdout.strip() == "" and "no CUDA device" in r.stderr
