@@ -8,9 +8,9 @@
 Every config is run at BASELINE size on one B200 with all buffers resident in HBM, timed with
 CUDA events on the library stream, checked through size-independent properties at full size and
 against the CPU oracle / the compiled reference on a bounded sample, and printed as one JSON line.
-Test/bench infrastructure: the only place besides tests/ and bench.py that touches oracle/.
+Test infrastructure (it lives under tests/ because it checks against oracle/ and the compiled reference).
 
-  python profiles/bench_configs.py --configs c1,c4,c5 [--scale 1.0] [--out gpurun_out/configs.json]
+  python tests/bench_configs.py --configs c1,c4,c5 [--scale 1.0] [--out gpurun_out/configs.json]
 """
 from __future__ import annotations
 

@@ -4,7 +4,7 @@ the very inputs the headline numbers are measured on.
 
   C2  100 M random + 20 M half-hit 23-mer queries on the 50 M-key index
   C3  one GPU's shard of the 13-mer counting job: 25 M x 150 bp reads (3.45 G windows)
-  C4  coverage of 1 M x 10 kb sequences;  C5  positions index over 50 M reads (profiles/bench_configs.py)
+  C4  coverage of 1 M x 10 kb sequences;  C5  positions index over 50 M reads (tests/bench_configs.py)
 """
 import os
 import sys
@@ -16,7 +16,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "profiles"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 @pytest.fixture(scope="module")
@@ -171,7 +171,7 @@ def test_c3_full_size_shard_properties(env):
 
 @pytest.mark.parametrize("config", ["c4", "c5"])
 def test_c4_c5_full_size(env, config):
-    """profiles/bench_configs.py at scale 1.0: every full-size property and every comparison with the
+    """tests/bench_configs.py at scale 1.0: every full-size property and every comparison with the
     oracle / the compiled reference must hold (the timings it also takes are not asserted)."""
     import bench_configs
     env.torch.cuda.empty_cache()
