@@ -70,6 +70,26 @@ def shard_reads(data: np.ndarray, world: int, lines_per_record: int = 1) -> List
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def shard_fasta(data: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """Byte ranges of a FASTA buffer, one per rank, every range starting at a header line ('>' at a line start), so
+    no record (whose lines are concatenated before counting, count_kmers13.cpp:211-235) is split between ranks."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    n = int(data.size)
+    cuts = [0]
+    if world > 1 and n:
+        gt = np.flatnonzero(data == ord(">"))
+        starts = gt[(gt == 0) | (data[np.maximum(gt - 1, 0)] == 10)]  # '>' at a line start only
+        for r in range(1, world):
+            target = (n * r) // world
+            i = int(np.searchsorted(starts, target, side="left"))
+            cut = int(starts[i]) if i < starts.size else n
+            cuts.append(min(max(cut, cuts[-1]), n))
+    while len(cuts) < world:
+        cuts.append(n)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def reduce_scatter_hist(hist, group=None):
     """Sum the per-rank direct-address histograms; return this rank's k-mer slice.
 

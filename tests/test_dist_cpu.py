@@ -48,6 +48,33 @@ def test_shard_reads_plain_and_fastq(world):
         D.kmer_range(0, 3)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_fasta_keeps_records_whole(world):
+    """every shard starts at a header; the per-shard oracle counts add up to the whole file's"""
+    from oracle import oracle as O
+    O.build()
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(60):
+        recs.append(b">r%d with > inside" % i)
+        for _ in range(int(rng.integers(0, 6))):
+            recs.append(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(1, 70))).tobytes())
+    data = np.frombuffer(b"\n".join(recs) + b"\n", dtype=np.uint8)
+    shards = D.shard_fasta(data, world)
+    assert len(shards) == world and shards[0][0] == 0 and shards[-1][1] == data.size
+    whole, wst = O.count13_direct(data, O.FMT_FASTA)
+    acc = np.zeros_like(whole)
+    tot = {k: 0 for k in wst}
+    for b, e in shards:
+        assert b == e or (data[b] == ord(">") and (b == 0 or data[b - 1] == 10))
+        if e > b:
+            h, st = O.count13_direct(data[b:e], O.FMT_FASTA)
+            acc += h
+            for k in tot:
+                tot[k] += st[k]
+    assert np.array_equal(acc, whole) and tot == wst
+
+
 def _worker(rank, world, port, fastq, q):
     import torch
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
