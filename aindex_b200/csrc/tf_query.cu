@@ -418,6 +418,7 @@ static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_
         const uint64_t n_tiles = q / 32;
         if (ix->canonical_only) {
             if (tf23_min_blocks() >= 6) launch_stream<kMode, true, 6>(ctx, st, id, md, recs, n_tiles, out);
+            else if (tf23_min_blocks() == 5) launch_stream<kMode, true, 5>(ctx, st, id, md, recs, n_tiles, out);
             else launch_stream<kMode, true, 1>(ctx, st, id, md, recs, n_tiles, out);
         } else {
             launch_stream<kMode, false, 6>(ctx, st, id, md, recs, n_tiles, out);
