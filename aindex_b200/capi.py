@@ -80,6 +80,7 @@ SIGNATURES = {
     "aix_get_freq23": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "aix_index13_upload": (_i, [_vp, _vp, _vp, _pp]),
     "aix_index13_destroy": (None, [_vp, _vp]),
+    "aix_index13_tf_direct": (_i, [_vp, _vp, _vp]),
     "aix_tf13_batch": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
     "aix_tf13_batch_dev": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
     "aix_count13": (_i, [_vp, _vp, _vp, _u64, _i, _vp, C.POINTER(CountStats)]),

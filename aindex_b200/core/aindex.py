@@ -403,6 +403,34 @@ class AIndex:
     def get_13mer_statistics(self) -> Dict[str, int]:
         return self._wrapper.get_13mer_statistics()
 
+    def get_top_kmers(self, n: int = 100, min_tf: int = 1, kmer_type: str = "auto") -> List[Tuple[str, int]]:
+        """The n most frequent k-mers as (kmer, tf), most frequent first (aindex.py:683-701)."""
+        return list(self.iter_kmers_by_frequency(min_tf=min_tf, max_kmers=n, kmer_type=kmer_type))
+
+    def get_kmer_frequency_stats(self, kmer_type: str = "auto") -> dict:
+        """Summary of the tf array (aindex.py:703-795): same keys, computed with numpy instead of Python loops."""
+        import numpy as np
+        if not self._loaded:
+            raise RuntimeError("Index not loaded")
+        if kmer_type == "auto":
+            kmer_type = "13mer" if self.k == 13 else "23mer"
+        if kmer_type == "13mer":
+            tf = np.asarray(self._wrapper.get_13mer_tf_array(), dtype=np.uint64)
+        elif kmer_type == "23mer":
+            if self.get_hash_size() == 0:
+                raise RuntimeError("23-mer index not properly loaded")
+            tf = np.asarray(self._wrapper.get_tf_array_23mer(), dtype=np.uint64)
+        else:
+            raise ValueError(f"Unsupported kmer_type: {kmer_type}. Use '13mer', '23mer', or 'auto'")
+        nz = tf[tf > 0]
+        total = int(tf.size)
+        return {
+            "kmer_type": kmer_type, "total_kmers": total, "non_zero_kmers": int(nz.size), "zero_kmers": total - int(nz.size),
+            "max_tf": int(nz.max()) if nz.size else 0, "min_tf": int(nz.min()) if nz.size else 0,
+            "avg_tf": float(nz.sum() / nz.size) if nz.size else 0, "total_tf": int(tf.sum()) if nz.size else 0,
+            "coverage": nz.size / total if total else 0,
+        }
+
     def get_23mer_statistics(self) -> str:
         return self._wrapper.get_23mer_statistics()
 
@@ -417,13 +445,17 @@ class AIndex:
         if kmer_type == "auto":
             kmer_type = "13mer" if self.k == 13 else "23mer"
         if kmer_type == "13mer":
-            tf = np.asarray(self._wrapper.get_13mer_tf_array(), dtype=np.uint32)
-            order = np.argsort(-tf.astype(np.int64), kind="stable")
-            # tf is in MPHF order: recover the k-mer of each id through the hash of all 13-mers
-            raise NotImplementedError("13-mer frequency iteration needs the inverse MPHF permutation; "
-                                      "use aindex_b200.capi.Mphf.perm13()")
-        n = self.get_hash_size()
-        tfs = np.fromiter((self._wrapper.get_kmer_info(i)[0] for i in range(n)), dtype=np.uint64, count=n)
+            # the tf file is in MPHF order; the direct-address copy (tf by 2-bit value) is what makes
+            # _index_to_13mer(index) name the right k-mer (the reference labels MPHF ids as if they were values)
+            tf = np.asarray(self._wrapper.get_13mer_tf_array_direct())
+            keep = np.flatnonzero(tf >= max(int(min_tf), 0))
+            order = keep[np.argsort(-tf[keep].astype(np.int64), kind="stable")]
+            if max_kmers is not None:
+                order = order[:max_kmers]
+            for v in order:
+                yield self._index_to_13mer(int(v)), int(tf[v])
+            return
+        tfs = np.asarray(self._wrapper.get_tf_array_23mer(), dtype=np.uint64)
         order = np.argsort(-tfs.astype(np.int64), kind="stable")
         emitted = 0
         for kid in order:

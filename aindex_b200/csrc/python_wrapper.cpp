@@ -678,6 +678,24 @@ public:
     uint64_t get_hash_size() { return is_13mer_mode ? kTotal13 : (uint64_t)checker.size(); }  // :846-851
     uint64_t get_reads_size() { return reads_size; }
 
+    // tf of every 13-mer indexed by its 2-bit value (addition): what get_13mer_tf_array would be if the MPHF were the identity
+    py::array_t<uint64_t> get_13mer_tf_array_direct() {
+        if (!is_13mer_mode || !ix13) throw std::runtime_error("13-mer index not loaded");
+        py::array_t<uint64_t> out((py::ssize_t)kTotal13);
+        uint64_t *o = out.mutable_data();
+        {
+            py::gil_scoped_release nogil;
+            check(aix_index13_tf_direct(ctx, ix13, o));
+        }
+        return out;
+    }
+    // tf of every stored 23-mer by kid (addition; the host copy the loader keeps for get_kmer_info)
+    py::array_t<uint32_t> get_tf_array_23mer() {
+        require23();
+        py::array_t<uint32_t> out((py::ssize_t)tf23.size());
+        if (!tf23.empty()) memcpy(out.mutable_data(), tf23.data(), tf23.size() * 4);
+        return out;
+    }
     std::vector<uint32_t> get_13mer_tf_array() {  // :983-990 (u64 -> u32 narrowing as in the reference)
         if (!is_13mer_mode) return {};
         const uint64_t *t = (const uint64_t *)tf13_map.ptr;
@@ -897,6 +915,8 @@ PYBIND11_MODULE(aindex_cpp, m) {
         .def("get_reverse_complement_13mer", &AindexWrapper::get_reverse_complement_13mer)
         .def("get_13mer_statistics", &AindexWrapper::get_13mer_statistics)
         .def("get_13mer_tf_array", &AindexWrapper::get_13mer_tf_array)
+        .def("get_13mer_tf_array_direct", &AindexWrapper::get_13mer_tf_array_direct, "uint64[4^13]: tf by 2-bit 13-mer value")
+        .def("get_tf_array_23mer", &AindexWrapper::get_tf_array_23mer, "uint32[n]: tf by kid")
         .def("get_tf_by_index_13mer", &AindexWrapper::get_tf_by_index_13mer)
         .def("get_tf_values_13mer", &AindexWrapper::tf_values_13mer_list)
         .def("get_tf_values_13mer", &AindexWrapper::get_tf_values_13mer)

@@ -680,6 +680,14 @@ int aix_index13_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *tf64, ai
     return AIX_OK;
 }
 
+int aix_index13_tf_direct(aix_ctx *ctx, const aix_index13 *ix, uint64_t *out) {
+    if (!ctx || !ix || !out) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_CUDA(ctx, cudaMemcpyAsync(out, ix->tf_direct_dev, AIX_TOTAL_13MERS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AIX_OK;
+}
+
 void aix_index13_destroy(aix_ctx *ctx, aix_index13 *ix) {
     if (!ix) return;
     if (ctx) cudaSetDevice(ctx->device);

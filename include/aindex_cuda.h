@@ -161,6 +161,9 @@ int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, 
 /* load_13mer_index (python_wrapper.cpp:404-437): tf64 = the 4^13 x u64 .tf.bin */
 int aix_index13_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *tf64, aix_index13 **out);
 void aix_index13_destroy(aix_ctx *ctx, aix_index13 *ix);
+/* out[v] = tf of the 13-mer with 2-bit value v (the tf file re-indexed by the MPHF), 4^13 x u64: the array the
+ * reference's frequency iterator (aindex/core/aindex.py:632-652, `_index_to_13mer(index)`) assumes it is given */
+int aix_index13_tf_direct(aix_ctx *ctx, const aix_index13 *ix, uint64_t *out);
 /* AIX_Q_TF    get_tf_value(s)_13mer :482-503, :938-980                 -> u32[q]
  * AIX_Q_TOTAL get_total_tf_value(s)_13mer :522-566                     -> u64[q]
  * AIX_Q_BOTH  get_tf_both_directions_13mer(_batch) :567-608            -> u64[2q] */

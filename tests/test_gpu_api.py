@@ -151,6 +151,17 @@ def test_aindex_class(golden_dir, g23):
     assert get_revcomp("ATCGN") == "NCGAT" and hamming_distance("ACGT", "ACNA") == 1
     kmers = list(ix.iter_sequence_kmers(seqs[0]))
     assert len(kmers) == len(seqs[0]) - 22 and kmers[0][1] == int(g23["cov_val"][0])
+    # frequency views (aindex.py:594-795): top k-mers by tf, summary statistics
+    tf_all = np.fromfile(prefix + ".tf.bin", dtype=np.uint32)
+    top = ix.get_top_kmers(25)
+    assert [t for _, t in top] == sorted(tf_all.tolist(), reverse=True)[:25]
+    assert all(ix[k] == t for k, t in top) and len({k for k, _ in top}) == 25
+    assert [t for _, t in ix.iter_kmers_by_frequency(min_tf=int(top[3][1]))] == [t for t in sorted(tf_all.tolist(), reverse=True) if t >= top[3][1]]
+    st = ix.get_kmer_frequency_stats()
+    nz = tf_all[tf_all > 0]
+    assert st["kmer_type"] == "23mer" and st["total_kmers"] == tf_all.size and st["non_zero_kmers"] == nz.size
+    assert st["max_tf"] == int(nz.max()) and st["min_tf"] == int(nz.min()) and st["total_tf"] == int(tf_all.sum())
+    assert abs(st["avg_tf"] - nz.mean()) < 1e-9
 
 
 @pytest.fixture(scope="module")
@@ -178,6 +189,17 @@ def test_wrapper_13mer_mode(cpp, pf13, tf13_file, g13, tmp_path):
     assert st["total_count"] == int(g13["plain_counts"].sum())
     assert w.get_tf_by_index_13mer(int(g13["plain_ids"][0])) == int(g13["plain_counts"][0])
     assert w.get_hash_size() == 1 << 26 and "Mode: 13-mer" in w.get_index_info()
+    # frequency iterator, 13-mer mode: the direct-address array names the right k-mers
+    direct = np.asarray(w.get_13mer_tf_array_direct())
+    assert direct.dtype == np.uint64 and direct.size == 1 << 26 and int(direct.sum()) == int(g13["plain_counts"].sum())
+    from aindex_b200.core.aindex import AIndex
+    a13 = AIndex()
+    a13._wrapper, a13._loaded, a13.k = w, True, 13
+    top = a13.get_top_kmers(40)
+    assert [t for _, t in top] == sorted(g13["plain_counts"].tolist(), reverse=True)[:40]
+    assert all(w.get_tf_value(k) == t for k, t in top) and len({k for k, _ in top}) == 40
+    st13 = a13.get_kmer_frequency_stats("13mer")
+    assert st13["non_zero_kmers"] == g13["plain_ids"].size and st13["total_tf"] == int(g13["plain_counts"].sum())
     # positions: build with the GPU (compute_aindex13 semantics), load back, query
     reads = tmp_path / "r13.reads"
     reads.write_bytes(g13["plain_data"].tobytes())
