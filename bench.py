@@ -213,6 +213,16 @@ def dist_setup(args):
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # ------------------------------------------------------------------------------------------
+def _tmp_root(min_free: int = 8 << 30):
+    """/dev/shm when it has room for the baseline's files (queries 2.3 GB + index 0.6 GB), else the default tmp dir"""
+    try:
+        if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free >= min_free:
+            return "/dev/shm"
+    except OSError:
+        pass
+    return None
+
+
 def ref_harness_path():
     p = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_harness")
     return p if os.path.exists(p) else None
@@ -554,7 +564,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        tmpdir = tempfile.mkdtemp(prefix="aix_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        tmpdir = tempfile.mkdtemp(prefix="aix_bench_", dir=_tmp_root())
         try:
             prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
             sample = args.cpu_sample or min(args.queries, 6_250_000 * threads)  # 16 threads: the whole 100 M batch (~4 s per pass)
@@ -630,7 +640,7 @@ def run_reference(args):
     del reads
     sample = args.cpu_sample or min(args.queries, 1_000_000 * threads)
     q = make_queries(torch, dev, args.queries, 3)[:sample].cpu().numpy()
-    tmpdir = tempfile.mkdtemp(prefix="aix_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    tmpdir = tempfile.mkdtemp(prefix="aix_ref_", dir=_tmp_root())
     try:
         prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
         del index, mphf, checker_t, tf_t

@@ -36,6 +36,7 @@ from aindex_b200 import capi  # noqa: E402
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+_tmp_root = bench._tmp_root
 
 
 def timed(ctx, stream, fn, reps=3, warmup=1):
@@ -166,7 +167,7 @@ def run_c4(ctx, stream, dev, args):
     ok_prop = bool(torch.equal(qout, out[si * per + oi]))
     # oracle on whole sequences (bounded): the reference loop aindex.py:314-322 restated in C
     from oracle import oracle as O
-    tmpdir = tempfile.mkdtemp(prefix="aix_c4_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    tmpdir = tempfile.mkdtemp(prefix="aix_c4_", dir=_tmp_root())
     cpu = None
     try:
         prefix = bench.write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
@@ -315,7 +316,7 @@ def run_c5(ctx, stream, dev, args):
     cbin = os.path.join(REF_BIN, "compute_aindex")
     if os.path.exists(cbin):
         n_sub = min(n_reads, 200_000)
-        tmpdir = tempfile.mkdtemp(prefix="aix_c5_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        tmpdir = tempfile.mkdtemp(prefix="aix_c5_", dir=_tmp_root())
         try:
             sub = reads[: n_sub * 151].cpu().numpy()
             # index of the subsample (tf must be counted on the same reads)

@@ -39,6 +39,11 @@ def env():
     torch.cuda.empty_cache()
 
 
+def _tmp_root():
+    import bench
+    return bench._tmp_root()
+
+
 def _revcomp_records(torch, q):
     comp = torch.zeros(256, device=q.device, dtype=torch.uint8)
     for a, b in zip(b"ACGT", b"TGCA"):
@@ -102,7 +107,7 @@ def test_c2_full_size_properties(env):
     qs = q[:3_000_000].cpu().numpy()
     assert np.array_equal(index.query(qs), o[:3_000_000].cpu().numpy().view(np.uint32))
     import tempfile, shutil
-    tmp = tempfile.mkdtemp(prefix="aix_t_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    tmp = tempfile.mkdtemp(prefix="aix_t_", dir=_tmp_root())
     try:
         prefix = env.bench.write_index_files(tmp, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
         mix = np.concatenate([qs[:1_000_000], q2[:1_000_000].cpu().numpy(), q2[-1_000_000:].cpu().numpy()])
@@ -158,7 +163,7 @@ def test_c3_full_size_shard_properties(env):
     pf = os.path.join(ROOT, "oracle", "_ref", "data", "all_13mers.pf")
     if os.path.exists(pf) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "count_kmers13")):
         import tempfile, shutil
-        tmp = tempfile.mkdtemp(prefix="aix_t_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        tmp = tempfile.mkdtemp(prefix="aix_t_", dir=_tmp_root())
         try:
             sample = reads[:300_000].cpu().numpy()
             kind, secs, nk, tf_ref, _ = env.bench.cpu_count_run(sample, os.cpu_count() or 1, tmp)
