@@ -67,7 +67,13 @@ __global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, Mphf
 // slot: the query bytes are already on chip when a warp starts a tile and there is no CTA-wide
 // barrier.
 constexpr int kStWarps = 8;
-constexpr int kStStages = 3;
+#ifndef AIX_ST_STAGES
+#define AIX_ST_STAGES 3
+#endif
+#ifndef AIX_ST_TILES
+#define AIX_ST_TILES 16
+#endif
+constexpr int kStStages = AIX_ST_STAGES;  // ring depth and tiles per warp are compile-time knobs (profiles/r01_tf23_sweep.txt)
 constexpr uint32_t kStTileBytes = 32u * 23u;  // 736 = 46 * 16: legal bulk-copy size, slots stay 16-byte aligned
 constexpr int kStSlot = 768;                  // the seventh word of lane 31 ends at byte 740
 
@@ -94,7 +100,7 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 // tiles w, w + 8, ...  Small enough that the hardware scheduler evens out SM speed differences (one wave of
 // resident CTAs per launch left a quarter of the warp slots idle at the tail), long enough that the two
 // exposed loads of the ring prologue are amortised.
-constexpr int kStTilesPerWarp = 16;
+constexpr int kStTilesPerWarp = AIX_ST_TILES;
 constexpr int kStTilesPerCta = kStWarps * kStTilesPerWarp;
 
 template <int kMode, bool kCanon, int kMinBlocks>
