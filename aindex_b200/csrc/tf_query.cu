@@ -218,6 +218,75 @@ __global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__re
     out[i] = res;
 }
 
+// ---- index split by hash-id range over several GPUs (north star: "split by hash range when it exceeds HBM") ------
+// The MPHF is small and replicated; the {checker, tf} records are cut into contiguous id ranges, one per GPU.
+// A rank turns its queries into probes {id, packed k-mer that must be stored at id}, the caller routes every probe
+// to the rank that owns the id (one all-to-all), the owner verifies it against its records and answers {hit, tf}.
+// get_tf_value_23mer needs at most two probes per query (forward, then reverse: python_wrapper.cpp:610-622); both
+// are produced eagerly and combined afterwards (first hit wins), which gives exactly the sequential answer.
+constexpr unsigned long long kNoProbe = ~0ull;
+
+template <bool kCanon>
+__global__ void __launch_bounds__(kQBlock) tf23_probes_kernel(MphfDev m, uint64_t n_total, const uint8_t *__restrict__ recs,
+                                                            uint32_t stride, const uint8_t *__restrict__ lens, uint64_t q,
+                                                            ulonglong2 *__restrict__ probes /* [2q] */) {
+    const uint64_t i = (uint64_t)blockIdx.x * kQBlock + threadIdx.x;
+    if (i >= q) return;
+    uint32_t len = lens ? lens[i] : stride;
+    if (len > stride) len = stride;
+    const uint8_t *p = recs + i * stride;
+    uint64_t w[3] = {0, 0, 0};
+    const uint32_t nb = len < 23u ? len : 23u;
+    for (uint32_t j = 0; j < nb; ++j) w[j >> 3] |= (uint64_t)__ldg(p + j) << (8 * (j & 7));
+    bool all_acgt;
+    const uint64_t u = encode_validate23(w[0], w[1], w[2], all_acgt), r = revcomp23(u);
+    uint64_t h1 = kNoProbe, k1 = 0, h2 = kNoProbe, k2 = 0, a, b, c, f0, f1, f2;
+    if (len == 23u && all_acgt) {
+        if (kCanon) {
+            const bool fwd = u <= r;
+            f0 = w[0]; f1 = w[1]; f2 = w[2];
+            if (!fwd) rc_ascii_words23(w[0], w[1], w[2], f0, f1, f2);
+            jenkins_short(m.seed, f0, f1, f2, 23u, a, b, c);
+            h1 = mphf_eval(m, a, b, c);
+            k1 = fwd ? u : r;
+        } else {
+            jenkins_short(m.seed, w[0], w[1], w[2], 23u, a, b, c);
+            h1 = mphf_eval(m, a, b, c);
+            k1 = u;
+            rc_ascii_words23(w[0], w[1], w[2], f0, f1, f2);
+            jenkins_short(m.seed, f0, f1, f2, 23u, a, b, c);
+            h2 = mphf_eval(m, a, b, c);
+            k2 = r;
+        }
+    } else {
+        const uint64_t us = encode23_strict(w[0], w[1], w[2]), rs = revcomp23(us);
+        if (len <= 23u) jenkins_short(m.seed, w[0], w[1], w[2], len, a, b, c);
+        else jenkins_bytes(m.seed, p, len, a, b, c);
+        h1 = mphf_eval(m, a, b, c);
+        k1 = us;
+        h2 = mphf_lookup23(m, us);  // hashes the ASCII string of rs
+        k2 = rs;
+    }
+    if (h1 >= n_total) h1 = kNoProbe;
+    if (h2 >= n_total) h2 = kNoProbe;
+    probes[2 * i] = make_ulonglong2(h1, k1);
+    probes[2 * i + 1] = make_ulonglong2(h2, k2);
+}
+
+// owner side: probes {local id, k-mer} -> (hit << 32) | tf
+__global__ void probe23_kernel(const uint4 *__restrict__ recs, uint64_t n_local, const ulonglong2 *__restrict__ probes,
+                               uint64_t cnt, unsigned long long *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const ulonglong2 pr = probes[i];
+    unsigned long long res = 0;
+    if (pr.x < n_local) {
+        const uint4 rec = ld_evict_first_u32x4(&recs[pr.x]);
+        if ((((uint64_t)rec.y << 32) | rec.x) == pr.y) res = (1ull << 32) | rec.z;
+    }
+    out[i] = res;
+}
+
 // ---- index upload helpers ----------------------------------------------------------------
 __global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const uint32_t *__restrict__ tf, uint64_t n,
                                     uint4 *__restrict__ recs, uint8_t *__restrict__ fp, int fp_bits,
@@ -646,6 +715,31 @@ int aix_tf23_batch(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uin
                               [&](cudaStream_t st, const uint8_t *r, const uint8_t *l, uint64_t nq, void *o) {
                                   return launch_tf23(ctx, ix, st, r, stride, l, nq, mode, o);
                               });
+}
+
+
+int aix_tf23_probes_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t n_total, int canonical_only, const uint8_t *recs_dev,
+                        uint32_t stride, const uint8_t *lens_dev, uint64_t q, uint64_t *probes_dev) {
+    if (!ctx || !m) return AIX_ERR_ARG;
+    if (q == 0) return AIX_OK;
+    if (!recs_dev || !probes_dev || !stride) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (canonical_only)
+        tf23_probes_kernel<true><<<aix_grid(q, kQBlock), kQBlock, 0, ctx->stream>>>(m->dev(), n_total, recs_dev, stride, lens_dev, q, (ulonglong2 *)probes_dev);
+    else
+        tf23_probes_kernel<false><<<aix_grid(q, kQBlock), kQBlock, 0, ctx->stream>>>(m->dev(), n_total, recs_dev, stride, lens_dev, q, (ulonglong2 *)probes_dev);
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+int aix_probe23_dev(aix_ctx *ctx, const aix_index23 *shard, const uint64_t *probes_dev, uint64_t cnt, uint64_t *out_dev) {
+    if (!ctx || !shard) return AIX_ERR_ARG;
+    if (cnt == 0) return AIX_OK;
+    if (!probes_dev || !out_dev) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    probe23_kernel<<<aix_grid(cnt, 256), 256, 0, ctx->stream>>>(shard->recs_dev, shard->n, (const ulonglong2 *)probes_dev, cnt, (unsigned long long *)out_dev);
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
 }
 
 int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q, uint32_t *out) {

@@ -163,6 +163,90 @@ class PeerHistogram:
         self.lib.aix_count13_peers_close(self.ctx.handle)
 
 
+class ShardedIndex23:
+    """A 23-mer index whose {checker, tf} records are split by hash-id range over the ranks (the MPHF, 0.4 B/key, is
+    replicated): for indexes that do not fit one GPU.  `query` is a collective: every rank passes its own batch.
+
+        probes (aix_tf23_probes_dev) -> all-to-all by owner of the id -> verify (aix_probe23_dev) -> all-to-all back
+        -> first hit of the (at most two) probes of a query.
+
+    The two device steps are methods so that the host logic (bucketing, the two all-to-alls, the inverse permutation,
+    the combine rule) can be exercised on CPU tensors with gloo (tests/test_dist_cpu.py)."""
+
+    def __init__(self, n_total: int, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_total = int(n_total)
+        self.bounds = [shard_range(self.n_total, r, self.world)[0] for r in range(self.world)] + [self.n_total]
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    # ---- device steps (GPU implementation; tests substitute CPU stand-ins) ------------------------------------
+    def attach(self, ctx, mphf, checker, tf, stream):
+        """Upload this rank's slice of the host arrays checker (u64[n]) / tf (u32[n])."""
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.ctx, self.mphf, self.stream, self.lib = ctx, mphf, stream, capi.lib()
+        self.shard = capi.Index23.upload(ctx, mphf, np.ascontiguousarray(checker[self.lo:self.hi]),
+                                         np.ascontiguousarray(tf[self.lo:self.hi]))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        flag = torch.tensor([1 if self.shard.info["canonical_only"] else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.canonical_only = int(flag.item())
+        return self
+
+    def _probes(self, recs):
+        """recs: uint8[q, 23] device tensor -> int64[2q, 2] {global id or -1, packed k-mer}"""
+        import torch
+        q = recs.shape[0]
+        out = torch.empty((2 * q, 2), dtype=torch.int64, device=recs.device)
+        self.ctx.check(self.lib.aix_tf23_probes_dev(self.ctx.handle, self.mphf._h, self.n_total, self.canonical_only,
+                                                    recs.data_ptr(), recs.shape[1], None, q, out.data_ptr()))
+        return out
+
+    def _verify(self, probes):
+        """probes: int64[c, 2] {local id, k-mer} -> int64[c] (hit << 32) | tf"""
+        import torch
+        out = torch.empty(probes.shape[0], dtype=torch.int64, device=probes.device)
+        self.ctx.check(self.lib.aix_probe23_dev(self.ctx.handle, self.shard._h, probes.data_ptr(), probes.shape[0], out.data_ptr()))
+        return out
+
+    # ---- host logic --------------------------------------------------------------------------------------------
+    def query(self, recs):
+        """tf of every 23-byte record of this rank's batch (uint8[q, 23] tensor) -> int64[q] tensor (values < 2^32)."""
+        import contextlib
+        import torch
+        import torch.distributed as dist
+        stream = getattr(self, "stream", None)
+        cm = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+        with cm:
+            q = recs.shape[0]
+            probes = self._probes(recs)
+            ids = probes[:, 0]
+            live = torch.nonzero(ids >= 0).reshape(-1)                     # -1 = no probe
+            inner = torch.tensor(self.bounds[1:-1], dtype=torch.int64, device=ids.device)
+            owner = torch.bucketize(ids[live], inner, right=True)           # rank that holds the id
+            order = torch.argsort(owner, stable=True)
+            live, owner = live[order], owner[order]
+            lo = torch.tensor(self.bounds[:-1], dtype=torch.int64, device=ids.device)
+            send = torch.stack([ids[live] - lo[owner], probes[live, 1]], dim=1).contiguous()
+            n_send = torch.bincount(owner, minlength=self.world)
+            n_recv = torch.empty_like(n_send)
+            dist.all_to_all_single(n_recv, n_send, group=self.group)
+            s_split, r_split = n_send.tolist(), n_recv.tolist()
+            recv = torch.empty((sum(r_split), 2), dtype=torch.int64, device=ids.device)
+            dist.all_to_all_single(recv, send, r_split, s_split, group=self.group)
+            answers = self._verify(recv)
+            back = torch.empty(send.shape[0], dtype=torch.int64, device=ids.device)
+            dist.all_to_all_single(back, answers, s_split, r_split, group=self.group)
+            res = torch.zeros(2 * q, dtype=torch.int64, device=ids.device)
+            res[live] = back
+            res = res.reshape(q, 2)
+            first_hit = (res[:, 0] >> 32) != 0
+            return torch.where(first_hit, res[:, 0], res[:, 1]) & 0xFFFFFFFF
+
+
 def sum_to_rank0(t, group=None):
     """Element-wise sum of a tensor onto rank 0 (the scattered MPHF-order partial results)."""
     import torch.distributed as dist

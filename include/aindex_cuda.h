@@ -153,6 +153,19 @@ int aix_tf23_batch(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uin
 int aix_tf23_batch_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs_dev,
                        uint32_t stride, const uint8_t *lens_dev, uint64_t q, int mode,
                        void *out_dev);
+/* Index split by hash-id range over several GPUs (one aix_index23 per rank holding records [lo, hi) of the
+ * checker / tf arrays, uploaded with aix_index23_upload[_dev] on the slice; the MPHF is replicated):
+ *   aix_tf23_probes_dev: query i -> probes_dev[4*i .. 4*i+3] = {id1, kmer1, id2, kmer2}; id = ~0 means "no probe".
+ *     These are the (at most two) checker comparisons of get_tf_value_23mer (python_wrapper.cpp:610-622) with GLOBAL ids;
+ *     canonical_only = 1 only if every rank's slice is canonical (then one probe per valid query).
+ *   [caller: route each probe to the owner of its id, subtract the owner's lo]
+ *   aix_probe23_dev: probes {local id, kmer} -> out = (hit << 32) | tf.
+ *   answer of query i = first hit of its two probes, else 0  (aindex_b200/dist.py::ShardedIndex23). */
+int aix_tf23_probes_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t n_total, int canonical_only,
+                        const uint8_t *recs_dev, uint32_t stride, const uint8_t *lens_dev, uint64_t q,
+                        uint64_t *probes_dev);
+int aix_probe23_dev(aix_ctx *ctx, const aix_index23 *shard, const uint64_t *probes_dev, uint64_t cnt,
+                    uint64_t *out_dev);
 /* PHASH_MAP::get_freq(uint64_t) (hash.hpp:123-140) for packed k-mers */
 int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q,
                    uint32_t *out);

@@ -76,6 +76,27 @@ def main():
     qb, qe = D.shard_range(len(q), rank, world)
     got = D.gather_concat(ix.query(q[qb:qe]))
     ok = ok and bool(np.array_equal(got, ix.query(q)))
+    # index split by hash-id range: every rank holds 1/world of the records and queries its OWN batch; the answers
+    # must equal those of the replicated index (hits on both strands, misses, non-ACGT and lower-case bytes)
+    kb = np.fromfile(os.path.join(g, "idx23.kmers.bin"), dtype=np.uint64)
+    tfb = np.fromfile(os.path.join(g, "idx23.tf.bin"), dtype=np.uint32)
+    sh = D.ShardedIndex23(kb.size).attach(ctx, ix.mphf, kb, tfb, stream)
+    rng2 = np.random.default_rng(900 + rank)
+    recs = rng2.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(20011, 23))
+    hit = rng2.random(recs.shape[0]) < 0.6
+    recs[hit] = ctx.decode(kb[rng2.integers(0, kb.size, size=int(hit.sum()))], 23)
+    flip = hit & (rng2.random(recs.shape[0]) < 0.5)
+    recs[flip] = ctx.decode(ctx.revcomp(ctx.encode(recs[flip], 23), 23), 23)
+    odd = rng2.random(recs.shape[0]) < 0.05
+    recs[odd, rng2.integers(0, 23, size=int(odd.sum()))] = rng2.choice(np.frombuffer(b"Nnacgt~", dtype=np.uint8), size=int(odd.sum()))
+    with torch.cuda.stream(stream):
+        recs_t = torch.from_numpy(recs).cuda()
+    got_sh = sh.query(recs_t)
+    stream.synchronize()
+    same = bool(np.array_equal(got_sh.cpu().numpy().astype(np.uint32), ix.query(recs)))
+    ok = ok and same
+    if rank == 0:
+        print(f"sharded index x{world}: equal={same} hits={int((got_sh > 0).sum())} canonical_only={sh.canonical_only} range=[{sh.lo},{sh.hi})")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -113,3 +113,75 @@ def test_count13_reduce_scatter_world2(fastq):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------- index split by hash-id range
+def _sharded_worker(rank, world, port, q):
+    """ShardedIndex23 host logic on gloo: the two device steps are replaced by oracle-based stand-ins."""
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        prefix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "idx23")
+        oix = O.Index23.load_prefix(prefix)
+        NONE = -1
+
+        class CpuSharded(D.ShardedIndex23):
+            def _probes(self, recs):
+                out = np.full((2 * recs.shape[0], 2), NONE, dtype=np.int64)
+                for i, row in enumerate(recs.numpy()):
+                    s = row.tobytes()
+                    us = O.dna23_bitset(s)
+                    rs = O.reverse_dna23(us)
+                    if not s.strip(b"ACGT"):                       # valid: canonical index -> one probe of min(u, r)
+                        c = min(us, rs)
+                        h = oix.mphf.lookup(O.bitset_dna23(c).encode())
+                        out[2 * i] = (h if h < oix.n else NONE, c)
+                    else:                                          # raw bytes forward, decoded reverse complement backward
+                        h1 = oix.mphf.lookup(s)
+                        h2 = oix.mphf.lookup(O.bitset_dna23(rs).encode())
+                        out[2 * i] = (h1 if h1 < oix.n else NONE, us)
+                        out[2 * i + 1] = (h2 if h2 < oix.n else NONE, rs)
+                return torch.from_numpy(out)
+
+            def _verify(self, probes):
+                p = probes.numpy()
+                res = np.zeros(p.shape[0], dtype=np.int64)
+                for j, (hl, km) in enumerate(p):
+                    if 0 <= hl < self.hi - self.lo and int(oix.checker[self.lo + hl]) == int(km) & ((1 << 64) - 1):
+                        res[j] = (1 << 32) | int(oix.tf[self.lo + hl])
+                return torch.from_numpy(res)
+
+        sh = CpuSharded(oix.n, None)
+        assert sh.bounds[0] == 0 and sh.bounds[-1] == oix.n and len(sh.bounds) == world + 1
+        rng = np.random.default_rng(100 + rank)                       # every rank has its own batch
+        recs = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(300, 23))
+        pick = rng.integers(0, oix.n, size=200)
+        for j, kid in enumerate(pick):
+            km = O.bitset_dna23(int(oix.checker[kid])).encode()
+            if j % 2:
+                km = km.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+            recs[j] = np.frombuffer(km, dtype=np.uint8)
+        recs[250:260, 5] = ord("N")
+        recs[260:270, 0] = ord("a")
+        got = sh.query(torch.from_numpy(recs)).numpy().astype(np.uint32)
+        want = oix.batch(recs, None, O.MODE_TF)
+        q.put((rank, bool(np.array_equal(got, want)), int((want > 0).sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_index_host_logic(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[:2] for r in res] == [(r, True) for r in range(world)]
+    assert all(r[2] >= 150 for r in res)  # the batches really contain hits on both strands

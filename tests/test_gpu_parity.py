@@ -201,6 +201,39 @@ def test_tf23_non_canonical_index_two_probe_path(capi, oracle, ctx, oidx23):
     q23 = [x for x in q if len(x) == 23]
     r23 = np.frombuffer(b"".join(q23), dtype=np.uint8).reshape(len(q23), 23).copy()
     assert np.array_equal(ix.query(r23, capi.Q_TF), oix.batch(r23, None, oracle.MODE_TF))
+    # the probe / verify split used by the hash-range-sharded index (dist.ShardedIndex23), here with one "rank"
+    assert np.array_equal(_probe_verify(capi, ctx, m, ix, recs, lens), oix.batch(recs, lens, oracle.MODE_TF))
+
+
+def _probe_verify(capi, ctx, mphf, ix, recs, lens):
+    """aix_tf23_probes_dev -> aix_probe23_dev -> first hit of the two probes (what ShardedIndex23.query does
+    around its all-to-alls), on one GPU that owns every id."""
+    import torch
+    lib = capi.lib()
+    q, stride = recs.shape
+    r_t = torch.from_numpy(np.ascontiguousarray(recs)).cuda()
+    l_t = torch.from_numpy(np.ascontiguousarray(lens)).cuda() if lens is not None else None
+    probes = torch.empty((2 * q, 2), dtype=torch.int64, device="cuda")
+    res = torch.empty(2 * q, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    info = ix.info
+    ctx.check(lib.aix_tf23_probes_dev(ctx.handle, mphf._h, info["n"], int(info["canonical_only"]), r_t.data_ptr(), stride,
+                                      l_t.data_ptr() if l_t is not None else None, q, probes.data_ptr()))
+    ctx.check(lib.aix_probe23_dev(ctx.handle, ix._h, probes.data_ptr(), 2 * q, res.data_ptr()))
+    ctx.sync()
+    r = res.cpu().numpy().reshape(q, 2)
+    first = (r[:, 0] >> 32) != 0
+    return (np.where(first, r[:, 0], r[:, 1]) & 0xFFFFFFFF).astype(np.uint32)
+
+
+def test_probe_verify_split_canonical_index(capi, oracle, ctx, idx23, oidx23):
+    rng = np.random.default_rng(77)
+    q = _mixed_queries(rng, oidx23, 5000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    assert np.array_equal(_probe_verify(capi, ctx, idx23.mphf, idx23, recs, lens), oidx23.batch(recs, lens, oracle.MODE_TF))
+    q23 = [x for x in q if len(x) == 23]
+    r23 = np.frombuffer(b"".join(q23), dtype=np.uint8).reshape(len(q23), 23).copy()
+    assert np.array_equal(_probe_verify(capi, ctx, idx23.mphf, idx23, r23, None), oidx23.batch(r23, None, oracle.MODE_TF))
 
 
 # ---------------------------------------------------------------------------- MPHF build
