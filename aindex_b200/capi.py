@@ -79,6 +79,7 @@ SIGNATURES = {
     "aix_tf23_batch_dev": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
     "aix_tf23_probes_dev": (_i, [_vp, _vp, _u64, _i, _vp, _u32, _vp, _u64, _vp]),
     "aix_probe23_dev": (_i, [_vp, _vp, _vp, _u64, _vp]),
+    "aix_probes_bucket_dev": (_i, [_vp, _vp, _u64, _vp, _i, _vp, _vp, _vp]),
     "aix_get_freq23": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "aix_index13_upload": (_i, [_vp, _vp, _vp, _pp]),
     "aix_index13_destroy": (None, [_vp, _vp]),

@@ -287,6 +287,78 @@ __global__ void probe23_kernel(const uint4 *__restrict__ recs, uint64_t n_local,
     out[i] = res;
 }
 
+// probes -> per-owner buckets (a counting sort with `world` <= 16 buckets): send[slot] = {id - lo[owner], k-mer},
+// tag[slot] = index of the probe, bucket o occupying [offs[o], offs[o] + counts[o]).  Order inside a bucket is arbitrary.
+constexpr int kMaxRanks = 16;
+struct OwnerBounds {
+    unsigned long long b[kMaxRanks + 1];
+    int world;
+};
+__device__ __forceinline__ int owner_of(const OwnerBounds &ob, unsigned long long id) {
+    int o = 0;
+#pragma unroll
+    for (int r = 1; r < kMaxRanks; ++r)
+        if (r < ob.world && id >= ob.b[r]) o = r;
+    return o;
+}
+
+__global__ void __launch_bounds__(256) probes_count_kernel(const ulonglong2 *__restrict__ probes, uint64_t n, OwnerBounds ob,
+                                                         unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int sc[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned long long id = probes[i].x;
+        if (id != kNoProbe) atomicAdd(&sc[owner_of(ob, id)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < ob.world && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
+}
+
+// offs[o] = exclusive prefix of counts; cursor[o] = 0
+__global__ void probes_offsets_kernel(const unsigned long long *__restrict__ counts, int world, unsigned long long *__restrict__ offs,
+                                      unsigned long long *__restrict__ cursor) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int o = 0; o < world; ++o) {
+            offs[o] = run;
+            cursor[o] = 0;
+            run += counts[o];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) probes_scatter_kernel(const ulonglong2 *__restrict__ probes, uint64_t n, OwnerBounds ob,
+                                                           const unsigned long long *__restrict__ offs,
+                                                           unsigned long long *__restrict__ cursor, ulonglong2 *__restrict__ send,
+                                                           uint32_t *__restrict__ tag) {
+    __shared__ unsigned int sc[kMaxRanks];
+    __shared__ unsigned long long sbase[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ulonglong2 pr = make_ulonglong2(kNoProbe, 0);
+    int o = -1;
+    unsigned int local = 0;
+    if (i < n) {
+        pr = probes[i];
+        if (pr.x != kNoProbe) {
+            o = owner_of(ob, pr.x);
+            local = atomicAdd(&sc[o], 1u);  // rank of this probe among the CTA's probes for owner o
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ob.world && sc[threadIdx.x])  // one reservation per owner and CTA
+        sbase[threadIdx.x] = offs[threadIdx.x] + atomicAdd(cursor + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
+    __syncthreads();
+    if (o >= 0) {
+        const unsigned long long slot = sbase[o] + local;
+        send[slot] = make_ulonglong2(pr.x - ob.b[o], pr.y);
+        tag[slot] = (uint32_t)i;
+    }
+}
+
 // ---- index upload helpers ----------------------------------------------------------------
 __global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const uint32_t *__restrict__ tf, uint64_t n,
                                     uint4 *__restrict__ recs, uint8_t *__restrict__ fp, int fp_bits,
@@ -728,6 +800,33 @@ int aix_tf23_probes_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t n_total, int c
         tf23_probes_kernel<true><<<aix_grid(q, kQBlock), kQBlock, 0, ctx->stream>>>(m->dev(), n_total, recs_dev, stride, lens_dev, q, (ulonglong2 *)probes_dev);
     else
         tf23_probes_kernel<false><<<aix_grid(q, kQBlock), kQBlock, 0, ctx->stream>>>(m->dev(), n_total, recs_dev, stride, lens_dev, q, (ulonglong2 *)probes_dev);
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+
+int aix_probes_bucket_dev(aix_ctx *ctx, const uint64_t *probes_dev, uint64_t n_probes, const uint64_t *bounds, int world,
+                          uint64_t *counts_dev, uint64_t *send_dev, uint32_t *tag_dev) {
+    if (!ctx || !bounds || world < 1 || world > kMaxRanks) return AIX_ERR_ARG;
+    if (n_probes >= (1ull << 32)) return ctx->fail(AIX_ERR_ARG, "at most 2^32-1 probes per call");
+    if (!counts_dev) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)world * 8, ctx->stream));
+    if (n_probes == 0) return AIX_OK;
+    if (!probes_dev || !send_dev || !tag_dev) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    OwnerBounds ob;
+    ob.world = world;
+    for (int r = 0; r <= world; ++r) ob.b[r] = bounds[r];  // HOST array of world + 1 ascending ids, bounds[0] = 0
+    for (int r = world + 1; r <= kMaxRanks; ++r) ob.b[r] = ~0ull;
+    void *scratch;
+    AIX_TRY(ctx->reserve(SCR_LEN1, 2 * kMaxRanks * 8, &scratch));
+    unsigned long long *offs = (unsigned long long *)scratch, *cursor = offs + kMaxRanks;
+    const unsigned grid = aix_grid(n_probes, 256);
+    probes_count_kernel<<<grid, 256, 0, ctx->stream>>>((const ulonglong2 *)probes_dev, n_probes, ob, (unsigned long long *)counts_dev);
+    AIX_LAUNCH_CHECK(ctx);
+    probes_offsets_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)counts_dev, world, offs, cursor);
+    AIX_LAUNCH_CHECK(ctx);
+    probes_scatter_kernel<<<grid, 256, 0, ctx->stream>>>((const ulonglong2 *)probes_dev, n_probes, ob, offs, cursor, (ulonglong2 *)send_dev, tag_dev);
     AIX_LAUNCH_CHECK(ctx);
     return AIX_OK;
 }

@@ -212,6 +212,32 @@ class ShardedIndex23:
         self.ctx.check(self.lib.aix_probe23_dev(self.ctx.handle, self.shard._h, probes.data_ptr(), probes.shape[0], out.data_ptr()))
         return out
 
+    def _bucket(self, probes):
+        """probes int64[2q, 2] -> (send int64[c, 2] {local id, k-mer} grouped by owner in rank order,
+        tag int64[c] probe index of every row, counts int64[world]).  GPU: one counting sort on the device
+        (aix_probes_bucket_dev); CPU tensors (gloo tests): the same thing with torch ops."""
+        import ctypes as C
+        import torch
+        n = probes.shape[0]
+        if probes.is_cuda:
+            counts = torch.empty(self.world, dtype=torch.int64, device=probes.device)
+            send = torch.empty((n, 2), dtype=torch.int64, device=probes.device)
+            tag = torch.empty(n, dtype=torch.int32, device=probes.device)
+            bounds = (C.c_uint64 * (self.world + 1))(*self.bounds)
+            self.ctx.check(self.lib.aix_probes_bucket_dev(self.ctx.handle, probes.data_ptr(), n, bounds, self.world,
+                                                          counts.data_ptr(), send.data_ptr(), tag.data_ptr()))
+            total = int(counts.sum().item())  # the split sizes are needed on the host anyway
+            return send[:total], tag[:total].long(), counts
+        ids = probes[:, 0]
+        live = torch.nonzero(ids >= 0).reshape(-1)                         # -1 = no probe
+        inner = torch.tensor(self.bounds[1:-1], dtype=torch.int64)
+        owner = torch.bucketize(ids[live], inner, right=True)              # rank that holds the id
+        order = torch.argsort(owner, stable=True)
+        live, owner = live[order], owner[order]
+        lo = torch.tensor(self.bounds[:-1], dtype=torch.int64)
+        send = torch.stack([ids[live] - lo[owner], probes[live, 1]], dim=1).contiguous()
+        return send, live, torch.bincount(owner, minlength=self.world)
+
     # ---- host logic --------------------------------------------------------------------------------------------
     def query(self, recs):
         """tf of every 23-byte record of this rank's batch (uint8[q, 23] tensor) -> int64[q] tensor (values < 2^32)."""
@@ -223,25 +249,17 @@ class ShardedIndex23:
         with cm:
             q = recs.shape[0]
             probes = self._probes(recs)
-            ids = probes[:, 0]
-            live = torch.nonzero(ids >= 0).reshape(-1)                     # -1 = no probe
-            inner = torch.tensor(self.bounds[1:-1], dtype=torch.int64, device=ids.device)
-            owner = torch.bucketize(ids[live], inner, right=True)           # rank that holds the id
-            order = torch.argsort(owner, stable=True)
-            live, owner = live[order], owner[order]
-            lo = torch.tensor(self.bounds[:-1], dtype=torch.int64, device=ids.device)
-            send = torch.stack([ids[live] - lo[owner], probes[live, 1]], dim=1).contiguous()
-            n_send = torch.bincount(owner, minlength=self.world)
+            send, tag, n_send = self._bucket(probes)
             n_recv = torch.empty_like(n_send)
             dist.all_to_all_single(n_recv, n_send, group=self.group)
             s_split, r_split = n_send.tolist(), n_recv.tolist()
-            recv = torch.empty((sum(r_split), 2), dtype=torch.int64, device=ids.device)
+            recv = torch.empty((sum(r_split), 2), dtype=torch.int64, device=probes.device)
             dist.all_to_all_single(recv, send, r_split, s_split, group=self.group)
             answers = self._verify(recv)
-            back = torch.empty(send.shape[0], dtype=torch.int64, device=ids.device)
+            back = torch.empty(send.shape[0], dtype=torch.int64, device=probes.device)
             dist.all_to_all_single(back, answers, s_split, r_split, group=self.group)
-            res = torch.zeros(2 * q, dtype=torch.int64, device=ids.device)
-            res[live] = back
+            res = torch.zeros(2 * q, dtype=torch.int64, device=probes.device)
+            res[tag] = back
             res = res.reshape(q, 2)
             first_hit = (res[:, 0] >> 32) != 0
             return torch.where(first_hit, res[:, 0], res[:, 1]) & 0xFFFFFFFF

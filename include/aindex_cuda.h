@@ -166,6 +166,12 @@ int aix_tf23_probes_dev(aix_ctx *ctx, const aix_mphf *m, uint64_t n_total, int c
                         uint64_t *probes_dev);
 int aix_probe23_dev(aix_ctx *ctx, const aix_index23 *shard, const uint64_t *probes_dev, uint64_t cnt,
                     uint64_t *out_dev);
+/* the routing step on the device: probes (as written by aix_tf23_probes_dev, n_probes = 2q) -> buckets by owner.
+ * bounds: HOST array of world + 1 ascending ids (rank r owns [bounds[r], bounds[r+1])).  counts_dev[world] (u64) =
+ * probes per owner; send_dev[n_probes] x {id - bounds[owner], kmer} grouped by owner in rank order (first
+ * sum(counts) entries used); tag_dev[slot] = index of the probe that sits in slot (to scatter the answers back). */
+int aix_probes_bucket_dev(aix_ctx *ctx, const uint64_t *probes_dev, uint64_t n_probes, const uint64_t *bounds,
+                          int world, uint64_t *counts_dev, uint64_t *send_dev, uint32_t *tag_dev);
 /* PHASH_MAP::get_freq(uint64_t) (hash.hpp:123-140) for packed k-mers */
 int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q,
                    uint32_t *out);

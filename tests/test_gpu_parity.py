@@ -226,6 +226,40 @@ def _probe_verify(capi, ctx, mphf, ix, recs, lens):
     return (np.where(first, r[:, 0], r[:, 1]) & 0xFFFFFFFF).astype(np.uint32)
 
 
+def test_probes_bucket_is_a_counting_sort(capi, ctx):
+    """aix_probes_bucket_dev: every live probe lands in its owner's bucket with its local id, k-mer and tag."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(83)
+    for world, n in ((1, 1000), (3, 70001), (8, 400003), (16, 5)):
+        n_total = 1_000_003
+        bounds = [(n_total * r) // world for r in range(world)] + [n_total]
+        probes = np.empty((n, 2), dtype=np.uint64)
+        probes[:, 0] = rng.integers(0, n_total, size=n, dtype=np.uint64)
+        probes[:, 1] = rng.integers(0, 1 << 46, size=n, dtype=np.uint64)
+        dead = rng.random(n) < 0.3
+        probes[dead, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        p_t = torch.from_numpy(probes.view(np.int64)).cuda()
+        counts = torch.empty(world, dtype=torch.int64, device="cuda")
+        send = torch.full((n, 2), -7, dtype=torch.int64, device="cuda")
+        tag = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.check(capi.lib().aix_probes_bucket_dev(ctx.handle, p_t.data_ptr(), n, (C.c_uint64 * (world + 1))(*bounds), world,
+                                                   counts.data_ptr(), send.data_ptr(), tag.data_ptr()))
+        ctx.sync()
+        cnt = counts.cpu().numpy()
+        live = np.flatnonzero(~dead)
+        owner = np.searchsorted(np.array(bounds[1:-1], dtype=np.uint64), probes[live, 0], side="right") if world > 1 else np.zeros(live.size, int)
+        assert np.array_equal(cnt, np.bincount(owner, minlength=world))
+        total = int(cnt.sum())
+        s_np, t_np = send.cpu().numpy().view(np.uint64)[:total], tag.cpu().numpy()[:total].astype(np.int64)
+        assert np.array_equal(np.sort(t_np), live)                       # every live probe exactly once
+        seg = np.repeat(np.arange(world), cnt)                           # bucket of every slot
+        assert np.array_equal(s_np[:, 0] + np.array(bounds, dtype=np.uint64)[seg], probes[t_np, 0])
+        assert np.array_equal(s_np[:, 1], probes[t_np, 1])
+        assert np.array_equal(seg, np.searchsorted(np.array(bounds[1:-1], dtype=np.uint64), probes[t_np, 0], side="right") if world > 1 else seg)
+
+
 def test_probe_verify_split_canonical_index(capi, oracle, ctx, idx23, oidx23):
     rng = np.random.default_rng(77)
     q = _mixed_queries(rng, oidx23, 5000)
