@@ -25,6 +25,7 @@
 #include <fcntl.h>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -167,6 +168,7 @@ struct Interval {  // python_wrapper.cpp:44-53 (end is stored as end+1, :271)
 
 class AindexWrapper {
     aix_ctx *ctx = nullptr;
+    mutable std::recursive_mutex mu;  // taken while the GIL is released around the batch entry points
     aix_mphf *mphf23 = nullptr;
     aix_index23 *ix23 = nullptr;
     aix_positions *pos23 = nullptr;
@@ -229,6 +231,16 @@ private:
         if (rc == AIX_ERR_ARG) throw std::invalid_argument(msg);
         throw std::runtime_error(msg);
     }
+    // a C-ABI call made with the GIL held: still exclusive with a batch call another thread runs with the GIL released
+    template <typename F>
+    void locked(F &&f) const {
+        int rc;
+        {
+            std::lock_guard<std::recursive_mutex> device_lock(mu);
+            rc = f();
+        }
+        check(rc);
+    }
     void require23() const {
         if (!ix23) throw std::runtime_error("23-mer index not loaded");
     }
@@ -239,6 +251,7 @@ private:
         std::vector<T> out(r.q * per);
         if (r.q) {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             check(aix_tf23_batch(ctx, ix23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, mode, out.data()));
         }
         return out;
@@ -248,6 +261,7 @@ private:
         std::vector<T> out(r.q * per);
         if (r.q) {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             check(aix_tf13_batch(ctx, ix13, r.bytes.data(), r.stride, r.lens_ptr(), r.q, mode, out.data()));
         }
         return out;
@@ -268,10 +282,11 @@ public:
         std::vector<uint32_t> out(r.q);
         if (r.q) {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             if (is_13mer_mode) check(aix_tf13_batch(ctx, ix13, r.bytes.data(), r.stride, r.lens_ptr(), r.q, AIX_Q_TF, out.data()));
             else {
                 if (!ix23) throw std::runtime_error("23-mer index not loaded");
-                check(aix_tf23_batch(ctx, ix23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, AIX_Q_TF, out.data()));
+                locked([&] { return aix_tf23_batch(ctx, ix23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, AIX_Q_TF, out.data()); });
             }
         }
         py::list res(r.q);
@@ -293,10 +308,10 @@ public:
         aix_positions_destroy(ctx, pos23); pos23 = nullptr;
         aix_index23_destroy(ctx, ix23); ix23 = nullptr;
         aix_mphf_destroy(ctx, mphf23); mphf23 = nullptr;
-        check(aix_mphf_load_pf(ctx, hash_filename.c_str(), &mphf23));
+        locked([&] { return aix_mphf_load_pf(ctx, hash_filename.c_str(), &mphf23); });
         checker.assign((const uint64_t *)kb.data(), (const uint64_t *)kb.data() + n);
         tf23.assign((const uint32_t *)tb.data(), (const uint32_t *)tb.data() + n);
-        check(aix_index23_upload(ctx, mphf23, checker.data(), tf23.data(), n, &ix23));
+        locked([&] { return aix_index23_upload(ctx, mphf23, checker.data(), tf23.data(), n, &ix23); });
         n_kmers = n;
         is_13mer_mode = false;
     }
@@ -349,7 +364,7 @@ public:
         pos.open(index_file);
         ind.open(indices_file);
         aix_positions_destroy(ctx, pos23); pos23 = nullptr;
-        check(aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos23));
+        locked([&] { return aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos23); });
         aindex_loaded = true;
     }
 
@@ -362,8 +377,8 @@ public:
         aix_positions_destroy(ctx, pos13); pos13 = nullptr;
         aix_index13_destroy(ctx, ix13); ix13 = nullptr;
         aix_mphf_destroy(ctx, mphf13); mphf13 = nullptr;
-        check(aix_mphf_load_pf(ctx, hash_file.c_str(), &mphf13));
-        check(aix_index13_upload(ctx, mphf13, (const uint64_t *)tf13_map.ptr, &ix13));
+        locked([&] { return aix_mphf_load_pf(ctx, hash_file.c_str(), &mphf13); });
+        locked([&] { return aix_index13_upload(ctx, mphf13, (const uint64_t *)tf13_map.ptr, &ix13); });
         is_13mer_mode = true;
         n_kmers = kTotal13;
     }
@@ -376,7 +391,7 @@ public:
         pos.open(index_file);
         ind.open(indices_file);
         aix_positions_destroy(ctx, pos13); pos13 = nullptr;
-        check(aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos13));
+        locked([&] { return aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos13); });
         aindex_loaded = true;
     }
 
@@ -437,10 +452,12 @@ public:
             uint32_t *o = out.mutable_data();
             if (is_13mer_mode) {
                 py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
                 check(aix_tf13_batch(ctx, ix13, in, stride, nullptr, q, AIX_Q_TF, o));
             } else {
                 require23();
                 py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
                 check(aix_tf23_batch(ctx, ix23, in, stride, nullptr, q, AIX_Q_TF, o));
             }
         }
@@ -497,9 +514,9 @@ public:
         ensure_ctx();
         uint64_t u = 0, r = 0;
         uint8_t out[23];
-        check(aix_encode_kmers(ctx, (const uint8_t *)kmer.data(), 23, nullptr, 1, 23, &u));
-        check(aix_revcomp_kmers(ctx, &u, 1, 23, &r));
-        check(aix_decode_kmers(ctx, &r, 1, 23, out));
+        locked([&] { return aix_encode_kmers(ctx, (const uint8_t *)kmer.data(), 23, nullptr, 1, 23, &u); });
+        locked([&] { return aix_revcomp_kmers(ctx, &u, 1, 23, &r); });
+        locked([&] { return aix_decode_kmers(ctx, &r, 1, 23, out); });
         return std::string((const char *)out, 23);
     }
 
@@ -508,7 +525,7 @@ public:
         require23();
         Records r = pack_records(kmers);
         std::vector<uint64_t> out(r.q);
-        if (r.q) check(aix_mphf_lookup(ctx, mphf23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, out.data()));
+        if (r.q) locked([&] { return aix_mphf_lookup(ctx, mphf23, r.bytes.data(), r.stride, r.lens_ptr(), r.q, out.data()); });
         return out;
     }
     uint64_t get_hash_value(std::string kmer) { return get_hash_values({kmer})[0]; }
@@ -517,7 +534,7 @@ public:
 
     std::string decode23(uint64_t u) const {
         uint8_t out[23];
-        check(aix_decode_kmers(ctx, &u, 1, 23, out));
+        locked([&] { return aix_decode_kmers(ctx, &u, 1, 23, out); });
         return std::string((const char *)out, 23);
     }
     std::string get_kmer_by_kid(uint64_t kid) {  // :718-724
@@ -529,7 +546,7 @@ public:
         require23();
         if (kid >= checker.size()) return std::make_tuple((uint64_t)0, std::string(""), std::string(""));
         uint64_t u = checker[kid], r = 0;
-        check(aix_revcomp_kmers(ctx, &u, 1, 23, &r));
+        locked([&] { return aix_revcomp_kmers(ctx, &u, 1, 23, &r); });
         return std::make_tuple((uint64_t)tf23[kid], decode23(u), decode23(r));
     }
 
@@ -592,11 +609,11 @@ public:
         const aix_positions *p = k == 23 ? pos23 : pos13;
         if (!p || (k == 23 && !ix23) || (k == 13 && !ix13)) return out;
         uint64_t cnt = 0, offs[2] = {0, 0};
-        check(aix_positions_query(ctx, ix23, ix13, p, (const uint8_t *)kmer.data(), (uint32_t)kmer.size(), nullptr, 1, k, &cnt, nullptr, nullptr));
+        locked([&] { return aix_positions_query(ctx, ix23, ix13, p, (const uint8_t *)kmer.data(), (uint32_t)kmer.size(), nullptr, 1, k, &cnt, nullptr, nullptr); });
         if (!cnt) return out;
         out.resize(cnt);
         offs[1] = cnt;
-        check(aix_positions_query(ctx, ix23, ix13, p, (const uint8_t *)kmer.data(), (uint32_t)kmer.size(), nullptr, 1, k, nullptr, offs, out.data()));
+        locked([&] { return aix_positions_query(ctx, ix23, ix13, p, (const uint8_t *)kmer.data(), (uint32_t)kmer.size(), nullptr, 1, k, nullptr, offs, out.data()); });
         return out;
     }
     std::vector<uint64_t> get_positions_23mer(const std::string &kmer) { return kmer.size() == 23 ? positions_of(kmer, 23) : std::vector<uint64_t>{}; }  // :800-822
@@ -618,10 +635,10 @@ public:
         uint64_t *o = offs.mutable_data();
         std::vector<uint64_t> counts(r.q);
         o[0] = 0;
-        if (r.q) check(aix_positions_query(ctx, ix23, ix13, p, r.bytes.data(), r.stride, r.lens_ptr(), r.q, k, counts.data(), nullptr, nullptr));
+        if (r.q) locked([&] { return aix_positions_query(ctx, ix23, ix13, p, r.bytes.data(), r.stride, r.lens_ptr(), r.q, k, counts.data(), nullptr, nullptr); });
         for (uint64_t i = 0; i < r.q; ++i) o[i + 1] = o[i] + counts[i];
         py::array_t<uint64_t> vals((py::ssize_t)o[r.q]);
-        if (o[r.q]) check(aix_positions_query(ctx, ix23, ix13, p, r.bytes.data(), r.stride, r.lens_ptr(), r.q, k, nullptr, o, vals.mutable_data()));
+        if (o[r.q]) locked([&] { return aix_positions_query(ctx, ix23, ix13, p, r.bytes.data(), r.stride, r.lens_ptr(), r.q, k, nullptr, o, vals.mutable_data()); });
         return py::make_tuple(offs, vals);
     }
 
@@ -649,6 +666,7 @@ public:
         if (n) {
             uint32_t *o = out.mutable_data();
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             check(aix_coverage(ctx, ix23, ix13, (const uint8_t *)seq.data(), offs, 1, k, cutoff, o));
         }
         return out;
@@ -669,6 +687,7 @@ public:
         if (total) {
             uint32_t *o = out.mutable_data();
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             check(aix_coverage(ctx, ix23, ix13, (const uint8_t *)sv.data(), op, n_seq, k, cutoff, o));
         }
         return out;
@@ -685,6 +704,7 @@ public:
         uint64_t *o = out.mutable_data();
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             check(aix_index13_tf_direct(ctx, ix13, o));
         }
         return out;
@@ -768,12 +788,13 @@ public:
         Mapped in;
         in.open(input_file);
         aix_mphf *m = nullptr;
-        check(aix_mphf_load_pf(ctx, pf_file.c_str(), &m));
+        locked([&] { return aix_mphf_load_pf(ctx, pf_file.c_str(), &m); });
         std::vector<uint64_t> tf(kTotal13);
         aix_count_stats st;
         int rc;
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             rc = aix_count13(ctx, m, (const uint8_t *)in.ptr, in.size, AIX_FMT_DETECT, tf.data(), &st);
         }
         aix_mphf_destroy(ctx, m);
@@ -800,11 +821,11 @@ public:
         uint64_t total = 0, n = 0;
         if (k == 23) {
             require23();
-            check(aix_positions_total23(ctx, ix23, &total));
+            locked([&] { return aix_positions_total23(ctx, ix23, &total); });
             n = checker.size();
         } else if (k == 13) {
             if (!ix13) throw std::runtime_error("13-mer index not loaded");
-            check(aix_positions_total13(ctx, ix13, &total));
+            locked([&] { return aix_positions_total13(ctx, ix13, &total); });
             n = kTotal13;
         } else {
             throw std::invalid_argument("k must be 13 or 23");
@@ -813,6 +834,7 @@ public:
         int rc;
         {
             py::gil_scoped_release nogil;
+            std::lock_guard<std::recursive_mutex> device_lock(mu);  // an aix_ctx serves one caller at a time (the reference relied on the GIL)
             rc = k == 23 ? aix_positions_build23(ctx, ix23, (const uint8_t *)rd.ptr, rd.size, indices.data(), positions.data())
                          : aix_positions_build13(ctx, ix13, (const uint8_t *)rd.ptr, rd.size, indices.data(), positions.data());
         }
@@ -836,12 +858,12 @@ public:
         Mapped rd;
         rd.open(reads_file);
         uint64_t n = 0;
-        check(aix_canonical23_count(ctx, (const uint8_t *)rd.ptr, rd.size, &n, nullptr, nullptr));
+        locked([&] { return aix_canonical23_count(ctx, (const uint8_t *)rd.ptr, rd.size, &n, nullptr, nullptr); });
         std::vector<uint64_t> kmers(n), chk(n);
         std::vector<uint32_t> counts(n), tfv(n);
-        check(aix_canonical23_count(ctx, (const uint8_t *)rd.ptr, rd.size, &n, kmers.data(), counts.data()));
+        locked([&] { return aix_canonical23_count(ctx, (const uint8_t *)rd.ptr, rd.size, &n, kmers.data(), counts.data()); });
         aix_mphf *m = nullptr;
-        check(aix_mphf_build(ctx, kmers.data(), n, 23, &m));
+        locked([&] { return aix_mphf_build(ctx, kmers.data(), n, 23, &m); });
         int rc = aix_index23_fill(ctx, m, kmers.data(), counts.data(), n, chk.data(), tfv.data());
         if (rc == AIX_OK) rc = aix_mphf_save_pf(ctx, m, (prefix + ".pf").c_str());
         aix_mphf_destroy(ctx, m);

@@ -261,6 +261,38 @@ def test_build_index_from_reads_roundtrip(cpp, golden_dir, tmp_path, oracle):
     assert w.get_tf_values(km).tolist() == ref.batch(km).tolist()
 
 
+def test_wrapper_is_safe_from_python_threads(cpp, golden_dir):
+    """The reference holds the GIL for every call, so one wrapper may be shared by threads.  This module releases the
+    GIL around batch calls and therefore guards its aix_ctx with a mutex: batch and single calls from several
+    threads on ONE wrapper neither race nor deadlock."""
+    import threading
+    p = os.path.join(golden_dir, "idx23")
+    w = cpp.AindexWrapper()
+    w.load(p + ".pf", p + ".tf.bin", p + ".kmers.bin", "")
+    tf = np.fromfile(p + ".tf.bin", dtype=np.uint32)
+    ids = list(range(0, tf.size, 3))
+    strs = [w.get_kmer_by_kid(i) for i in ids]
+    want = [int(tf[i]) for i in ids]
+    errs = []
+
+    def batch():
+        for _ in range(20):
+            if w.get_tf_values(strs) != want:
+                errs.append("batch")
+
+    def single():
+        for k, t in list(zip(strs, want))[:2000]:
+            if w.get_tf_value(k) != t:
+                errs.append("single")
+
+    ts = [threading.Thread(target=batch), threading.Thread(target=single), threading.Thread(target=batch)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs and not any(t.is_alive() for t in ts)
+
+
 def test_multi_gpu_count_and_queries():
     """2 ranks on 2 GPUs (skipped on a single-GPU box): NCCL reduce-scatter path == single GPU."""
     import sys
