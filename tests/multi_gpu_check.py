@@ -97,7 +97,7 @@ def main():
     ok = ok and same
     if os.environ.get("AIX_CHECK_TIMING"):
         import time
-        big = torch.from_numpy(rng2.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(5_000_000, 23))).cuda()
+        big = torch.from_numpy(rng2.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(int(os.environ.get("AIX_CHECK_TIMING_Q", "5000000")), 23))).cuda()
         sh.query(big)
         stream.synchronize()
         dist.barrier()
@@ -107,7 +107,7 @@ def main():
         stream.synchronize()
         dist.barrier()
         if rank == 0:
-            print(f"sharded index x{world}: {world * 3 * 5_000_000 / (time.perf_counter() - t0) / 1e9:.2f} G queries/s aggregate (5 M per rank and call)")
+            print(f"sharded index x{world}: {world * 3 * big.shape[0] / (time.perf_counter() - t0) / 1e9:.2f} G queries/s aggregate ({big.shape[0]} per rank and call)")
     if rank == 0:
         print(f"sharded index x{world}: equal={same} hits={int((got_sh > 0).sum())} canonical_only={sh.canonical_only} range=[{sh.lo},{sh.hi})")
     flag = torch.tensor([1 if ok else 0], device="cuda")
