@@ -46,6 +46,10 @@ int mphf_build_layout(aix_ctx *ctx, aix_mphf *m) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     uint64_t nw = m->n_words ? m->n_words : 1;
     uint64_t *words_dev = nullptr, *ranks_dev = nullptr;
+    struct Staging {  // freed on every exit path (AIX_CUDA returns early)
+        uint64_t *&a, *&b;
+        ~Staging() { if (a) cudaFree(a); if (b) cudaFree(b); }
+    } staging{words_dev, ranks_dev};
     const bool compact = m->bv_size < (1ull << 32) && m->hash_domain < (1ull << 31) && m->n < (1ull << 32) && !mphf_force_wide();
     if (compact) {
         const uint64_t n_recs = (2 * nw + 2) / 3 + 1;
@@ -61,8 +65,6 @@ int mphf_build_layout(aix_ctx *ctx, aix_mphf *m) {
             AIX_LAUNCH_CHECK(ctx);
         }
         AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (words_dev) cudaFree(words_dev);
-        if (ranks_dev) cudaFree(ranks_dev);
         return AIX_OK;
     }
     m->layout_bytes = nw * sizeof(ulonglong2);
@@ -77,8 +79,6 @@ int mphf_build_layout(aix_ctx *ctx, aix_mphf *m) {
         AIX_LAUNCH_CHECK(ctx);
     }
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (words_dev) cudaFree(words_dev);
-    if (ranks_dev) cudaFree(ranks_dev);
     return AIX_OK;
 }
 
@@ -121,6 +121,8 @@ int aix_mphf_upload(aix_ctx *ctx, uint64_t n, uint64_t hash_domain, uint64_t see
     if (!ctx || !out) return AIX_ERR_ARG;
     *out = nullptr;
     uint64_t bv = 3 * hash_domain;
+    // an empty structure (hash_domain == 0) has no node to evaluate: fastmod by 0 would index the records with the raw hash
+    if (hash_domain == 0) return ctx->fail(AIX_ERR_ARG, "empty mphf (hash_domain == 0)");
     if (n_words != (bv + 31) / 32 || n_blocks != (bv + 511) / 512)
         return ctx->fail(AIX_ERR_ARG, "mphf arrays do not match hash_domain (n_words=%llu n_blocks=%llu bv=%llu)",
                          (unsigned long long)n_words, (unsigned long long)n_blocks, (unsigned long long)bv);
@@ -153,7 +155,7 @@ int aix_mphf_load_pf(aix_ctx *ctx, const char *pf_path, aix_mphf **out) {
     m->n = hdr[0]; m->hash_domain = hdr[1]; m->seed = hdr[2]; m->bv_size = hdr[3];
     m->n_words = (m->bv_size + 31) / 32;
     m->n_blocks = (m->bv_size + 511) / 512;
-    if (m->bv_size != 3 * m->hash_domain || m->n_words > (1ull << 40)) {
+    if (m->hash_domain == 0 || m->bv_size != 3 * m->hash_domain || m->n_words > (1ull << 40)) {
         fclose(f);
         delete m;
         return ctx->fail(AIX_ERR_IO, "corrupt .pf header: %s", pf_path);

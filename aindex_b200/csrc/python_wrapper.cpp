@@ -305,6 +305,9 @@ public:
         std::vector<uint8_t> kb = slurp(kmers_bin_filename), tb = slurp(tf_file);
         uint64_t n = kb.size() / 8;  // hash.cpp:388-392
         if (tb.size() / 4 < n) throw std::runtime_error("tf file shorter than kmers file");
+        std::lock_guard<std::recursive_mutex> device_lock(mu);  // teardown + upload are one critical section: a batch call on another thread must not see freed objects
+        is_13mer_mode = false;
+        n_kmers = 0;
         aix_positions_destroy(ctx, pos23); pos23 = nullptr;
         aix_index23_destroy(ctx, ix23); ix23 = nullptr;
         aix_mphf_destroy(ctx, mphf23); mphf23 = nullptr;
@@ -363,6 +366,8 @@ public:
         Mapped pos, ind;
         pos.open(index_file);
         ind.open(indices_file);
+        std::lock_guard<std::recursive_mutex> device_lock(mu);  // teardown + upload are one critical section: a batch call on another thread must not see freed objects
+        aindex_loaded = false;
         aix_positions_destroy(ctx, pos23); pos23 = nullptr;
         locked([&] { return aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos23); });
         aindex_loaded = true;
@@ -374,6 +379,9 @@ public:
         ensure_ctx();
         tf13_map.open(tf_file);
         if (tf13_map.size < kTotal13 * 8) throw std::runtime_error("13-mer tf file must hold 4^13 uint64 values: " + tf_file);
+        std::lock_guard<std::recursive_mutex> device_lock(mu);  // teardown + upload are one critical section: a batch call on another thread must not see freed objects
+        is_13mer_mode = false;  // stays false if the reload fails: run13 must never see a null ix13 in 13-mer mode
+        n_kmers = 0;
         aix_positions_destroy(ctx, pos13); pos13 = nullptr;
         aix_index13_destroy(ctx, ix13); ix13 = nullptr;
         aix_mphf_destroy(ctx, mphf13); mphf13 = nullptr;
@@ -390,6 +398,7 @@ public:
         Mapped pos, ind;
         pos.open(index_file);
         ind.open(indices_file);
+        std::lock_guard<std::recursive_mutex> device_lock(mu);  // teardown + upload are one critical section: a batch call on another thread must not see freed objects
         aix_positions_destroy(ctx, pos13); pos13 = nullptr;
         locked([&] { return aix_positions_upload(ctx, (const uint64_t *)ind.ptr, ind.size / 8, (const uint64_t *)pos.ptr, pos.size / 8, &pos13); });
         aindex_loaded = true;
@@ -864,9 +873,13 @@ public:
         locked([&] { return aix_canonical23_count(ctx, (const uint8_t *)rd.ptr, rd.size, &n, kmers.data(), counts.data()); });
         aix_mphf *m = nullptr;
         locked([&] { return aix_mphf_build(ctx, kmers.data(), n, 23, &m); });
-        int rc = aix_index23_fill(ctx, m, kmers.data(), counts.data(), n, chk.data(), tfv.data());
-        if (rc == AIX_OK) rc = aix_mphf_save_pf(ctx, m, (prefix + ".pf").c_str());
-        aix_mphf_destroy(ctx, m);
+        int rc;
+        {
+            std::lock_guard<std::recursive_mutex> device_lock(mu);
+            rc = aix_index23_fill(ctx, m, kmers.data(), counts.data(), n, chk.data(), tfv.data());
+            if (rc == AIX_OK) rc = aix_mphf_save_pf(ctx, m, (prefix + ".pf").c_str());
+            aix_mphf_destroy(ctx, m);
+        }
         check(rc);
         auto dump = [](const std::string &path, const void *p, size_t bytes) {
             FILE *f = fopen(path.c_str(), "wb");

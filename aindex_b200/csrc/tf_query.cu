@@ -776,6 +776,7 @@ int aix_tf23_batch_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs_
                        const uint8_t *lens_dev, uint64_t q, int mode, void *out_dev) {
     if (!ctx || !ix) return AIX_ERR_ARG;
     if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     return launch_tf23(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
 }
 
@@ -899,6 +900,7 @@ int aix_tf13_batch_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *recs_
                        const uint8_t *lens_dev, uint64_t q, int mode, void *out_dev) {
     if (!ctx || !ix) return AIX_ERR_ARG;
     if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     return launch_tf13(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
 }
 

@@ -47,14 +47,16 @@ def shard_reads(data: np.ndarray, world: int, lines_per_record: int = 1) -> List
         if lines_per_record == 1:
             for r in range(1, world):
                 target = max(cuts[-1], (n * r) // world)
-                # next newline at or after target-1 ends a line; cut after it
-                nl = np.flatnonzero(data[max(target - 1, 0):min(n, target + (1 << 20))] == 10)
-                while nl.size == 0 and target < n:  # very long line: widen the search
-                    target2 = min(n, target + (1 << 20))
-                    nl = np.flatnonzero(data[max(target - 1, 0):min(n, target2 + (1 << 24))] == 10)
-                    if target2 >= n:
+                # next newline at or after target-1 ends a line; cut after it.  Searched in slices whose
+                # upper bound advances every pass (chromosome-length lines), cut = n when there is none.
+                lo, cut, span = max(target - 1, 0), n, 1 << 20
+                while lo < n:
+                    hi = min(n, lo + span)
+                    nl = np.flatnonzero(data[lo:hi] == 10)
+                    if nl.size:
+                        cut = lo + int(nl[0]) + 1
                         break
-                cut = max(target - 1, 0) + int(nl[0]) + 1 if nl.size else n
+                    lo, span = hi, min(span * 4, 1 << 28)
                 cuts.append(min(max(cut, cuts[-1]), n))
         else:
             nl_pos = np.flatnonzero(data == 10)

@@ -14,6 +14,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+_HAS_GPU = None
+
+
+def _has_gpu() -> bool:
+    """True when the driver sees at least one CUDA device (no torch import, no context creation)."""
+    global _HAS_GPU
+    if _HAS_GPU is None:
+        import ctypes
+        try:
+            cu = ctypes.CDLL("libcuda.so.1")
+            n = ctypes.c_int(0)
+            _HAS_GPU = cu.cuInit(0) == 0 and cu.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+        except OSError:
+            _HAS_GPU = False
+    return _HAS_GPU
+
+
+def pytest_runtest_setup(item):
+    # `-m gpu` on a box without a device: skip (the product itself still fails loudly, tests/test_abi.py)
+    if item.get_closest_marker("gpu") is not None and not _has_gpu():
+        pytest.skip("no CUDA device visible")
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

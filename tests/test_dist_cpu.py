@@ -48,6 +48,19 @@ def test_shard_reads_plain_and_fastq(world):
         D.kmer_range(0, 3)
 
 
+@pytest.mark.timeout(60)
+def test_shard_reads_very_long_lines():
+    """chromosome-length lines (plain reads built from genomes): the newline search must advance, not spin"""
+    data = np.full(40 << 20, ord("A"), dtype=np.uint8)
+    assert D.shard_reads(data, 2) == [(0, data.size), (data.size, data.size)]      # no newline at all
+    data[-1] = 10
+    assert D.shard_reads(data, 2) == [(0, data.size), (data.size, data.size)]      # one 40 MiB line
+    data[30 << 20] = 10                                                           # newline 10 MiB past the split target
+    assert D.shard_reads(data, 2) == [(0, (30 << 20) + 1), ((30 << 20) + 1, data.size)]
+    s4 = D.shard_reads(data, 4)
+    assert s4[0] == (0, (30 << 20) + 1) and s4[1][0] == s4[1][1] and s4[-1][1] == data.size
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_shard_fasta_keeps_records_whole(world):
     """every shard starts at a header; the per-shard oracle counts add up to the whole file's"""
