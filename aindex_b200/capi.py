@@ -118,6 +118,8 @@ SIGNATURES = {
     "aix_canonical23_count": (_i, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "aix_canonical23_count_dev": (_i, [_vp, _vp, _u64, _vp]),
     "aix_canonical23_result_dev": (_i, [_vp, _pp, _pp, _vp]),
+    "aix_sort_u64_dev": (_i, [_vp, _vp, _vp, _u64, _i, _i, C.POINTER(_i)]),
+    "aix_rle_u64_dev": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
 }
 
 

@@ -13,11 +13,10 @@
 // retract it from its three vertices), records the rounds, and assigns the 2-bit values
 // round by round in reverse.  Both loops run inside one cooperative kernel each.
 #include <cooperative_groups.h>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_run_length_encode.cuh>
 #include <random>
 
 #include "aix_internal.cuh"
+#include "radix_sort.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -497,51 +496,25 @@ int aix_index23_fill(aix_ctx *ctx, const aix_mphf *m, const uint64_t *kmers, con
 }
 
 // sort + run-length of `n_keys` k-mers held in keys (keys_alt = spare of the same size, cnts = u32[n_keys]);
-// the unique k-mers end up in *uniq_out (one of the two key buffers) with their counts in cnts
+// the unique k-mers end up in *uniq_out (one of the two key buffers) with their counts in cnts.
+// Hand-written LSD radix sort + run-length kernels (radix_sort.cu): the `sort | uniq -c` of the reference's
+// counting stage (scripts/compute_aindex.py:140-182).
 static int c23_sort_rle(aix_ctx *ctx, uint64_t *keys, uint64_t *keys_alt, uint32_t *cnts, uint64_t n_keys, int end_bit,
                         uint64_t **uniq_out, uint64_t *n_uniq) {
-    cudaStream_t st = ctx->stream;
     *n_uniq = 0;
     *uniq_out = keys_alt;
     if (n_keys == 0) return AIX_OK;
-    void *tmp = nullptr;
-    int *n_runs = nullptr;
-    auto cleanup = [&]() { cudaFree(tmp); cudaFree(n_runs); };
-    cub::DoubleBuffer<uint64_t> db(keys, keys_alt);
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int)n_keys, 0, end_bit, st);
-    cudaError_t e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-    if (e == cudaSuccess) e = cudaMalloc(&n_runs, sizeof(int));
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)n_keys, 0, end_bit, st);
-    ctx->launches += 8;
-    if (e != cudaSuccess) {
-        cudaGetLastError(); cleanup();
-        return ctx->fail(AIX_ERR_CUDA, "canonical23 sort: %s", cudaGetErrorString(e));
-    }
-    uint64_t *sorted = db.Current();
-    uint64_t *spare = db.Alternate();  // reused for the unique keys
-    cudaFree(tmp); tmp = nullptr;
-    size_t tmp2 = 0;
-    cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, sorted, spare, cnts, n_runs, (int)n_keys, st);
-    e = cudaMalloc(&tmp, tmp2 ? tmp2 : 1);
-    if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(tmp, tmp2, sorted, spare, cnts, n_runs, (int)n_keys, st);
-    ctx->launches += 3;
-    int h_runs = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_runs, n_runs, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return ctx->fail(AIX_ERR_CUDA, "canonical23 run-length: %s", cudaGetErrorString(e));
-    }
+    uint64_t *sorted = keys;
+    AIX_TRY(aix::radix_sort_u64(ctx, ctx->stream, keys, keys_alt, n_keys, 0, end_bit, &sorted));
+    uint64_t *spare = sorted == keys ? keys_alt : keys;  // reused for the unique keys
+    AIX_TRY(aix::rle_u64(ctx, ctx->stream, sorted, n_keys, spare, cnts, n_uniq));
     *uniq_out = spare;
-    *n_uniq = (uint64_t)h_runs;
     return AIX_OK;
 }
 
-// per-pass key capacity: CUB takes int counts, and keys + spare + counts + sort scratch must fit
+// per-pass key capacity: keys + spare + counts + sort scratch must fit the free HBM
 static uint64_t c23_pass_capacity(uint64_t reserve_bytes) {
-    uint64_t cap = (1ull << 31) - 4096;
+    uint64_t cap = 1ull << 36;
     if (const char *e = getenv("AIX_CANONICAL23_PASS_KEYS")) {  // test hook: force the multi-pass path
         uint64_t v = strtoull(e, nullptr, 10);
         if (v >= 1024) return v < cap ? v : cap;
@@ -549,7 +522,7 @@ static uint64_t c23_pass_capacity(uint64_t reserve_bytes) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         uint64_t usable = free_b > reserve_bytes ? free_b - reserve_bytes : 0;
-        uint64_t by_mem = usable / 26;  // 8 + 8 + 4 bytes per key + onesweep scratch + slack
+        uint64_t by_mem = usable / 30;  // 8 + 8 + 4 bytes per key + sort status words + run-length scratch + slack
         if (by_mem < cap) cap = by_mem;
     }
     return cap;
@@ -569,7 +542,7 @@ static int c23_single_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len,
     canonical23_kernel<<<aix_grid((n_win + kCanRoll - 1) / kCanRoll, 128), 128, 0, ctx->stream>>>(reads_dev, len, keys);
     ctx->launches++;
     uint64_t *uniq = nullptr, n = 0;
-    int rc = c23_sort_rle(ctx, keys, keys_alt, cnts, n_win, 64, &uniq, &n);
+    int rc = c23_sort_rle(ctx, keys, keys_alt, cnts, n_win, 47, &uniq, &n)  /* 46 k-mer bits + the bit that sets the all-ones sentinel apart */;
     if (rc != AIX_OK) { cleanup(); return rc; }
     uint64_t last_key = 0;
     if (n) e = cudaMemcpy(&last_key, uniq + (n - 1), 8, cudaMemcpyDeviceToHost);

@@ -9,23 +9,24 @@
 // Reference query: get_positions_23mer python_wrapper.cpp:800-822, get_positions_13mer
 // :1070-1101.
 //
-// GPU build = device prefix sum -> count pass (occurrences per bucket) -> scatter with one
-// atomic cursor per bucket -> per-bucket ascending sort (atomic order is not deterministic)
-// -> clip to tf.  When no bucket has more occurrences than tf (the normal case: tf was
-// counted on the same reads) the scatter goes straight into the final layout.
-#include <cub/device/device_radix_sort.cuh>
-
+// GPU build = device prefix sum of tf -> ONE streaming lookup pass that emits a packed key
+// (bucket << pos_bits | position) per occurrence, compacted in position order (decoupled
+// look-back) -> hand-written stable LSD radix sort on the bucket bits (radix_sort.cu).  CSR
+// order is bucket order and the stable sort keeps positions ascending inside a bucket, so when
+// every bucket holds exactly tf occurrences (the normal case: tf was counted on the same
+// reads) the sorted low words ARE positions[]: no cursor atomics, no indices[h] gather, no
+// scattered 8-byte stores, no per-bucket sort.  Otherwise the sorted keys are clipped into the
+// tf-sized layout (first tf kept, zero tail).
 #include "aix_internal.cuh"
 #include "query23.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
 
 namespace aix {
 
 constexpr uint64_t kNoBucket = ~0ULL;
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 8;  // per thread
-constexpr int kScanTile = kScanBlock * kScanItems;
 
-// ---- exclusive prefix sum of per-bucket sizes (u64 out, n+1 entries) -------------------
+// per-bucket sizes for the prefix sum (tf of the index = the size of every bucket, hash.hpp:373-378)
 struct TfFromRecs {
     const uint4 *recs;
     __device__ uint64_t operator()(uint64_t i) const { return recs[i].z; }
@@ -34,103 +35,6 @@ struct TfFromU64 {
     const uint64_t *v;
     __device__ uint64_t operator()(uint64_t i) const { return v[i]; }
 };
-struct TfFromU32 {
-    const uint32_t *v;
-    __device__ uint64_t operator()(uint64_t i) const { return v[i]; }
-};
-
-__device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long v, unsigned long long *sm /*>=33*/,
-                                                             unsigned long long &total) {
-    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    unsigned long long x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= (unsigned)o) x += y;
-    }
-    if (lane == 31) sm[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned long long t = lane < nw ? sm[lane] : 0ull;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o);
-            if (lane >= (unsigned)o) t += y;
-        }
-        sm[lane] = t;
-    }
-    __syncthreads();
-    total = sm[nw - 1];
-    unsigned long long off = wid ? sm[wid - 1] : 0ull;
-    __syncthreads();
-    return off + x - v;
-}
-
-template <typename F>
-__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(F f, uint64_t n, unsigned long long *__restrict__ tile_sum) {
-    __shared__ unsigned long long sm[33];
-    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    unsigned long long s = 0;
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j)
-        if (base + j < n) s += f(base + j);
-    unsigned long long total;
-    block_scan_u64(s, sm, total);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
-}
-
-__global__ void scan_tiles_kernel(unsigned long long *__restrict__ tile_sum, uint64_t n_tiles) {
-    __shared__ unsigned long long sm[33];
-    __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint64_t i0 = 0; i0 < n_tiles; i0 += blockDim.x) {
-        uint64_t i = i0 + threadIdx.x;
-        unsigned long long v = i < n_tiles ? tile_sum[i] : 0ull, total;
-        unsigned long long ex = block_scan_u64(v, sm, total);
-        if (i < n_tiles) tile_sum[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-}
-
-template <typename F>
-__global__ void __launch_bounds__(kScanBlock) scan_down_kernel(F f, uint64_t n, const unsigned long long *__restrict__ tile_off,
-                                                             unsigned long long *__restrict__ out /* n+1 */) {
-    __shared__ unsigned long long sm[33];
-    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-    unsigned long long v[kScanItems], s = 0;
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        v[j] = base + j < n ? f(base + j) : 0ull;
-        s += v[j];
-    }
-    unsigned long long total;
-    unsigned long long run = tile_off[blockIdx.x] + block_scan_u64(s, sm, total);
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-        if (base + j < n) out[base + j] = run;
-        run += v[j];
-        if (base + j + 1 == n) out[n] = run;
-    }
-}
-
-template <typename F>
-static int exclusive_scan(aix_ctx *ctx, cudaStream_t st, F f, uint64_t n, unsigned long long *out, void *tile_scratch) {
-    uint64_t tiles = (n + kScanTile - 1) / kScanTile;
-    if (n == 0) {
-        AIX_CUDA(ctx, cudaMemsetAsync(out, 0, 8, st));
-        return AIX_OK;
-    }
-    scan_reduce_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(f, n, (unsigned long long *)tile_scratch);
-    AIX_LAUNCH_CHECK(ctx);
-    scan_tiles_kernel<<<1, 1024, 0, st>>>((unsigned long long *)tile_scratch, tiles);
-    AIX_LAUNCH_CHECK(ctx);
-    scan_down_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(f, n, (const unsigned long long *)tile_scratch, out);
-    AIX_LAUNCH_CHECK(ctx);
-    return AIX_OK;
-}
 
 // ---- bucket of the window starting at byte i (or kNoBucket) ---------------------------
 // k = 23: hash.cpp:1006-1051.  Skip windows containing '\n', '~', 'N'; canonical form by
@@ -176,101 +80,115 @@ __device__ __forceinline__ uint64_t bucket13(const MphfDev &m, const uint8_t *p)
     return h < AIX_TOTAL_13MERS ? h : kNoBucket;
 }
 
-// phase 1: tmp[off[h] + cursor[h]++] = i + 1 (every occurrence, general path)
-// phase 2: the optimistic single pass -- positions[indices[h] + cursor[h]++] = i + 1 while the slot is
-//          below tf[h]; cursor[h] ends as the true occurrence count, so a bucket with more occurrences
-//          than tf is detected afterwards (classify) and only then the general path runs
-template <int K, int kPhase, typename F>
-__global__ void __launch_bounds__(256) positions_scan_kernel(Index23Dev ix, MphfDev m, F tf, const uint8_t *__restrict__ reads,
-                                                           uint64_t start, uint64_t n_win_end /* len-k+1 */,
-                                                           uint32_t *__restrict__ cursor,
-                                                           const unsigned long long *__restrict__ off,
-                                                           unsigned long long *__restrict__ dst) {
-    uint64_t i = start + (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_win_end) return;
-    uint64_t h = K == 23 ? bucket23(ix, m, reads + i) : bucket13(m, reads + i);
-    if (h == kNoBucket) return;
-    uint32_t slot = atomicAdd(cursor + h, 1u);
-    if (kPhase == 1 || (uint64_t)slot < tf(h)) dst[off[h] + slot] = i + 1;
-}
+// ---- emit pass: one key per occurrence, in position order ------------------------------------
+constexpr int kEmitThreads = 256;
+constexpr int kEmitItems = 8;
+constexpr int kEmitTile = kEmitThreads * kEmitItems;  // windows per CTA
 
-// any bucket with more occurrences than tf?  also classifies buckets by size for the sort
-template <typename F>
-__global__ void classify_kernel(F tf, const uint32_t *__restrict__ occ, uint64_t n, int *__restrict__ over,
-                                uint32_t *__restrict__ medium_list, uint32_t *__restrict__ large_list,
-                                unsigned int *__restrict__ counts /* [0] medium, [1] large */, uint32_t small_max,
-                                uint32_t medium_max) {
-    uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n) return;
-    uint32_t c = occ[h];
-    if ((uint64_t)c > tf(h)) *over = 1;
-    if (c > medium_max) large_list[atomicAdd(counts + 1, 1u)] = (uint32_t)h;
-    else if (c > small_max) medium_list[atomicAdd(counts + 0, 1u)] = (uint32_t)h;
-}
-
-// small buckets: one thread each, insertion sort (atomic arrival order is nearly sorted)
-__global__ void sort_small_kernel(unsigned long long *__restrict__ data, const unsigned long long *__restrict__ off,
-                                  const uint32_t *__restrict__ occ, uint64_t n, uint32_t small_max) {
-    uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n) return;
-    uint32_t c = occ[h];
-    if (c < 2 || c > small_max) return;
-    unsigned long long *a = data + off[h];
-    for (uint32_t i = 1; i < c; ++i) {
-        unsigned long long x = a[i];
-        uint32_t j = i;
-        while (j > 0 && a[j - 1] > x) {
-            a[j] = a[j - 1];
-            --j;
-        }
-        a[j] = x;
-    }
-}
-
-// medium buckets: one CTA each, bitonic sort in shared memory
-constexpr uint32_t kSmallMax = 48;
-constexpr uint32_t kMediumMax = 4096;
-__global__ void __launch_bounds__(512) sort_medium_kernel(unsigned long long *__restrict__ data,
-                                                        const unsigned long long *__restrict__ off,
-                                                        const uint32_t *__restrict__ occ,
-                                                        const uint32_t *__restrict__ medium_list) {
-    __shared__ unsigned long long s[kMediumMax];
-    const uint32_t h = medium_list[blockIdx.x];
-    const uint32_t c = occ[h];
-    unsigned long long *a = data + off[h];
-    uint32_t p2 = 1;
-    while (p2 < c) p2 <<= 1;
-    for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) s[i] = i < c ? a[i] : ~0ull;
+// keys[r] = (bucket << pos_bits) | (i + 1) for the r-th window (in order of i) that has a bucket.  The tile's
+// keys are staged in shared memory, counted with ballots in window order, and the tile's first output slot comes
+// from a decoupled look-back over the earlier tiles (scan.cuh).  Keys beyond `cap` are counted but not stored;
+// the last tile stores the grand total in *n_valid.
+template <int K>
+__global__ void __launch_bounds__(kEmitThreads) positions_emit_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ reads,
+                                                                    uint64_t start, uint64_t n_win_end, int pos_bits,
+                                                                    uint64_t *__restrict__ keys, uint64_t cap,
+                                                                    unsigned long long *__restrict__ status,
+                                                                    unsigned int *__restrict__ tile_counter,
+                                                                    unsigned long long *__restrict__ n_valid) {
+    __shared__ uint64_t s_key[kEmitTile];
+    __shared__ uint32_t s_cnt[kEmitItems * (kEmitThreads / 32)];
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_excl;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
-    for (uint32_t k = 2; k <= p2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
-                uint32_t l = i ^ j;
-                if (l > i) {
-                    unsigned long long x = s[i], y = s[l];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) { s[i] = y; s[l] = x; }
-                }
-            }
-            __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t base = start + tile * kEmitTile;
+#pragma unroll 1
+    for (int j = 0; j < kEmitItems; ++j) {
+        const uint64_t i = base + (uint64_t)j * kEmitThreads + tid;
+        uint64_t h = kNoBucket;
+        if (i < n_win_end) h = K == 23 ? bucket23(ix, m, reads + i) : bucket13(m, reads + i);
+        s_key[j * kEmitThreads + tid] = h == kNoBucket ? ~0ULL : ((h << pos_bits) | (i + 1));
+    }
+    // every thread reads back its own keys only: no barrier needed before the ballots
+    uint32_t rank[kEmitItems];
+    uint32_t have = 0;
+#pragma unroll
+    for (int j = 0; j < kEmitItems; ++j) {
+        const bool v = s_key[j * kEmitThreads + tid] != ~0ULL;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, v);
+        rank[j] = __popc(b & ((1u << lane) - 1u));
+        have |= (v ? 1u : 0u) << j;
+        if (lane == 0) s_cnt[j * (kEmitThreads / 32) + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {  // 64 (item, warp) counts in window order -> exclusive prefix; look back for the tile's first slot
+        const uint32_t v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
+        uint32_t x = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+        s_cnt[2 * lane] = x - v0 - v1;
+        s_cnt[2 * lane + 1] = x - v1;
+        if (lane == 0) {
+            const unsigned long long excl = lookback_exclusive(status, 1, tile, total);
+            s_excl = excl;
+            if (tile + 1 == gridDim.x) *n_valid = excl + total;
         }
     }
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) a[i] = s[i];
+    __syncthreads();
+    const unsigned long long excl = s_excl;
+#pragma unroll
+    for (int j = 0; j < kEmitItems; ++j) {
+        if ((have >> j) & 1u) {
+            const unsigned long long r = excl + s_cnt[j * (kEmitThreads / 32) + warp] + rank[j];
+            if (r < cap) keys[r] = s_key[j * kEmitThreads + tid];
+        }
+    }
 }
 
-// general path: copy the first min(occ, tf) sorted occurrences into the final layout
+// normal-case test on the sorted keys: key j lies inside the bucket that owns slot j
+__global__ void positions_check_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
+                                       const unsigned long long *__restrict__ indices, uint64_t n_buckets,
+                                       int *__restrict__ bad) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t h = sorted[j] >> pos_bits;
+    if (h >= n_buckets || j < indices[h] || j >= indices[h + 1]) *bad = 1;
+}
+
+__global__ void positions_mask_kernel(uint64_t *__restrict__ buf, uint64_t n, uint64_t mask) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) buf[j] &= mask;
+}
+
+// general case: first sorted slot of every bucket that occurs ...
+__global__ void positions_run_start_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
+                                           unsigned long long *__restrict__ run_start) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t h = sorted[j] >> pos_bits;
+    if (j == 0 || (sorted[j - 1] >> pos_bits) != h) run_start[h] = j;
+}
+
+// ... then the first tf[h] occurrences of every bucket go to positions[indices[h] ...]; the rest of the bucket
+// stays 0 (hash.cpp:1037-1041: slot >= tf is dropped; unfilled slots keep the zero of the allocation)
 template <typename F>
-__global__ void clip_copy_kernel(F tf, const unsigned long long *__restrict__ tmp, const unsigned long long *__restrict__ tmp_off,
-                                 const uint32_t *__restrict__ occ, const unsigned long long *__restrict__ indices, uint64_t n,
-                                 unsigned long long *__restrict__ positions) {
-    uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n) return;
-    uint64_t keep = occ[h];
-    uint64_t cap = tf(h);
-    if (keep > cap) keep = cap;
-    const unsigned long long *src = tmp + tmp_off[h];
-    unsigned long long *dst = positions + indices[h];
-    for (uint64_t i = 0; i < keep; ++i) dst[i] = src[i];
+__global__ void positions_clip_kernel(F tf, const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
+                                      const unsigned long long *__restrict__ run_start,
+                                      const unsigned long long *__restrict__ indices,
+                                      unsigned long long *__restrict__ positions) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t key = sorted[j];
+    const uint64_t h = key >> pos_bits;
+    const uint64_t r = j - run_start[h];
+    if (r < tf(h)) positions[indices[h] + r] = key & ((1ULL << pos_bits) - 1);
 }
 
 // ---- K7 query ----------------------------------------------------------------------------
@@ -361,6 +279,12 @@ static uint64_t first_start(const uint8_t *c, uint64_t len, uint64_t k) {
     return start;
 }
 
+static int bit_length(uint64_t x) {
+    int b = 0;
+    while (x) { ++b; x >>= 1; }
+    return b;
+}
+
 // Device part of the build.  reads_dev must be readable for 8 bytes past len (aligned word
 // loads of the last windows); `start` = first_start of the image.  On success *indices_dev
 // (u64[n+1]) and *positions_dev (u64[total], at least one element) are owned by the caller.
@@ -370,13 +294,12 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
                       uint64_t *total_out) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    unsigned long long *indices = nullptr, *positions = nullptr, *tmp = nullptr, *tmp_off = nullptr, *tiles = nullptr;
-    uint32_t *occ = nullptr, *cursor = nullptr, *medium = nullptr, *large = nullptr;
-    int *over = nullptr;
-    unsigned int *cls = nullptr;
+    unsigned long long *indices = nullptr, *positions = nullptr, *tiles = nullptr, *emit_scratch = nullptr, *run_start = nullptr;
+    uint64_t *keys = nullptr, *alt = nullptr;
     auto cleanup_tmp = [&]() {
-        cudaFree(tmp); cudaFree(tmp_off); cudaFree(tiles);
-        cudaFree(occ); cudaFree(cursor); cudaFree(medium); cudaFree(large); cudaFree(over); cudaFree(cls);
+        cudaFree(tiles); cudaFree(emit_scratch); cudaFree(run_start); cudaFree(keys); cudaFree(alt);
+        tiles = emit_scratch = run_start = nullptr;
+        keys = alt = nullptr;
     };
     auto cleanup = [&]() {
         cleanup_tmp();
@@ -388,109 +311,96 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         if (e__ != cudaSuccess) {                                                                       \
             cudaGetLastError();                                                                         \
             cleanup();                                                                                  \
-            return ctx->fail(AIX_ERR_CUDA, "positions build %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return ctx->fail(e__ == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA,           \
+                             "positions build %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
         }                                                                                               \
     } while (0)
     AixTrace trace(st, "positions build");
-    const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile + 1;
     PB_CUDA(cudaMalloc(&indices, (n + 1) * 8));
-    PB_CUDA(cudaMalloc(&tiles, n_tiles * 8));
+    PB_CUDA(cudaMalloc(&tiles, scan_scratch_bytes(n)));
     int rc = exclusive_scan(ctx, st, tf, n, indices, tiles);
     if (rc != AIX_OK) { cleanup(); return rc; }
     unsigned long long total = 0;
     PB_CUDA(cudaMemcpyAsync(&total, indices + n, 8, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
-    PB_CUDA(cudaMalloc(&positions, (total ? total : 1) * 8));
-    PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
-    if (len >= (uint64_t)K && n && total) {
-        const uint64_t n_win_end = len - K + 1;
-        if (start < n_win_end) {
-            PB_CUDA(cudaMalloc(&occ, n * 4));
-            PB_CUDA(cudaMalloc(&medium, n * 4));
-            PB_CUDA(cudaMalloc(&large, n * 4));
-            PB_CUDA(cudaMalloc(&over, sizeof(int)));
-            PB_CUDA(cudaMalloc(&cls, 2 * sizeof(unsigned int)));
-            PB_CUDA(cudaMemsetAsync(occ, 0, n * 4, st));
-            PB_CUDA(cudaMemsetAsync(over, 0, sizeof(int), st));
-            PB_CUDA(cudaMemsetAsync(cls, 0, 2 * sizeof(unsigned int), st));
-            trace.mark("prefix sum + allocations");
-            // grids are limited to 2^31-1 CTAs: scan the image in launches of <= 2^38 windows
-            const uint64_t kLaunchWin = 1ull << 38;
-            // optimistic single pass straight into the final layout (occ doubles as the cursor)
-            for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
-                const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
-                positions_scan_kernel<K, 2><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, tf, reads_dev, w0, w1, occ, indices, positions);
-                ctx->launches++;
-            }
-            trace.mark("scatter pass (lookup + cursor atomic + 8-byte store per window)");
-            classify_kernel<<<aix_grid(n, 256), 256, 0, st>>>(tf, occ, n, over, medium, large, cls, kSmallMax, kMediumMax);
+    trace.mark("prefix sum of tf");
+    const uint64_t n_win_end = len >= (uint64_t)K ? len - K + 1 : 0;
+    const bool any_window = n && total && start < n_win_end;
+    if (!any_window) {
+        PB_CUDA(cudaMalloc(&positions, (total ? total : 1) * 8));
+        PB_CUDA(cudaMemsetAsync(positions, 0, (total ? total : 1) * 8, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // key = bucket << pos_bits | position (1-based byte offset <= len)
+        const int pos_bits = bit_length(len), h_bits = bit_length(n - 1) ? bit_length(n - 1) : 1;
+        if (pos_bits + h_bits > 64) {
+            cleanup();
+            return ctx->fail(AIX_ERR_ARG, "positions build: %d position bits + %d bucket bits do not fit a 64-bit key", pos_bits, h_bits);
+        }
+        const uint64_t n_win = n_win_end - start;
+        const uint64_t e_tiles = (n_win + kEmitTile - 1) / kEmitTile;
+        if (e_tiles >= (1ull << 31)) { cleanup(); return ctx->fail(AIX_ERR_ARG, "positions build: reads image too large"); }
+        // emit scratch: [0] n_valid, [1] tile counter, [2] bad flag, [8 ...] one look-back word per tile
+        PB_CUDA(cudaMalloc(&emit_scratch, (8 + e_tiles) * 8));
+        unsigned long long n_valid = 0;
+        uint64_t cap = total;  // the normal case needs exactly `total` keys; more valid windows than that = general case
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            PB_CUDA(cudaMalloc(&keys, cap * 8));
+            PB_CUDA(cudaMalloc(&alt, cap * 8));
+            PB_CUDA(cudaMemsetAsync(emit_scratch, 0, (8 + e_tiles) * 8, st));
+            positions_emit_kernel<K><<<(unsigned)e_tiles, kEmitThreads, 0, st>>>(id, md, reads_dev, start, n_win_end, pos_bits, keys, cap,
+                                                                                emit_scratch + 8, (unsigned int *)(emit_scratch + 1), emit_scratch);
             ctx->launches++;
-            int h_over = 0;
-            unsigned int h_cls[2] = {0, 0};
-            PB_CUDA(cudaMemcpyAsync(&h_over, over, sizeof(int), cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaMemcpyAsync(h_cls, cls, sizeof h_cls, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaGetLastError());
+            PB_CUDA(cudaMemcpyAsync(&n_valid, emit_scratch, 8, cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
-            trace.mark("classify");
-            unsigned long long *data = positions;
-            const unsigned long long *off = indices;
-            if (h_over) {  // some bucket overflows its tf: scatter everything aside, sort, then clip
-                PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
-                PB_CUDA(cudaMalloc(&tmp_off, (n + 1) * 8));
-                rc = exclusive_scan(ctx, st, TfFromU32{occ}, n, tmp_off, tiles);
-                if (rc != AIX_OK) { cleanup(); return rc; }
-                unsigned long long tmp_total = 0;
-                PB_CUDA(cudaMemcpyAsync(&tmp_total, tmp_off + n, 8, cudaMemcpyDeviceToHost, st));
-                PB_CUDA(cudaStreamSynchronize(st));
-                PB_CUDA(cudaMalloc(&tmp, (tmp_total ? tmp_total : 1) * 8));
-                PB_CUDA(cudaMalloc(&cursor, n * 4));
-                PB_CUDA(cudaMemsetAsync(cursor, 0, n * 4, st));
-                data = tmp;
-                off = tmp_off;
-                for (uint64_t w0 = start; w0 < n_win_end; w0 += kLaunchWin) {
-                    const uint64_t w1 = n_win_end - w0 < kLaunchWin ? n_win_end : w0 + kLaunchWin;
-                    positions_scan_kernel<K, 1><<<aix_grid(w1 - w0, 256), 256, 0, st>>>(id, md, tf, reads_dev, w0, w1, cursor, off, data);
-                    ctx->launches++;
-                }
-                trace.mark("general path: second scatter");
-            }
-            sort_small_kernel<<<aix_grid(n, 256), 256, 0, st>>>(data, off, occ, n, kSmallMax);
+            if (n_valid <= cap) break;
+            // more occurrences in the reads than the index's tf sums to (index counted on other reads): all of them
+            // must be ordered before the first tf of every bucket can be picked -- emit again with room for all
+            cudaFree(keys); cudaFree(alt);
+            keys = alt = nullptr;
+            cap = n_valid;
+        }
+        trace.mark("emit pass (lookup + ordered compaction of one key per occurrence)");
+        uint64_t *sorted = keys;
+        rc = radix_sort_u64(ctx, st, keys, alt, n_valid, pos_bits, pos_bits + h_bits, &sorted);
+        if (rc != AIX_OK) { cleanup(); return rc; }
+        trace.mark("radix sort on the bucket bits");
+        int bad = 1;
+        if (n_valid == total) {
+            int *bad_dev = (int *)(emit_scratch + 2);
+            PB_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
+            positions_check_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, indices, n, bad_dev);
             ctx->launches++;
-            if (h_cls[0]) {
-                sort_medium_kernel<<<h_cls[0], 512, 0, st>>>(data, off, occ, medium);
-                ctx->launches++;
+            PB_CUDA(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t *spare = sorted == keys ? alt : keys;
+        if (!bad) {  // every bucket exactly full: the sorted low words are positions[]
+            positions_mask_kernel<<<aix_grid(total, 256), 256, 0, st>>>(sorted, total, (1ULL << pos_bits) - 1);
+            ctx->launches++;
+            PB_CUDA(cudaGetLastError());
+            PB_CUDA(cudaStreamSynchronize(st));
+            positions = (unsigned long long *)sorted;
+            cudaFree(spare);
+            keys = alt = nullptr;
+            trace.mark("check + mask in place");
+        } else {
+            cudaFree(spare);
+            if (sorted == keys) alt = nullptr; else keys = nullptr;
+            PB_CUDA(cudaMalloc(&positions, total * 8));
+            PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
+            if (n_valid) {
+                PB_CUDA(cudaMalloc(&run_start, n * 8));
+                positions_run_start_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, run_start);
+                positions_clip_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(tf, sorted, n_valid, pos_bits, run_start, indices, positions);
+                ctx->launches += 2;
+                PB_CUDA(cudaGetLastError());
             }
-            if (h_cls[1]) {  // very large buckets (repeats): one device radix sort each
-                std::vector<uint32_t> lg(h_cls[1]);
-                PB_CUDA(cudaMemcpyAsync(lg.data(), large, (size_t)h_cls[1] * 4, cudaMemcpyDeviceToHost, st));
-                PB_CUDA(cudaStreamSynchronize(st));
-                for (uint32_t h : lg) {
-                    unsigned long long o2[2];
-                    uint32_t c = 0;
-                    PB_CUDA(cudaMemcpy(o2, off + h, 8, cudaMemcpyDeviceToHost));
-                    PB_CUDA(cudaMemcpy(&c, occ + h, 4, cudaMemcpyDeviceToHost));
-                    unsigned long long *alt = nullptr;
-                    void *ws = nullptr;
-                    size_t ws_bytes = 0;
-                    PB_CUDA(cudaMalloc(&alt, (size_t)c * 8));
-                    cub::DeviceRadixSort::SortKeys(nullptr, ws_bytes, data + o2[0], alt, (int)c, 0, 64, st);
-                    cudaError_t e2 = cudaMalloc(&ws, ws_bytes ? ws_bytes : 1);
-                    if (e2 == cudaSuccess) e2 = cub::DeviceRadixSort::SortKeys(ws, ws_bytes, data + o2[0], alt, (int)c, 0, 64, st);
-                    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(data + o2[0], alt, (size_t)c * 8, cudaMemcpyDeviceToDevice, st);
-                    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
-                    cudaFree(alt);
-                    cudaFree(ws);
-                    ctx->launches += 6;
-                    PB_CUDA(e2);
-                }
-            }
-            if (h_over) {
-                clip_copy_kernel<<<aix_grid(n, 256), 256, 0, st>>>(tf, tmp, tmp_off, occ, indices, n, positions);
-                ctx->launches++;
-            }
-            trace.mark("per-bucket sort (+ clip)");
+            PB_CUDA(cudaStreamSynchronize(st));
+            trace.mark("general case: clip the sorted occurrences to tf per bucket");
         }
     }
-    PB_CUDA(cudaStreamSynchronize(st));
 #undef PB_CUDA
     cleanup_tmp();
     trace.mark("free scratch");

@@ -1,0 +1,345 @@
+// radix_sort.cu -- hand-written LSD radix sort of 64-bit keys (one scatter kernel per digit with
+// decoupled look-back, "onesweep" style) and run-length encoding of a sorted key array.
+//
+// Users: the positions-index build (positions.cu: packed (bucket << pos_bits | position) keys, sorted on
+// the bucket bits only -- the sort is stable and the keys are emitted in position order, so every bucket
+// comes out ascending = the order of the 1-thread reference worker, src/hash.cpp:1006-1051) and the
+// canonical 23-mer table (mphf_build.cu: sort + run-length = the `sort | uniq -c` of the reference's
+// jellyfish / kmer_counter stage, scripts/compute_aindex.py:140-182).
+//
+// Per pass every key is read once and written once (16 B); the digit histograms of all passes come from
+// one extra read of the keys.  A tile is 8192 keys: ranked inside each warp with match_any (stable),
+// staged in shared memory in digit order, then written out as runs of ~32 keys (256 B) per digit.
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace aix {
+
+constexpr int kRsThreads = 512;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;  // 8192 keys
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsMaxBits = 8;
+constexpr int kRsMaxRadix = 1 << kRsMaxBits;
+constexpr int kRsMaxPasses = 8;
+// stage[kRsTile] (aliased by the per-warp histograms) + total[256] + dstart[256] + gbase[256]
+constexpr size_t kRsSmem = (size_t)kRsTile * 8 + kRsMaxRadix * 4 * 2 + kRsMaxRadix * 8;
+
+struct RsPlan {
+    int begin_bit, n_pass, bits;  // digit p covers [begin_bit + p*bits, min(end_bit, begin_bit + (p+1)*bits))
+    int end_bit;
+    __host__ __device__ int shift(int p) const { return begin_bit + p * bits; }
+    __host__ __device__ int width(int p) const {
+        int w = end_bit - shift(p);
+        return w < bits ? w : bits;
+    }
+};
+
+// hist[p][d] += number of keys whose digit p is d, for every pass in one read of the keys
+__global__ void __launch_bounds__(512) rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, RsPlan plan,
+                                                    unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t sh[kRsMaxPasses * kRsMaxRadix];
+    for (int i = threadIdx.x; i < plan.n_pass * kRsMaxRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per;
+    const uint64_t hi = lo + per < n ? lo + per : n;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint64_t k = keys[i];
+        for (int p = 0; p < plan.n_pass; ++p) {
+            const uint32_t d = (uint32_t)(k >> plan.shift(p)) & ((1u << plan.width(p)) - 1u);
+            atomicAdd(&sh[p * kRsMaxRadix + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.n_pass * kRsMaxRadix; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
+// base[p][d] = number of keys whose digit p is below d  (one CTA of 256 threads per pass)
+__global__ void __launch_bounds__(kRsMaxRadix) rs_base_kernel(const unsigned long long *__restrict__ hist,
+                                                            unsigned long long *__restrict__ base) {
+    __shared__ unsigned long long sm[33];
+    unsigned long long total;
+    const unsigned long long v = hist[blockIdx.x * kRsMaxRadix + threadIdx.x];
+    base[blockIdx.x * kRsMaxRadix + threadIdx.x] = block_scan_u64(v, sm, total);
+}
+
+// One digit pass.  Stable: equal digits keep their input order.
+__global__ void __launch_bounds__(kRsThreads, 2)
+rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, int shift, int bits,
+               const unsigned long long *__restrict__ digit_base, unsigned long long *__restrict__ status,
+               unsigned int *__restrict__ tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *stage = (uint64_t *)smem;                                        // [kRsTile]
+    uint32_t *whist = (uint32_t *)smem;                                        // [kRsWarps][radix], dead before stage is written
+    uint32_t *s_total = (uint32_t *)(smem + (size_t)kRsTile * 8);              // [256] keys of this tile per digit
+    uint32_t *s_dstart = s_total + kRsMaxRadix;                                // [256] first stage slot of the digit
+    unsigned long long *s_gbase = (unsigned long long *)(s_dstart + kRsMaxRadix);  // [256] out index of stage slot 0 of the digit
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_wsum[kRsMaxRadix / 32];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t radix = 1u << bits, mask = radix - 1u;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (uint32_t i = tid; i < kRsWarps * radix; i += kRsThreads) whist[i] = 0;
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t tile_base = tile * kRsTile;
+    const uint32_t tile_n = n - tile_base < (uint64_t)kRsTile ? (uint32_t)(n - tile_base) : (uint32_t)kRsTile;
+
+    // keys, warp-striped: item j of lane l of warp w = tile_base + w*32*ITEMS + j*32 + l
+    uint64_t key[kRsItems];
+    uint16_t pos[kRsItems];
+    const uint32_t wbase = warp * (32 * kRsItems) + lane;
+#pragma unroll
+    for (int j = 0; j < kRsItems; ++j) {
+        const uint32_t idx = wbase + j * 32;
+        key[j] = idx < tile_n ? (uint64_t)__ldcs((const unsigned long long *)(in + tile_base + idx)) : ~0ull;
+    }
+    // rank inside the warp: lanes with the same digit form a group (match_any); the group's lowest lane
+    // reserves the group's slots in the warp's histogram, members follow in lane order
+    uint32_t *my_hist = whist + warp * radix;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kRsItems; ++j) {
+        const bool valid = wbase + j * 32 < tile_n;
+        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader && valid) {
+            base = my_hist[d];
+            my_hist[d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        pos[j] = (uint16_t)(base + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over the warps, tile total; publish the aggregate at once
+    unsigned long long *my_status = status + tile * radix;
+    uint32_t total = 0;
+    if (tid < radix) {
+        for (int w = 0; w < kRsWarps; ++w) {
+            const uint32_t c = whist[w * radix + tid];
+            whist[w * radix + tid] = total;
+            total += c;
+        }
+        s_total[tid] = total;
+        st_relaxed_u64(my_status + tid, (tile == 0 ? kLbInclusive : kLbAggregate) | total);
+    }
+    // exclusive scan of the totals over the digits -> first stage slot of every digit
+    if (tid < kRsMaxRadix) {
+        uint32_t x = tid < radix ? total : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) s_wsum[warp] = x;
+        s_dstart[tid] = x - (tid < radix ? total : 0u);  // exclusive inside the warp
+    }
+    __syncthreads();
+    if (tid < kRsMaxRadix) {
+        uint32_t add = 0;
+        for (unsigned w = 0; w < warp; ++w) add += s_wsum[w];
+        s_dstart[tid] += add;
+    }
+    __syncthreads();
+    // stage slot of every key
+#pragma unroll
+    for (int j = 0; j < kRsItems; ++j) {
+        if (wbase + j * 32 < tile_n) {
+            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+            pos[j] = (uint16_t)(pos[j] + my_hist[d] + s_dstart[d]);
+        }
+    }
+    __syncthreads();  // whist is dead from here on: stage may overwrite it
+#pragma unroll
+    for (int j = 0; j < kRsItems; ++j)
+        if (wbase + j * 32 < tile_n) stage[pos[j]] = key[j];
+    // look back over the earlier tiles, one thread per digit
+    if (tid < radix) {
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            for (uint64_t p = tile; p-- > 0;) {
+                unsigned long long s;
+                do {
+                    s = ld_relaxed_u64(status + p * radix + tid);
+                } while ((s >> 62) == 0);
+                excl += s & kLbValueMask;
+                if ((s >> 62) == 2) break;
+            }
+            st_relaxed_u64(my_status + tid, kLbInclusive | (excl + total));
+        }
+        s_gbase[tid] = digit_base[tid] + excl - s_dstart[tid];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < tile_n; i += kRsThreads) {
+        const uint64_t k = stage[i];
+        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        out[s_gbase[d] + i] = k;
+    }
+}
+
+// ---- run-length encoding of a sorted array ---------------------------------------------------
+struct HeadFlag {
+    const uint64_t *k;
+    __device__ unsigned long long operator()(uint64_t i) const { return (i == 0 || k[i] != k[i - 1]) ? 1ull : 0ull; }
+};
+
+// run r starts at the r-th head: uniq[r] = key, starts[r] = its index
+__global__ void __launch_bounds__(kScanBlock) rle_heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+                                                             const unsigned long long *__restrict__ tile_off,
+                                                             uint64_t *__restrict__ uniq, unsigned long long *__restrict__ starts) {
+    __shared__ unsigned long long sm[33];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint64_t k[kScanItems + 1];
+    k[0] = (base > 0 && base - 1 < n) ? keys[base - 1] : 0;
+    unsigned long long s = 0;
+    uint32_t heads = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        k[j + 1] = base + j < n ? keys[base + j] : 0;
+        const bool h = base + j < n && (base + j == 0 || k[j + 1] != k[j]);
+        heads |= (h ? 1u : 0u) << j;
+        s += h ? 1 : 0;
+    }
+    unsigned long long total;
+    unsigned long long r = tile_off[blockIdx.x] + block_scan_u64(s, sm, total);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if ((heads >> j) & 1u) {
+            uniq[r] = k[j + 1];
+            starts[r] = base + j;
+            ++r;
+        }
+    }
+}
+
+__global__ void rle_counts_kernel(const unsigned long long *__restrict__ starts, uint64_t n_runs, uint64_t n,
+                                  uint32_t *__restrict__ counts) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const unsigned long long e = r + 1 < n_runs ? starts[r + 1] : n;
+    const unsigned long long c = e - starts[r];
+    counts[r] = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c;  // the tf arrays are u32 (src/hash.hpp:97)
+}
+
+int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt, uint64_t n, int begin_bit, int end_bit,
+                   uint64_t **sorted) {
+    *sorted = keys;
+    if (begin_bit < 0 || end_bit > 64 || (n && (!keys || !alt))) return ctx->fail(AIX_ERR_ARG, "radix sort: bad arguments");
+    if (n < 2 || end_bit <= begin_bit) return AIX_OK;
+    RsPlan plan;
+    plan.begin_bit = begin_bit;
+    plan.end_bit = end_bit;
+    const int total_bits = end_bit - begin_bit;
+    plan.n_pass = (total_bits + kRsMaxBits - 1) / kRsMaxBits;
+    plan.bits = (total_bits + plan.n_pass - 1) / plan.n_pass;
+    const uint64_t tiles = (n + kRsTile - 1) / kRsTile;
+    if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "radix sort: too many keys");
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmem));
+        attr_set[ctx->device & 63] = true;
+    }
+    // scratch: hist[8][256] | base[8][256] | counters[8] (+pad) | status[tiles][radix]
+    const size_t front = (size_t)kRsMaxPasses * kRsMaxRadix * 8 * 2 + 64;
+    const size_t status_bytes = (size_t)tiles * ((size_t)1 << plan.bits) * 8;
+    unsigned char *scratch = nullptr;
+    cudaError_t e = cudaMalloc(&scratch, front + status_bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_NOMEM, "radix sort scratch (%zu bytes): %s", front + status_bytes, cudaGetErrorString(e));
+    }
+    unsigned long long *hist = (unsigned long long *)scratch;
+    unsigned long long *base = hist + kRsMaxPasses * kRsMaxRadix;
+    unsigned int *counters = (unsigned int *)(base + kRsMaxPasses * kRsMaxRadix);
+    unsigned long long *status = (unsigned long long *)(scratch + front);
+    auto fail = [&](cudaError_t err, const char *what) {
+        cudaGetLastError();
+        cudaFree(scratch);
+        return ctx->fail(AIX_ERR_CUDA, "radix sort %s: %s", what, cudaGetErrorString(err));
+    };
+    if ((e = cudaMemsetAsync(scratch, 0, front, st)) != cudaSuccess) return fail(e, "memset");
+    unsigned hgrid = (unsigned)((n + 512ull * 64 - 1) / (512ull * 64));
+    const unsigned hmax = (unsigned)ctx->sm_count * 8u;
+    if (hgrid > hmax) hgrid = hmax;
+    if (hgrid < 1) hgrid = 1;
+    rs_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, plan, hist);
+    rs_base_kernel<<<plan.n_pass, kRsMaxRadix, 0, st>>>(hist, base);
+    ctx->launches += 2;
+    uint64_t *src = keys, *dst = alt;
+    for (int p = 0; p < plan.n_pass; ++p) {
+        if ((e = cudaMemsetAsync(status, 0, (size_t)tiles * ((size_t)1 << plan.width(p)) * 8, st)) != cudaSuccess) return fail(e, "memset");
+        rs_pass_kernel<<<(unsigned)tiles, kRsThreads, kRsSmem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
+                                                                      base + p * kRsMaxRadix, status, counters + p);
+        ctx->launches++;
+        uint64_t *t = src; src = dst; dst = t;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "launch");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "run");
+    cudaFree(scratch);
+    *sorted = src;
+    return AIX_OK;
+}
+
+int rle_u64(aix_ctx *ctx, cudaStream_t st, const uint64_t *sorted, uint64_t n, uint64_t *uniq, uint32_t *counts,
+            uint64_t *n_runs_out) {
+    *n_runs_out = 0;
+    if (n == 0) return AIX_OK;
+    const uint64_t tiles = scan_tiles(n);
+    unsigned long long *tile_off = nullptr, *starts = nullptr;
+    auto fail = [&](cudaError_t err, const char *what) {
+        cudaGetLastError();
+        cudaFree(tile_off);
+        cudaFree(starts);
+        return ctx->fail(err == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA, "run-length %s: %s", what, cudaGetErrorString(err));
+    };
+    cudaError_t e = cudaMalloc(&tile_off, scan_scratch_bytes(n));
+    if (e != cudaSuccess) return fail(e, "scratch");
+    scan_reduce_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(HeadFlag{sorted}, n, tile_off);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_off, tiles);
+    ctx->launches += 2;
+    unsigned long long n_runs = 0;
+    if ((e = cudaMemcpyAsync(&n_runs, tile_off + tiles, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "copy");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "count");
+    if ((e = cudaMalloc(&starts, (n_runs + 1) * 8)) != cudaSuccess) return fail(e, "starts");
+    rle_heads_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(sorted, n, tile_off, uniq, starts);
+    rle_counts_kernel<<<aix_grid(n_runs, 256), 256, 0, st>>>(starts, n_runs, n, counts);
+    ctx->launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "launch");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "run");
+    cudaFree(tile_off);
+    cudaFree(starts);
+    *n_runs_out = n_runs;
+    return AIX_OK;
+}
+
+}  // namespace aix
+
+using namespace aix;
+
+extern "C" {
+
+int aix_sort_u64_dev(aix_ctx *ctx, uint64_t *keys_dev, uint64_t *alt_dev, uint64_t n, int begin_bit, int end_bit,
+                     int *result_in_alt) {
+    if (!ctx || !result_in_alt) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *sorted = keys_dev;
+    AIX_TRY(radix_sort_u64(ctx, ctx->stream, keys_dev, alt_dev, n, begin_bit, end_bit, &sorted));
+    *result_in_alt = sorted == alt_dev && sorted != keys_dev ? 1 : 0;
+    return AIX_OK;
+}
+
+int aix_rle_u64_dev(aix_ctx *ctx, const uint64_t *sorted_dev, uint64_t n, uint64_t *uniq_dev, uint32_t *counts_dev,
+                    uint64_t *n_runs) {
+    if (!ctx || !n_runs || (n && (!sorted_dev || !uniq_dev || !counts_dev))) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return rle_u64(ctx, ctx->stream, sorted_dev, n, uniq_dev, counts_dev, n_runs);
+}
+
+}  // extern "C"

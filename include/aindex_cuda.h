@@ -308,6 +308,16 @@ int aix_canonical23_count_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t l
 int aix_canonical23_result_dev(aix_ctx *ctx, const uint64_t **kmers_dev,
                                const uint32_t **counts_dev, uint64_t *n);
 
+/* ---- building blocks of the two builders above, exposed for tests and callers that hold keys in HBM ------- */
+/* stable LSD radix sort of n u64 keys on bits [begin_bit, end_bit) (hand-written, csrc/radix_sort.cu; replaces the
+ * `sort` of scripts/compute_aindex.py:140-182 and the per-bucket ordering of the 1-thread worker, hash.cpp:1006-1051).
+ * alt_dev = spare buffer of n keys; *result_in_alt = 1 when the sorted keys ended up in alt_dev. */
+int aix_sort_u64_dev(aix_ctx *ctx, uint64_t *keys_dev, uint64_t *alt_dev, uint64_t n, int begin_bit, int end_bit,
+                     int *result_in_alt);
+/* run-length encoding of a sorted array (`uniq -c`): uniq_dev[r], counts_dev[r] for the *n_runs distinct keys */
+int aix_rle_u64_dev(aix_ctx *ctx, const uint64_t *sorted_dev, uint64_t n, uint64_t *uniq_dev, uint32_t *counts_dev,
+                    uint64_t *n_runs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -684,3 +684,146 @@ uint64_t orc_positions_query13(const orc_mphf *m, const uint64_t *indices,
     }
     return cnt;
 }
+
+/* ========================================================================= */
+/* canonical 23-mer table: tests/analyze_kmers.py:25-33, scripts/compute_aindex.py:164-182 */
+/* ========================================================================= */
+
+void orc_free(void *p) { free(p); }
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* canonical values of the windows [lo, hi) of the image, rolled: fwd = (fwd << 2 | code) & mask,
+ * rc = rc >> 2 | (3 - code) << 44 (identical to get_dna23_bitset + reverseDNA, kmers.cpp:12-25, 376-381,
+ * for ACGT-only windows -- checked against those functions in tests/test_oracle_golden.py);
+ * cb(value, arg) is called for every ACGT-only window */
+typedef void (*c23_cb)(uint64_t c, void *arg);
+static void canonical23_roll(const uint8_t *s, uint64_t lo, uint64_t hi, c23_cb cb, void *arg) {
+    const uint64_t mask = (1ULL << 46) - 1;
+    uint64_t f = 0, r = 0;
+    int run = 0; /* ACGT characters in a row ending at the current one */
+    if (lo >= hi) return;
+    for (uint64_t i = lo; i < hi + 22; ++i) {
+        uint64_t c;
+        switch (s[i]) {
+        case 'A': c = 0; break;
+        case 'C': c = 1; break;
+        case 'G': c = 2; break;
+        case 'T': c = 3; break;
+        default: run = 0; f = 0; r = 0; continue;
+        }
+        f = ((f << 2) | c) & mask;
+        r = (r >> 2) | ((3 - c) << 44);
+        if (++run >= 23) cb(f <= r ? f : r, arg);
+    }
+}
+static void c23_count_cb(uint64_t c, void *arg) { ((uint64_t *)arg)[c >> 34]++; }
+struct c23_scatter { uint64_t *cur, *all; };
+static void c23_scatter_cb(uint64_t c, void *arg) {
+    struct c23_scatter *sc = (struct c23_scatter *)arg;
+    sc->all[sc->cur[c >> 34]++] = c;
+}
+
+#define C23_BINS 4096 /* top 12 of the 46 bits */
+
+uint64_t orc_canonical23_count(const uint8_t *reads, uint64_t len, int threads, uint64_t **kmers_out,
+                               uint32_t **counts_out) {
+    *kmers_out = NULL;
+    *counts_out = NULL;
+    if (len < 23) return 0;
+    if (threads < 1) threads = 1;
+    const uint64_t n_win = len - 22;
+    /* pass 1: windows per bin; pass 2: scatter into bins; then every bin is sorted and run-length encoded */
+    uint64_t *bin_n = (uint64_t *)calloc((size_t)threads * C23_BINS, 8);
+    uint64_t *bin_off = (uint64_t *)calloc(C23_BINS + 1, 8);
+    const uint64_t chunk = (n_win + (uint64_t)threads - 1) / (uint64_t)threads;
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+        uint64_t lo = (uint64_t)t * chunk, hi = lo + chunk < n_win ? lo + chunk : n_win;
+        canonical23_roll(reads, lo, hi, c23_count_cb, bin_n + (size_t)t * C23_BINS);
+    }
+    /* bin b: thread 0's part, thread 1's part, ...  (bin_n becomes the write cursor of every (thread, bin)) */
+    uint64_t total = 0;
+    for (int b = 0; b < C23_BINS; ++b) {
+        bin_off[b] = total;
+        for (int t = 0; t < threads; ++t) {
+            uint64_t c = bin_n[(size_t)t * C23_BINS + b];
+            bin_n[(size_t)t * C23_BINS + b] = total;
+            total += c;
+        }
+    }
+    bin_off[C23_BINS] = total;
+    uint64_t *all = (uint64_t *)malloc((total ? total : 1) * 8);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+        uint64_t lo = (uint64_t)t * chunk, hi = lo + chunk < n_win ? lo + chunk : n_win;
+        struct c23_scatter sc = {bin_n + (size_t)t * C23_BINS, all};
+        canonical23_roll(reads, lo, hi, c23_scatter_cb, &sc);
+    }
+    uint64_t *uniq_n = (uint64_t *)calloc(C23_BINS + 1, 8);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8)
+    for (int b = 0; b < C23_BINS; ++b) {
+        uint64_t *a = all + bin_off[b], m = bin_off[b + 1] - bin_off[b], u = 0;
+        qsort(a, m, 8, cmp_u64);
+        for (uint64_t i = 0; i < m; ++i)
+            if (i == 0 || a[i] != a[i - 1]) ++u;
+        uniq_n[b] = u;
+    }
+    uint64_t n = 0;
+    for (int b = 0; b < C23_BINS; ++b) {
+        uint64_t u = uniq_n[b];
+        uniq_n[b] = n;
+        n += u;
+    }
+    uint64_t *kmers = (uint64_t *)malloc((n ? n : 1) * 8);
+    uint32_t *counts = (uint32_t *)malloc((n ? n : 1) * 4);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8)
+    for (int b = 0; b < C23_BINS; ++b) {
+        const uint64_t *a = all + bin_off[b];
+        uint64_t m = bin_off[b + 1] - bin_off[b], w = uniq_n[b];
+        for (uint64_t i = 0; i < m;) {
+            uint64_t j = i + 1;
+            while (j < m && a[j] == a[i]) ++j;
+            kmers[w] = a[i];
+            counts[w] = (uint32_t)(j - i);
+            ++w;
+            i = j;
+        }
+    }
+    free(all); free(bin_n); free(bin_off); free(uniq_n);
+    *kmers_out = kmers;
+    *counts_out = counts;
+    return n;
+}
+
+int orc_write_dat(const uint64_t *kmers, const uint32_t *counts, uint64_t n, const char *dat_path,
+                  const char *keys_path) {
+    FILE *fd = dat_path ? fopen(dat_path, "wb") : NULL, *fk = keys_path ? fopen(keys_path, "wb") : NULL;
+    if ((dat_path && !fd) || (keys_path && !fk)) {
+        if (fd) fclose(fd);
+        if (fk) fclose(fk);
+        return -1;
+    }
+    static char big1[1 << 20], big2[1 << 20];
+    if (fd) setvbuf(fd, big1, _IOFBF, sizeof big1);
+    if (fk) setvbuf(fk, big2, _IOFBF, sizeof big2);
+    char line[48];
+    int ok = 1;
+    for (uint64_t i = 0; i < n && ok; ++i) {
+        orc_bitset_dna23(kmers[i], (uint8_t *)line, 23);
+        if (fk) {
+            line[23] = '\n';
+            ok = fwrite(line, 1, 24, fk) == 24;
+        }
+        if (fd && ok) {
+            int m = 23 + snprintf(line + 23, sizeof line - 23, "\t%u\n", counts ? counts[i] : 1u);
+            ok = fwrite(line, 1, (size_t)m, fd) == (size_t)m;
+        }
+    }
+    if (fd) ok = (fclose(fd) == 0) && ok;
+    if (fk) ok = (fclose(fk) == 0) && ok;
+    return ok ? 0 : -1;
+}

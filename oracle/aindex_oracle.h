@@ -128,6 +128,21 @@ uint64_t orc_positions_query13(const orc_mphf *m, const uint64_t *indices,
                                const uint64_t *positions, uint64_t n_positions, const uint8_t *s,
                                uint64_t len, uint64_t *out, uint64_t cap);
 
+/* ---- canonical 23-mer table (the counting stage in front of the index build) ------------ */
+/* Definition: tests/analyze_kmers.py:25-33, :70-71 and the jellyfish -C branch of
+ * scripts/compute_aindex.py:164-182 -- every window of 23 upper-case ACGT characters counts for
+ * min(kmer, revcomp(kmer)) (lexicographic = numeric on the 2-bit values, kmers.cpp:376-381).
+ * (The reference's own kmer_counter is broken)  Returns the number of distinct
+ * k-mers; *kmers_out / *counts_out are malloc'ed arrays sorted by k-mer (free with orc_free). */
+uint64_t orc_canonical23_count(const uint8_t *reads, uint64_t len, int threads, uint64_t **kmers_out,
+                               uint32_t **counts_out);
+void orc_free(void *p);
+/* the two text files of scripts/compute_aindex.py:140-200: `.dat` = "KMER\tCOUNT\n" lines (input of
+ * compute_index, hash.cpp:696-701) and the key file = "KMER\n" lines (`cut -f1`, input of compute_mphf_seq).
+ * Either path may be NULL.  Returns 0 on success. */
+int orc_write_dat(const uint64_t *kmers, const uint32_t *counts, uint64_t n, const char *dat_path,
+                  const char *keys_path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,11 @@ def lib():
         L.orc_positions_query23.argtypes = [C.POINTER(_Index23), vp, vp, vp, u64, vp, u64]
         L.orc_positions_query13.restype = u64
         L.orc_positions_query13.argtypes = [C.POINTER(_Mphf), vp, vp, u64, vp, u64, vp, u64]
+        L.orc_canonical23_count.restype = u64
+        L.orc_canonical23_count.argtypes = [vp, u64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.orc_free.argtypes = [vp]
+        L.orc_write_dat.restype = C.c_int
+        L.orc_write_dat.argtypes = [vp, vp, u64, C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -363,6 +368,51 @@ def count13_direct(data, fmt: int = FMT_DETECT):
     st = CountStats()
     lib().orc_count13_direct(_ptr(a), a.size, fmt, _ptr(hist), C.byref(st))
     return hist, st.as_dict()
+
+
+def canonical23_count(reads, threads: int = 0):
+    """Sorted distinct canonical 23-mers (uint64) + counts (uint32) of a reads image
+    (tests/analyze_kmers.py:25-33: ACGT-only windows, min(kmer, revcomp))."""
+    a = _bytes_arr(reads)
+    kp, cp = C.c_void_p(), C.c_void_p()
+    n = int(lib().orc_canonical23_count(_ptr(a), a.size, threads or (os.cpu_count() or 1), C.byref(kp), C.byref(cp)))
+    try:
+        kmers = np.ctypeslib.as_array(C.cast(kp, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
+        counts = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint32)), shape=(max(n, 1),))[:n].copy()
+    finally:
+        lib().orc_free(kp)
+        lib().orc_free(cp)
+    return kmers, counts
+
+
+def write_dat(kmers, counts, dat_path=None, keys_path=None):
+    """`KMER\\tCOUNT` lines (compute_index input) and / or `KMER` lines (compute_mphf_seq input)."""
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    counts = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
+    rc = lib().orc_write_dat(_ptr(kmers), _ptr(counts), kmers.size, os.fsencode(dat_path) if dat_path else None,
+                             os.fsencode(keys_path) if keys_path else None)
+    if rc != 0:
+        raise OSError("orc_write_dat failed")
+
+
+def build_reference_index23(kmers, counts, prefix, threads: int = 0):
+    """{prefix}.pf/.kmers.bin/.tf.bin with the UNMODIFIED reference tools (oracle/_ref/bin):
+    compute_mphf_seq (emphf/compute_mphf_generic.hpp:19-61) + compute_index (compute_index.cpp:53-67).
+    Returns the seconds each tool took, or None when the reference was not compiled."""
+    import time
+    mp, ci = os.path.join(REF_BIN, "compute_mphf_seq"), os.path.join(REF_BIN, "compute_index")
+    if not (os.path.exists(mp) and os.path.exists(ci)):
+        return None
+    write_dat(kmers, counts, prefix + ".dat", prefix + ".kmers")
+    t0 = time.perf_counter()
+    subprocess.check_call([mp, prefix + ".kmers", prefix + ".pf"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    subprocess.check_call([ci, prefix + ".dat", prefix + ".pf", prefix, str(threads or (os.cpu_count() or 1)), "0"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t2 = time.perf_counter()
+    os.unlink(prefix + ".dat")
+    os.unlink(prefix + ".kmers")
+    return {"compute_mphf_seq_s": t1 - t0, "compute_index_s": t2 - t1}
 
 
 def all_13mers_block(start: int, count: int) -> np.ndarray:
