@@ -152,19 +152,29 @@ __global__ void __launch_bounds__(kEmitThreads) positions_emit_kernel(Index23Dev
     }
 }
 
-// normal-case test on the sorted keys: key j lies inside the bucket that owns slot j
-__global__ void positions_check_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
-                                       const unsigned long long *__restrict__ indices, uint64_t n_buckets,
-                                       int *__restrict__ bad) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// normal case, one pass over the sorted keys: positions[j] = low word of key j, written to the spare buffer (the
+// keys stay intact), and the test that makes this valid -- key j lies inside the bucket that owns slot j, for every
+// j; with n_valid == sum(tf) that means every bucket holds exactly its tf occurrences.  Two keys per thread.
+__global__ void __launch_bounds__(256) positions_finalize_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
+                                                               const unsigned long long *__restrict__ indices,
+                                                               uint64_t n_buckets, unsigned long long *__restrict__ positions,
+                                                               int *__restrict__ bad) {
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (j >= n) return;
-    const uint64_t h = sorted[j] >> pos_bits;
-    if (h >= n_buckets || j < indices[h] || j >= indices[h + 1]) *bad = 1;
-}
-
-__global__ void positions_mask_kernel(uint64_t *__restrict__ buf, uint64_t n, uint64_t mask) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) buf[j] &= mask;
+    const uint64_t mask = (1ULL << pos_bits) - 1;
+    bool ok = true;
+    if (j + 1 < n) {
+        const ulonglong2 k = __ldcs((const ulonglong2 *)(sorted + j));  // 16-byte aligned: j is even
+        const uint64_t h0 = k.x >> pos_bits, h1 = k.y >> pos_bits;
+        ok = h0 < n_buckets && h1 < n_buckets && j >= indices[h0] && j < indices[h0 + 1] && j + 1 >= indices[h1] &&
+             j + 1 < indices[h1 + 1];
+        __stcs((ulonglong2 *)(positions + j), make_ulonglong2(k.x & mask, k.y & mask));
+    } else {
+        const uint64_t k = sorted[j], h = k >> pos_bits;
+        ok = h < n_buckets && j >= indices[h] && j < indices[h + 1];
+        positions[j] = k & mask;
+    }
+    if (!ok) *bad = 1;
 }
 
 // general case: first sorted slot of every bucket that occurs ...
@@ -367,24 +377,21 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         if (rc != AIX_OK) { cleanup(); return rc; }
         trace.mark("radix sort on the bucket bits");
         int bad = 1;
+        uint64_t *spare = sorted == keys ? alt : keys;
         if (n_valid == total) {
             int *bad_dev = (int *)(emit_scratch + 2);
             PB_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
-            positions_check_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, indices, n, bad_dev);
+            positions_finalize_kernel<<<aix_grid((n_valid + 1) / 2, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, indices, n,
+                                                                                     (unsigned long long *)spare, bad_dev);
             ctx->launches++;
             PB_CUDA(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
         }
-        uint64_t *spare = sorted == keys ? alt : keys;
-        if (!bad) {  // every bucket exactly full: the sorted low words are positions[]
-            positions_mask_kernel<<<aix_grid(total, 256), 256, 0, st>>>(sorted, total, (1ULL << pos_bits) - 1);
-            ctx->launches++;
-            PB_CUDA(cudaGetLastError());
-            PB_CUDA(cudaStreamSynchronize(st));
-            positions = (unsigned long long *)sorted;
-            cudaFree(spare);
+        if (!bad) {  // every bucket exactly full: the low words of the sorted keys are positions[]
+            positions = (unsigned long long *)spare;
+            cudaFree(sorted);
             keys = alt = nullptr;
-            trace.mark("check + mask in place");
+            trace.mark("check + low words -> positions[] (one pass, out of place)");
         } else {
             cudaFree(spare);
             if (sorted == keys) alt = nullptr; else keys = nullptr;

@@ -15,15 +15,12 @@
 
 namespace aix {
 
-constexpr int kRsThreads = 512;
 constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;  // 8192 keys
-constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsMaxBits = 8;
 constexpr int kRsMaxRadix = 1 << kRsMaxBits;
 constexpr int kRsMaxPasses = 8;
-// stage[kRsTile] (aliased by the per-warp histograms) + total[256] + dstart[256] + gbase[256]
-constexpr size_t kRsSmem = (size_t)kRsTile * 8 + kRsMaxRadix * 4 * 2 + kRsMaxRadix * 8;
+// stage[tile] (aliased by the per-warp histograms) + total[256] + dstart[256] + gbase[256]
+constexpr size_t rs_smem(int threads) { return (size_t)threads * kRsItems * 8 + kRsMaxRadix * 4 * 2 + kRsMaxRadix * 8; }
 
 struct RsPlan {
     int begin_bit, n_pass, bits;  // digit p covers [begin_bit + p*bits, min(end_bit, begin_bit + (p+1)*bits))
@@ -66,11 +63,14 @@ __global__ void __launch_bounds__(kRsMaxRadix) rs_base_kernel(const unsigned lon
     base[blockIdx.x * kRsMaxRadix + threadIdx.x] = block_scan_u64(v, sm, total);
 }
 
-// One digit pass.  Stable: equal digits keep their input order.
-__global__ void __launch_bounds__(kRsThreads, 2)
+// One digit pass.  Stable: equal digits keep their input order.  kRsThreads = 512 (8192-key tiles, 2 CTAs / SM) or
+// 256 (4096-key tiles, 4 CTAs / SM: same threads per SM, finer interleaving of the load / rank / look-back / store phases).
+template <int kRsThreads>
+__global__ void __launch_bounds__(kRsThreads, 1024 / kRsThreads)
 rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, int shift, int bits,
                const unsigned long long *__restrict__ digit_base, unsigned long long *__restrict__ status,
                unsigned int *__restrict__ tile_counter) {
+    constexpr int kRsTile = kRsThreads * kRsItems, kRsWarps = kRsThreads / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *stage = (uint64_t *)smem;                                        // [kRsTile]
     uint32_t *whist = (uint32_t *)smem;                                        // [kRsWarps][radix], dead before stage is written
@@ -164,13 +164,22 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
     if (tid < radix) {
         unsigned long long excl = 0;
         if (tile > 0) {
-            for (uint64_t p = tile; p-- > 0;) {
-                unsigned long long s;
-                do {
-                    s = ld_relaxed_u64(status + p * radix + tid);
-                } while ((s >> 62) == 0);
-                excl += s & kLbValueMask;
-                if ((s >> 62) == 2) break;
+            // four predecessors are read at once (independent loads), then consumed in order
+            uint64_t p = tile;
+            bool done = false;
+            while (!done) {
+                unsigned long long s4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s4[u] = p > (uint64_t)u ? ld_relaxed_u64(status + (p - 1 - u) * radix + tid) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (done || p == 0) break;
+                    unsigned long long s = s4[u];
+                    while ((s >> 62) == 0) s = ld_relaxed_u64(status + (p - 1) * radix + tid);
+                    excl += s & kLbValueMask;
+                    --p;
+                    if ((s >> 62) == 2 || p == 0) done = true;
+                }
             }
             st_relaxed_u64(my_status + tid, kLbInclusive | (excl + total));
         }
@@ -239,13 +248,22 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     const int total_bits = end_bit - begin_bit;
     plan.n_pass = (total_bits + kRsMaxBits - 1) / kRsMaxBits;
     plan.bits = (total_bits + plan.n_pass - 1) / plan.n_pass;
-    const uint64_t tiles = (n + kRsTile - 1) / kRsTile;
+    static int variant = 0;  // threads per CTA of the pass kernel (AIX_RS_THREADS = 256 | 512 for A/B runs)
+    if (!variant) {
+        const char *e = getenv("AIX_RS_THREADS");
+        variant = (e && atoi(e) == 512) ? 512 : 256;  // measured at 6.4 G keys: 48.5 ms vs 55.5 ms per pass
+    }
+    const int threads = variant, tile_keys = threads * kRsItems;
+    const size_t smem = rs_smem(threads);
+    const uint64_t tiles = (n + tile_keys - 1) / tile_keys;
     if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "radix sort: too many keys");
     static bool attr_set[64] = {};
     if (!attr_set[ctx->device & 63]) {
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmem));
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(512)));
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
         attr_set[ctx->device & 63] = true;
     }
+    AixTrace trace(st, "radix sort");
     // scratch: hist[8][256] | base[8][256] | counters[8] (+pad) | status[tiles][radix]
     const size_t front = (size_t)kRsMaxPasses * kRsMaxRadix * 8 * 2 + 64;
     const size_t status_bytes = (size_t)tiles * ((size_t)1 << plan.bits) * 8;
@@ -269,20 +287,28 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     const unsigned hmax = (unsigned)ctx->sm_count * 8u;
     if (hgrid > hmax) hgrid = hmax;
     if (hgrid < 1) hgrid = 1;
+    trace.mark("scratch allocation");
     rs_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, plan, hist);
     rs_base_kernel<<<plan.n_pass, kRsMaxRadix, 0, st>>>(hist, base);
     ctx->launches += 2;
+    trace.mark("digit histograms of all passes");
     uint64_t *src = keys, *dst = alt;
     for (int p = 0; p < plan.n_pass; ++p) {
         if ((e = cudaMemsetAsync(status, 0, (size_t)tiles * ((size_t)1 << plan.width(p)) * 8, st)) != cudaSuccess) return fail(e, "memset");
-        rs_pass_kernel<<<(unsigned)tiles, kRsThreads, kRsSmem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
-                                                                      base + p * kRsMaxRadix, status, counters + p);
+        if (threads == 256)
+            rs_pass_kernel<256><<<(unsigned)tiles, 256, smem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
+                                                                    base + p * kRsMaxRadix, status, counters + p);
+        else
+            rs_pass_kernel<512><<<(unsigned)tiles, 512, smem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
+                                                                    base + p * kRsMaxRadix, status, counters + p);
         ctx->launches++;
+        trace.mark("digit pass");
         uint64_t *t = src; src = dst; dst = t;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "launch");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "run");
     cudaFree(scratch);
+    trace.mark("free scratch");
     *sorted = src;
     return AIX_OK;
 }
