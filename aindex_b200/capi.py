@@ -118,6 +118,7 @@ SIGNATURES = {
     "aix_canonical23_count": (_i, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "aix_canonical23_count_dev": (_i, [_vp, _vp, _u64, _vp]),
     "aix_canonical23_result_dev": (_i, [_vp, _pp, _pp, _vp]),
+    "aix_write_dat": (_i, [_vp, _vp, _vp, _u64, C.c_char_p, C.c_char_p]),
     "aix_sort_u64_dev": (_i, [_vp, _vp, _vp, _u64, _i, _i, C.POINTER(_i)]),
     "aix_rle_u64_dev": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
 }
@@ -277,6 +278,14 @@ class Context:
         counts = np.zeros(n.value, dtype=np.uint32)
         self.check(lib().aix_canonical23_count(self._h, _p(a), a.size, C.byref(n), _p(kmers), _p(counts)))
         return kmers, counts
+
+
+    def write_dat(self, kmers, counts, dat_path=None, keys_path=None):
+        """`.dat` ("KMER\\tCOUNT") and / or key-file ("KMER") text of a canonical 23-mer table"""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        counts = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
+        self.check(lib().aix_write_dat(self._h, _p(kmers), _p(counts), kmers.size,
+                                       os.fsencode(dat_path) if dat_path else None, os.fsencode(keys_path) if keys_path else None))
 
 
 def _free_pinned(ptr):

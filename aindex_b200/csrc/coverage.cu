@@ -126,10 +126,10 @@ using namespace aix;
 
 extern "C" {
 
-int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *seqs_dev,
-                     const int64_t *offs_dev, uint64_t n_seq, uint64_t total_bytes, uint64_t total_out, int k,
-                     uint32_t cutoff, uint32_t *out_dev) {
-    (void)total_bytes;
+// the device form on a given stream; `slot` = scratch slot of the per-call offset tables (one per stream in flight)
+static int coverage_on(aix_ctx *ctx, cudaStream_t st, int slot, const aix_index23 *ix23, const aix_index13 *ix13,
+                       const uint8_t *seqs_dev, const int64_t *offs_dev, uint64_t n_seq, uint64_t total_out, int k,
+                       uint32_t cutoff, uint32_t *out_dev) {
     if (!ctx) return AIX_ERR_ARG;
     if (k == 23 && !ix23) return ctx->fail(AIX_ERR_STATE, "23-mer index not loaded");
     if (k == 13 && !ix13) return ctx->fail(AIX_ERR_STATE, "13-mer index not loaded");
@@ -140,11 +140,11 @@ int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *i
     const uint64_t n_ctas = (total_out + kCovBlock - 1) / kCovBlock;
     void *oo;
     const size_t oo_bytes = ((n_seq + 1) * 8 + 255) & ~(size_t)255;
-    AIX_TRY(ctx->reserve(SCR_TMP1, oo_bytes + (n_ctas + 1) * 4, &oo));
+    AIX_TRY(ctx->reserve(slot, oo_bytes + (n_ctas + 1) * 4, &oo));
     uint32_t *cta_seq = reinterpret_cast<uint32_t *>((char *)oo + oo_bytes);
-    coverage_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(offs_dev, n_seq, k, (unsigned long long *)oo);
+    coverage_offsets_kernel<<<1, 1024, 0, st>>>(offs_dev, n_seq, k, (unsigned long long *)oo);
     AIX_LAUNCH_CHECK(ctx);
-    coverage_cta_seq_kernel<<<aix_grid(n_ctas + 1, 256), 256, 0, ctx->stream>>>((unsigned long long *)oo, n_seq, total_out, n_ctas, cta_seq);
+    coverage_cta_seq_kernel<<<aix_grid(n_ctas + 1, 256), 256, 0, st>>>((unsigned long long *)oo, n_seq, total_out, n_ctas, cta_seq);
     AIX_LAUNCH_CHECK(ctx);
     unsigned grid = (unsigned)n_ctas;
     Index23Dev id = {};
@@ -157,14 +157,22 @@ int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *i
         const char *e = getenv("AIX_COVERAGE_TIER");
         if (!(e && atoi(e) != 0)) id.fp = nullptr;
         if (ix23->canonical_only)
-            coverage_kernel<23, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
+            coverage_kernel<23, true><<<grid, kCovBlock, 0, st>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
         else
-            coverage_kernel<23, false><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
+            coverage_kernel<23, false><<<grid, kCovBlock, 0, st>>>(id, md, nullptr, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
     } else {
-        coverage_kernel<13, true><<<grid, kCovBlock, 0, ctx->stream>>>(id, md, ix13->tf_direct_dev, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
+        coverage_kernel<13, true><<<grid, kCovBlock, 0, st>>>(id, md, ix13->tf_direct_dev, seqs_dev, offs_dev, (unsigned long long *)oo, cta_seq, total_out, cutoff, out_dev);
     }
     AIX_LAUNCH_CHECK(ctx);
     return AIX_OK;
+}
+
+int aix_coverage_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *seqs_dev,
+                     const int64_t *offs_dev, uint64_t n_seq, uint64_t total_bytes, uint64_t total_out, int k,
+                     uint32_t cutoff, uint32_t *out_dev) {
+    (void)total_bytes;
+    if (!ctx) return AIX_ERR_ARG;
+    return coverage_on(ctx, ctx->stream, SCR_TMP1, ix23, ix13, seqs_dev, offs_dev, n_seq, total_out, k, cutoff, out_dev);
 }
 
 // Host buffers: sequences are processed in groups of whole sequences (<= ~256 MiB of
@@ -180,10 +188,11 @@ int aix_coverage(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13,
         if (offs[s + 1] < offs[s]) return ctx->fail(AIX_ERR_ARG, "offsets must be non-decreasing");
     const uint64_t group_out_target = 64ull << 20;  // output values per group
     uint64_t s0 = 0, out_done = 0;
-    std::vector<int64_t> rel;
-    // single stream: the group loop is ordered; transfers of the next group overlap through the
-    // copy engines because they are asynchronous with respect to the kernel of the previous one
-    cudaStream_t st = ctx->stream;
+    // two groups in flight on the two transfer streams, each with its own device buffers: the H2D copy of group
+    // g+1 and the D2H copy of group g-1 overlap the kernel of group g.  Device buffers are reused in stream order;
+    // the host waits only at the end.
+    std::vector<int64_t> rel[2];
+    int g = 0;
     while (s0 < n_seq) {
         uint64_t s1 = s0, g_out = 0;
         while (s1 < n_seq) {
@@ -196,22 +205,27 @@ int aix_coverage(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13,
         const uint64_t g_seq = s1 - s0;
         const uint64_t byte0 = (uint64_t)offs[s0], g_bytes = (uint64_t)offs[s1] - byte0;
         if (g_out) {
-            rel.resize(g_seq + 1);
-            for (uint64_t i = 0; i <= g_seq; ++i) rel[i] = offs[s0 + i] - (int64_t)byte0;
+            const int b = g & 1;
+            cudaStream_t st = ctx->xfer[b];
+            if (g >= 2) AIX_CUDA(ctx, cudaStreamSynchronize(st));  // rel[b] and the buffers of group g-2 are free again
+            rel[b].resize(g_seq + 1);
+            for (uint64_t i = 0; i <= g_seq; ++i) rel[b][i] = offs[s0 + i] - (int64_t)byte0;
             void *d_seq, *d_offs, *d_out;
-            AIX_TRY(ctx->reserve(SCR_IN0, g_bytes + 64, &d_seq));
-            AIX_TRY(ctx->reserve(SCR_LEN0, (g_seq + 1) * 8, &d_offs));
-            AIX_TRY(ctx->reserve(SCR_OUT0, g_out * 4, &d_out));
+            AIX_TRY(ctx->reserve(SCR_IN0 + b, g_bytes + 64, &d_seq));
+            AIX_TRY(ctx->reserve(SCR_LEN0 + b, (g_seq + 1) * 8, &d_offs));
+            AIX_TRY(ctx->reserve(SCR_OUT0 + b, g_out * 4, &d_out));
             AIX_CUDA(ctx, cudaMemcpyAsync(d_seq, seqs + byte0, g_bytes, cudaMemcpyHostToDevice, st));
-            AIX_CUDA(ctx, cudaMemcpyAsync(d_offs, rel.data(), (g_seq + 1) * 8, cudaMemcpyHostToDevice, st));
-            AIX_TRY(aix_coverage_dev(ctx, ix23, ix13, (const uint8_t *)d_seq, (const int64_t *)d_offs, g_seq, g_bytes, g_out, k,
-                                     cutoff, (uint32_t *)d_out));
+            AIX_CUDA(ctx, cudaMemcpyAsync(d_offs, rel[b].data(), (g_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+            AIX_TRY(coverage_on(ctx, st, SCR_TMP0 + b, ix23, ix13, (const uint8_t *)d_seq, (const int64_t *)d_offs, g_seq, g_out, k,
+                                cutoff, (uint32_t *)d_out));
             AIX_CUDA(ctx, cudaMemcpyAsync(out + out_done, d_out, g_out * 4, cudaMemcpyDeviceToHost, st));
-            AIX_CUDA(ctx, cudaStreamSynchronize(st));  // rel / scratch are reused by the next group
+            ++g;
         }
         out_done += g_out;
         s0 = s1;
     }
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[0]));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[1]));
     return AIX_OK;
 }
 

@@ -706,4 +706,57 @@ int aix_canonical23_count(aix_ctx *ctx, const uint8_t *reads, uint64_t len, uint
     return AIX_OK;
 }
 
+// the text files the reference's index build consumes (scripts/compute_aindex.py:140-200): `.dat` = "KMER\tCOUNT\n"
+// (input of compute_index, hash.cpp:696-701) and the key file = "KMER\n" (`cut -f1`, input of compute_mphf_seq).
+// The k-mers are decoded on the GPU (get_bitset_dna23, kmers.cpp:89-114); the host only formats the lines.
+int aix_write_dat(aix_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, const char *dat_path,
+                  const char *keys_path) {
+    if (!ctx || (n && !kmers) || (!dat_path && !keys_path)) return AIX_ERR_ARG;
+    if (dat_path && n && !counts) return ctx->fail(AIX_ERR_ARG, "write_dat: counts are required for the .dat file");
+    FILE *fd = dat_path ? fopen(dat_path, "wb") : nullptr, *fk = keys_path ? fopen(keys_path, "wb") : nullptr;
+    if ((dat_path && !fd) || (keys_path && !fk)) {
+        if (fd) fclose(fd);
+        if (fk) fclose(fk);
+        return ctx->fail(AIX_ERR_IO, "write_dat: cannot create %s", (dat_path && !fd) ? dat_path : keys_path);
+    }
+    const uint64_t chunk = 1u << 22;
+    std::vector<uint8_t> ascii(chunk * 23);
+    std::vector<char> lines(chunk * 36);
+    bool ok = true;
+    int rc = AIX_OK;
+    for (uint64_t i0 = 0; i0 < n && ok && rc == AIX_OK; i0 += chunk) {
+        const uint64_t m = n - i0 < chunk ? n - i0 : chunk;
+        rc = aix_decode_kmers(ctx, kmers + i0, m, 23, ascii.data());
+        if (rc != AIX_OK) break;
+        if (fk) {
+            char *w = lines.data();
+            for (uint64_t i = 0; i < m; ++i) {
+                memcpy(w, ascii.data() + i * 23, 23);
+                w[23] = '\n';
+                w += 24;
+            }
+            ok = fwrite(lines.data(), 1, (size_t)(w - lines.data()), fk) == (size_t)(w - lines.data());
+        }
+        if (fd && ok) {
+            char *w = lines.data();
+            for (uint64_t i = 0; i < m; ++i) {
+                memcpy(w, ascii.data() + i * 23, 23);
+                w += 23;
+                *w++ = '\t';
+                char tmp[12];
+                int d = 0;
+                uint32_t c = counts[i0 + i];
+                do { tmp[d++] = (char)('0' + c % 10); c /= 10; } while (c);
+                while (d) *w++ = tmp[--d];
+                *w++ = '\n';
+            }
+            ok = fwrite(lines.data(), 1, (size_t)(w - lines.data()), fd) == (size_t)(w - lines.data());
+        }
+    }
+    if (fd) ok = (fclose(fd) == 0) && ok;
+    if (fk) ok = (fclose(fk) == 0) && ok;
+    if (rc != AIX_OK) return rc;
+    return ok ? AIX_OK : ctx->fail(AIX_ERR_IO, "write_dat: short write");
+}
+
 }  // extern "C"

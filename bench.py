@@ -46,15 +46,6 @@ RED_PEAK_256M_G = 32.0        # random RED.ADD.U32 into a 256 MiB table (the nor
 RED_PEAK_L2_G = 210.0         # the same into a 64 MiB (L2-resident) slice, G/s
 
 
-def _ncu_traffic(key, units, units_profiled):
-    """DRAM bytes per launch from the committed ncu capture, scaled if the run uses another size."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
-        return d["bytes_per_launch"] * (units / units_profiled)
-    except Exception:
-        return None
-
-
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -68,139 +59,15 @@ def parse_args():
     ap.add_argument("--count-genome", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="c4,c1,c5", help="other BASELINE configs measured at N=1 ('' = none)")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the BASELINE sizes for --configs (smoke runs)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-# ------------------------------------------------------------------------------------------
-# synthetic data (torch on the GPU: setup only, never timed)
-# ------------------------------------------------------------------------------------------
-def make_reads(torch, dev, genome_len, n_reads, read_len, seed_genome, seed_reads):
-    """uint8[n_reads, read_len+1] plain-text reads ('\\n' terminated), uniform start, strand
-    flipped with p = 0.5, no errors."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed_genome)
-    genome = torch.randint(0, 4, (genome_len,), generator=g, device=dev, dtype=torch.uint8)
-    g.manual_seed(seed_reads)
-    lut = torch.tensor(list(b"ACGT"), device=dev, dtype=torch.uint8)
-    out = torch.empty((n_reads, read_len + 1), device=dev, dtype=torch.uint8)
-    ar = torch.arange(read_len, device=dev, dtype=torch.int64)
-    chunk = 2_000_000
-    for s in range(0, n_reads, chunk):
-        e = min(n_reads, s + chunk)
-        start = torch.randint(0, genome_len - read_len, (e - s,), generator=g, device=dev, dtype=torch.int64)
-        flip = torch.rand((e - s,), generator=g, device=dev) < 0.5
-        codes = genome[start[:, None] + ar[None, :]]
-        rc = (3 - codes).flip(1)
-        codes = torch.where(flip[:, None], rc, codes)
-        out[s:e, :read_len] = lut[codes.long()]
-    out[:, read_len] = 10
-    return out
-
-
-def make_queries(torch, dev, n, seed):
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    lut = torch.tensor(list(b"ACGT"), device=dev, dtype=torch.uint8)
-    out = torch.empty((n, 23), device=dev, dtype=torch.uint8)
-    chunk = 20_000_000
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
-        out[s:e] = lut[torch.randint(0, 4, (e - s, 23), generator=g, device=dev, dtype=torch.uint8).long()]
-    return out
-
-
-def make_hit_queries(torch, dev, reads, n, seed):
-    """Q2 half: 23-byte substrings of the reads at random offsets, random strand."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    n_reads, width = reads.shape
-    out = torch.empty((n, 23), device=dev, dtype=torch.uint8)
-    ar = torch.arange(23, device=dev, dtype=torch.int64)
-    comp = torch.zeros(256, device=dev, dtype=torch.uint8)
-    for a, b in zip(b"ACGT", b"TGCA"):
-        comp[a] = b
-    chunk = 10_000_000
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
-        r = torch.randint(0, n_reads, (e - s,), generator=g, device=dev, dtype=torch.int64)
-        o = torch.randint(0, width - 1 - 23 + 1, (e - s,), generator=g, device=dev, dtype=torch.int64)
-        sub = reads.reshape(-1)[(r * width + o)[:, None] + ar[None, :]]
-        flip = torch.rand((e - s,), generator=g, device=dev) < 0.5
-        out[s:e] = torch.where(flip[:, None], comp[sub.long()].flip(1), sub)
-    return out
-
-
-def build_index(torch, capi, ctx, reads):
-    """reads (device tensor) -> canonical 23-mer table -> GPU MPHF -> {checker, tf} fill.
-    Returns (mphf, index, checker_dev, tf_dev, n)."""
-    import ctypes as C
-    lib = capi.lib()
-    n = C.c_uint64()
-    ctx.check(lib.aix_canonical23_count_dev(ctx.handle, reads.data_ptr(), reads.numel(), C.byref(n)))
-    kp, cp = C.c_void_p(), C.c_void_p()
-    ctx.check(lib.aix_canonical23_result_dev(ctx.handle, C.byref(kp), C.byref(cp), None))
-    n = int(n.value)
-    mphf = capi.Mphf.build_dev(ctx, kp.value, n, 23)
-    checker = torch.empty(n, device=reads.device, dtype=torch.int64)
-    tf = torch.empty(n, device=reads.device, dtype=torch.int32)
-    ctx.check(lib.aix_index23_fill_dev(ctx.handle, mphf._h, kp.value, cp.value, n, checker.data_ptr(), tf.data_ptr()))
-    index = capi.Index23.upload_dev(ctx, mphf, checker.data_ptr(), tf.data_ptr(), n)
-    return mphf, index, checker, tf, n
-
-
-# ------------------------------------------------------------------------------------------
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.path = None
-
-    def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(prefix="aix_clocks_", suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.proc:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        return out
+from bench_common import (ClockSampler, _tmp_root, _wrap_device_i64, build_index, cpu_count_run, cpu_query_runs,  # noqa: E402,F401
+                          make_hit_queries, make_queries, make_reads, ncu_traffic, peak_hbm_gbs, ref_harness_path,
+                          write_index_files)
 
 
 def dist_setup(args):
@@ -210,75 +77,201 @@ def dist_setup(args):
     return rank, world, local
 
 
-# ------------------------------------------------------------------------------------------
-# CPU baseline / reference arm
-# ------------------------------------------------------------------------------------------
-def _tmp_root(min_free: int = 8 << 30):
-    """/dev/shm when it has room for the baseline's files (queries 2.3 GB + index 0.6 GB), else the default tmp dir"""
+def c2_config(args, world, n_keys):
+    """The `config` object of the JSON line: identical in both arms (the reference arm times the same 100 M-query
+    batch per step on the same index; it has one host, so its rate does not depend on `world`)."""
+    return {"workload": "C2: 23-mer index over 10M synthetic 150bp reads; 100M random batch tf queries (Q1, ~100% miss) per GPU",
+            "reads": args.reads, "genome_bp": args.genome, "queries_per_gpu": args.queries, "index_keys": n_keys,
+            "parallelism": f"replicated index, queries sharded x{world}",
+            "l2": "inputs larger than L2 (2.3 GB of queries, 0.8 GB index per pass); no flush needed"}
+
+
+def _guard(fn):
+    """A config run must not take the headline line down with it: report the error in its block instead."""
     try:
-        if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free >= min_free:
-            return "/dev/shm"
-    except OSError:
-        pass
-    return None
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
-def ref_harness_path():
-    p = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_harness")
-    return p if os.path.exists(p) else None
+# ------------------------------------------------------------------------------------------
+# the C2 index built by the UNMODIFIED reference tools, cached per box
+# ------------------------------------------------------------------------------------------
+def ref_index_cache_dir(args):
+    root = _tmp_root(4 << 30) or tempfile.gettempdir()
+    return os.path.join(root, f"aix_bench_cache_c2_{args.reads}_{args.genome}")
 
 
-def write_index_files(tmpdir, mphf, checker_np, tf_np):
-    prefix = os.path.join(tmpdir, "c2.23")
-    mphf.save(prefix + ".pf")
-    checker_np.tofile(prefix + ".kmers.bin")
-    tf_np.tofile(prefix + ".tf.bin")
-    return prefix
-
-
-def cpu_query_runs(prefix, queries_np, threads, reps, mphf_info=None, checker_np=None, tf_np=None):
-    """Run the reference CPU path over `queries_np` (uint8[q,23]) `reps` times.
-    -> (kind, [seconds per rep], results uint32[q])."""
-    q = queries_np.shape[0]
-    h = ref_harness_path()
-    if h:
-        qf, of = prefix + ".queries.bin", prefix + ".out.bin"
-        queries_np.tofile(qf)
-        r = subprocess.run([h, "tf23", prefix + ".pf", prefix + ".tf.bin", prefix + ".kmers.bin", qf, str(q),
-                            str(threads), of, str(reps)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        if r.returncode == 0:
-            secs = [float(l.split()[0].split("=")[1]) for l in r.stdout.splitlines() if l.startswith("seconds=")]
-            return "reference", secs, np.fromfile(of, dtype=np.uint32)
-    # the reference was not compiled: time the C oracle port (oracle/aindex_oracle.c, OpenMP)
+def build_reference_index_c2(args, reads_np, cache):
+    """reads (uint8 host array) -> canonical 23-mer table (oracle, CPU; definition tests/analyze_kmers.py:25-33) ->
+    compute_mphf_seq + compute_index (unmodified reference binaries) -> {cache}/c2.23.{pf,kmers.bin,tf.bin} + meta.json.
+    No product code is involved.  Returns the meta dict, or None when the reference was not compiled."""
     from oracle import oracle as O
-    oix = O.Index23.load_prefix(prefix)
-    secs, res = [], None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        res = oix.batch(queries_np, None, O.MODE_TF, threads=threads)
-        secs.append(time.perf_counter() - t0)
-    return "port", secs, res
+    meta_p = os.path.join(cache, "meta.json")
+    if os.path.exists(meta_p):
+        return json.load(open(meta_p))
+    os.makedirs(cache, exist_ok=True)
+    t0 = time.perf_counter()
+    kmers, counts = O.canonical23_count(reads_np)
+    t1 = time.perf_counter()
+    tool_s = O.build_reference_index23(kmers, counts, os.path.join(cache, "c2.23"))
+    if tool_s is None:
+        return None
+    meta = {"index_keys": int(kmers.size), "canonical_count_s": t1 - t0, **tool_s,
+            "built_by": "oracle canonical23_count + oracle/_ref/bin/compute_mphf_seq + compute_index"}
+    with open(meta_p + ".tmp", "w") as f:
+        json.dump(meta, f)
+    os.replace(meta_p + ".tmp", meta_p)
+    return meta
 
 
-def cpu_count_run(reads_np, threads, tmpdir):
-    """count_kmers13 of the reference on a plain reads sample -> (kind, seconds, k-mers, tf array)."""
-    binp = os.path.join(ROOT, "oracle", "_ref", "bin", "count_kmers13")
-    pf = os.path.join(ROOT, "oracle", "_ref", "data", "all_13mers.pf")
-    n_kmers = (reads_np.shape[1] - 1 - 12) * reads_np.shape[0]
-    if os.path.exists(binp) and os.path.exists(pf):
-        rp, op = os.path.join(tmpdir, "c3.reads"), os.path.join(tmpdir, "c3.tf.bin")
-        reads_np.tofile(rp)
-        t0 = time.perf_counter()
-        r = subprocess.run([binp, rp, pf, op, str(threads)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        wall = time.perf_counter() - t0
-        if r.returncode == 0:
-            ms = [l for l in r.stdout.splitlines() if l.startswith("Processing completed in")]
-            secs = float(ms[0].split()[3]) / 1e3 if ms else wall
-            tf = np.fromfile(op, dtype=np.uint64)
-            os.unlink(op)
-            os.unlink(rp)
-            return "reference", secs, n_kmers, tf, pf
-    return None
+def reference_built_index_check(torch, capi, ctx, stream, args, q_dev, out_dev, n_keys):
+    """north_star: "MPHF construction reuses the reference's emphf output".  When the reference arm (run first by the
+    driver) has left its reference-built C2 index in the box's cache, load THOSE files and answer the same 100 M
+    queries with them: answers must equal the GPU-built index's, and the rate is reported next to the headline."""
+    cache = ref_index_cache_dir(args)
+    prefix = os.path.join(cache, "c2.23")
+    if not os.path.exists(os.path.join(cache, "meta.json")):
+        return {"available": False, "note": "no reference-built index cached on this box (the --impl reference arm builds it; "
+                                            "tests/test_gpu_fullsize.py::test_c2_reference_built_index builds and checks it as well)"}
+    try:
+        meta = json.load(open(os.path.join(cache, "meta.json")))
+        ix = capi.Index23.load_prefix(ctx, prefix)
+        out2 = torch.empty_like(out_dev)
+
+        def step():
+            ix.query_dev(q_dev.data_ptr(), 23, None, args.queries, capi.Q_TF, out2.data_ptr())
+
+        for _ in range(3):
+            step()
+        ctx.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(5):
+            step()
+        b.record(stream)
+        ctx.sync()
+        ms = a.elapsed_time(b) / 5
+        return {"available": True, "index_keys": meta["index_keys"], "same_key_count_as_gpu_built": meta["index_keys"] == n_keys,
+                "answers_equal_gpu_built_index": bool(torch.equal(out2, out_dev)), "queries": args.queries,
+                "value": args.queries / (ms / 1e3), "unit": "queries/s (device resident, reference-built .pf/.kmers.bin/.tf.bin)",
+                "ms_per_step": ms, "layout": ix.layout if hasattr(ix, "layout") else None, "built_by": meta.get("built_by")}
+    except Exception as e:  # noqa: BLE001
+        return {"available": False, "error": f"{type(e).__name__}: {e}"}
+
+
+def sharded_index_check(torch, dist, capi, ctx, stream, dev, args, rank, world, mphf, checker_t, tf_t, n_keys, q_dev, out_dev,
+                        barrier, max_over_ranks):
+    """The index split by hash-id range over the ranks (north_star: "split by hash range when it exceeds HBM"):
+    one `query` collective per rank batch; answers must equal the replicated index's, and on rank 0 the
+    unmodified reference's on the first 1 M queries."""
+    from aindex_b200 import dist as D
+    nq = min(args.queries, 20_000_000)
+    try:
+        sh = D.ShardedIndex23(n_keys).attach(ctx, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32), stream)
+        recs = q_dev[:nq]
+        res = sh.query(recs)  # warm-up (NCCL all-to-all buffers)
+        ctx.sync()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        res = sh.query(recs)
+        b.record(stream)
+        ctx.sync()
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        same = torch.tensor([1 if torch.equal(res.to(torch.int32), out_dev[:nq]) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out = {"equal": bool(int(same.item())), "queries_per_rank": nq, "value": world * nq / (ms / 1e3), "unit": "queries/s (aggregate)",
+               "ms_per_step": ms, "records_per_rank": sh.hi - sh.lo, "equals_reference_1M": None}
+        if rank == 0 and ref_harness_path():
+            tmpdir = tempfile.mkdtemp(prefix="aix_shard_", dir=_tmp_root())
+            try:
+                prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
+                n1 = min(nq, 1_000_000)
+                kind, secs, ref = cpu_query_runs(prefix, recs[:n1].cpu().numpy(), os.cpu_count() or 1, 1)
+                out["equals_reference_1M"] = bool(kind == "reference" and np.array_equal(ref, res[:n1].cpu().numpy().astype(np.uint32)))
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
+        return out
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return {"equal": None, "error": f"{type(e).__name__}: {e}"}
+
+
+def count13_multi_gpu_vs_reference(torch, dist, capi, ctx, stream, dev, rank, world, creads, peer, hist_tensor, rs_out):
+    """Multi-GPU counting against the UNMODIFIED reference binary: every rank counts the first reads of its shard,
+    the histograms are combined over k-mer ranges exactly as in the timed step (fused peer-memory combine, else NCCL
+    reduce-scatter), the slices are gathered on rank 0 and permuted into .tf.bin order; rank 0 runs count_kmers13 on
+    the concatenation of the samples.  Also checks rank 0's own sample alone (single-GPU path on the same data)."""
+    lib = capi.lib()
+    from bench_common import PF13
+    n_s = max(50_000, 2_000_000 // world)
+    n_s = min(n_s, creads.shape[0])
+    sample = creads[:n_s].contiguous()
+    out = {"reads_per_rank": n_s, "combined_equal": None, "rank0_alone_equal": None}
+    try:
+        ctx.check(lib.aix_count13_begin(ctx.handle))
+        ctx.check(lib.aix_count13_add_dev(ctx.handle, sample.data_ptr(), sample.numel(), capi.FMT_PLAIN))
+        if peer is not None:
+            res = peer.reduce(stream)
+            with torch.cuda.stream(stream):
+                mine = res.clone()
+        else:
+            ctx.check(lib.aix_count13_flush(ctx.handle))
+            with torch.cuda.stream(stream):
+                dist.reduce_scatter_tensor(rs_out, hist_tensor, op=dist.ReduceOp.SUM)
+                mine = rs_out.clone()
+        ctx.sync()
+        with torch.cuda.stream(stream):
+            parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            reads_parts = [torch.empty_like(sample) for _ in range(world)] if rank == 0 else None
+            dist.gather(sample, reads_parts, dst=0)
+        ctx.sync()
+        ok = torch.ones(2, device=dev, dtype=torch.int32)
+        if rank == 0:
+            have_ref = os.path.exists(PF13) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "count_kmers13"))
+            if have_ref:
+                m13 = capi.Mphf.load(ctx, PF13)
+                # combined direct-address histogram -> the library's buffer -> MPHF order (.tf.bin layout)
+                ctx.check(lib.aix_count13_flush(ctx.handle))
+                with torch.cuda.stream(stream):
+                    hist_tensor.copy_(torch.cat(parts))
+                    tf_dev = torch.zeros(1 << 26, device=dev, dtype=torch.int64)
+                ctx.check(lib.aix_count13_finish_dev(ctx.handle, m13._h, 0, 1 << 26, tf_dev.data_ptr()))
+                ctx.sync()
+                tmpdir = tempfile.mkdtemp(prefix="aix_mg_", dir=_tmp_root())
+                try:
+                    all_reads = torch.cat(reads_parts).cpu().numpy()
+                    cr = cpu_count_run(all_reads, os.cpu_count() or 1, tmpdir)
+                    if cr:
+                        ok[0] = 1 if np.array_equal(cr[3], tf_dev.cpu().numpy().view(np.uint64)) else 0
+                        out["reference_seconds"] = cr[1]
+                        cr1 = cpu_count_run(all_reads[:min(n_s, 250_000)], os.cpu_count() or 1, tmpdir)
+                        tf_q, _ = ctx.count13(m13, all_reads[:min(n_s, 250_000)].reshape(-1), capi.FMT_PLAIN)
+                        ok[1] = 1 if (cr1 and np.array_equal(cr1[3], tf_q)) else 0
+                finally:
+                    shutil.rmtree(tmpdir, ignore_errors=True)
+                del m13
+            else:
+                ok[:] = -1
+        with torch.cuda.stream(stream):
+            dist.broadcast(ok, src=0)
+        ctx.sync()
+        v = [int(x) for x in ok.cpu()]
+        out["combined_equal"] = None if v[0] < 0 else bool(v[0])
+        out["rank0_alone_equal"] = None if v[1] < 0 else bool(v[1])
+        out["total_reads"] = n_s * world
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
 
 
 # ------------------------------------------------------------------------------------------
@@ -423,6 +416,11 @@ def run_ours(args):
         q_host = None
         e2e_packed = None
 
+    # ---- parity legs that need the queries still in HBM (untimed except where a value is reported) ---------
+    ref_built = reference_built_index_check(torch, capi, ctx, stream, args, q_dev, out_dev, n_keys) if rank == 0 else None
+    sharded = sharded_index_check(torch, dist, capi, ctx, stream, dev, args, rank, world, mphf, checker_t, tf_t, n_keys,
+                                  q_dev, out_dev, barrier, max_over_ranks) if world > 1 else None
+
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks = {}
     try:
@@ -437,7 +435,7 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_unit": Q1_BYTES_PER_QUERY, "units_per_launch": args.queries, "kernel_ms": k_ms,
                 "achieved_one_probe_bytes": args.queries * Q1_BYTES_ONE_PROBE / (k_ms / 1e3) / 1e9,
-                "traffic": _ncu_traffic("tf23_fixed_kernel_q1_100M", args.queries, 100_000_000),
+                "traffic": ncu_traffic("tf23_stream_kernel_q1_100M", args.queries),
                 "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
                 # the other denominators of this kernel (profiles/r01_atomic_roofline.txt):
                 # random 16-byte gathers from a 1 GiB table run at 50.1 G/s on this GPU (the index is 0.8 GB)
@@ -449,7 +447,8 @@ def run_ours(args):
     # ---- 13-mer counting (second half of the metric), per-GPU shard of C3 -------------------------
     extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries,
                        "canonical_only": index.info["canonical_only"]},
-             "tf23_q2_half_hits": q2, "tf23_packed_e2e": e2e_packed, "setup_s": setup_s}
+             "tf23_q2_half_hits": q2, "tf23_packed_e2e": e2e_packed, "setup_s": setup_s,
+             "reference_built_index": ref_built, "sharded_index23": sharded}
     creads = None
     if args.count_reads > 0:
         del q_dev
@@ -556,9 +555,29 @@ def run_ours(args):
                                        "h2d_bytes_per_step": int(n_bytes * world), "d2h_bytes_per_step": 32 * world,
                                        "stats_ok": bool(st.valid == n_kmers)}
             del r_host
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # the reference binary on the first 1 M reads of the shard, all host threads; results compared
+            n_s = min(args.count_reads, 1_000_000)
+            tmpdir = tempfile.mkdtemp(prefix="aix_bench_", dir=_tmp_root())
+            try:
+                sample_np = creads[:n_s].cpu().numpy()
+                cr = cpu_count_run(sample_np, os.cpu_count() or 1, tmpdir)
+                if cr:
+                    kind_c, secs_c, nk, tf_ref, pf13 = cr
+                    m13 = capi.Mphf.load(ctx, pf13)
+                    tf_gpu, _ = ctx.count13(m13, sample_np.reshape(-1), capi.FMT_PLAIN)
+                    extra["count13"]["cpu_baseline"] = {"value": nk / secs_c, "unit": "k-mers/s", "cores": os.cpu_count() or 1,
+                                                        "kind": kind_c, "sample": f"first {n_s} reads of the shard (count_kmers13, all host threads)",
+                                                        "seconds": secs_c, "results_equal_gpu": bool(np.array_equal(tf_ref, tf_gpu))}
+                    del m13
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
+        if world > 1:
+            extra["count13"]["multi_gpu_equals_reference"] = count13_multi_gpu_vs_reference(
+                torch, dist, capi, ctx, stream, dev, rank, world, creads, peer, hist_tensor, rs_out)
         ctx.check(lib.aix_count13_end(ctx.handle))
-
-    clocks = sampler.stop() if rank == 0 else None
+    del creads
+    torch.cuda.empty_cache()
 
     # ---- CPU baseline on the same box (rank 0, N = 1 only) -------------------------------------
     cpu_baseline = None
@@ -567,28 +586,39 @@ def run_ours(args):
         tmpdir = tempfile.mkdtemp(prefix="aix_bench_", dir=_tmp_root())
         try:
             prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
-            sample = args.cpu_sample or min(args.queries, 6_250_000 * threads)  # 16 threads: the whole 100 M batch (~4 s per pass)
+            sample = args.cpu_sample or min(args.queries, 2_000_000 * threads)  # ~1.5 s per pass
             if q_host is None:
                 raise RuntimeError("cpu baseline needs the host copy of the queries")
             qs = np.ascontiguousarray(q_host[:sample])
-            kind, secs, res = cpu_query_runs(prefix, qs, threads, 2)
+            kind, secs, res = cpu_query_runs(prefix, qs, threads, 3)
             gpu_res = o_host[:sample]
             cpu_baseline = {"value": sample / min(secs), "unit": "queries/s", "cores": threads, "kind": kind,
                             "sample": f"first {sample} of the {args.queries} Q1 queries, best of {len(secs)} passes, "
                                       f"{threads} std::threads over PHASH_MAP::get_freq",
                             "seconds": min(secs), "results_equal_gpu": bool(np.array_equal(res, gpu_res))}
-            if creads is not None:
-                n_s = min(args.count_reads, 1_000_000)
-                cr = cpu_count_run(creads[:n_s].cpu().numpy(), threads, tmpdir)
-                if cr:
-                    kind_c, secs_c, nk, tf_ref, pf13 = cr
-                    m13 = capi.Mphf.load(ctx, pf13)
-                    tf_gpu, _ = ctx.count13(m13, creads[:n_s].cpu().numpy().reshape(-1), capi.FMT_PLAIN)
-                    extra["count13"]["cpu_baseline"] = {"value": nk / secs_c, "unit": "k-mers/s", "cores": threads,
-                                                        "kind": kind_c, "sample": f"first {n_s} reads of the shard (count_kmers13, {threads} threads)",
-                                                        "seconds": secs_c, "results_equal_gpu": bool(np.array_equal(tf_ref, tf_gpu))}
         finally:
             shutil.rmtree(tmpdir, ignore_errors=True)
+    q_host = o_host = None
+
+    # ---- the other BASELINE configs (C4 coverage on this index, C1 all-4^13 tf query, C5 positions index), N = 1 ---
+    if rank == 0 and world == 1 and args.configs:
+        import types
+        import bench_configs
+        torch.cuda.set_stream(stream)  # torch work of the config runs and the library's kernels share one stream
+        cargs = types.SimpleNamespace(scale=args.config_scale, checks=False, e2e=not args.no_e2e, cpu=not args.no_cpu_baseline)
+        names = [c.strip().lower() for c in args.configs.split(",") if c.strip()]
+        if "c4" in names:
+            extra["c4_coverage"] = _guard(lambda: bench_configs.run_c4(ctx, stream, dev, cargs,
+                                                                      None if args.config_scale != 1.0 else (mphf, index, checker_t, tf_t, n_keys)))
+        del index, mphf, checker_t, tf_t
+        torch.cuda.empty_cache()
+        if "c1" in names:
+            extra["c1_tf13_all"] = _guard(lambda: bench_configs.run_c1(ctx, stream, dev, cargs))
+            torch.cuda.empty_cache()
+        if "c5" in names:
+            extra["c5_positions"] = _guard(lambda: bench_configs.run_c5(ctx, stream, dev, cargs))
+            torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         line = {
@@ -599,10 +629,7 @@ def run_ours(args):
                                 "the Python list API on unstated hardware (README.md:14) -- another config, so no ratio is formed; "
                                 "the reference is timed on this box instead (cpu_baseline, --impl reference, profiles/r01_api_path.json)",
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C2: 23-mer index over 10M synthetic 150bp reads; 100M random batch tf queries (Q1, ~100% miss) per GPU",
-                       "reads": args.reads, "genome_bp": args.genome, "queries_per_gpu": args.queries, "index_keys": n_keys,
-                       "parallelism": f"replicated index, queries sharded x{world}",
-                       "l2": "inputs larger than L2 (2.3 GB of queries, 0.8 GB index per pass); no flush needed"},
+            "config": c2_config(args, world, n_keys),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "extra": extra,
         }
@@ -611,56 +638,69 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _wrap_device_i64(torch, ptr, n, dev):
-    """torch view of a device buffer owned by libaindex_cuda (no copy)."""
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
-    return torch.as_tensor(h, device=dev)
-
-
 # ------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's own CPU implementation of the path, all host threads, same config."""
+    """The reference's own CPU implementation of the path, all host threads, same config: the same synthetic reads,
+    the index built from them by the reference's own tools, the same 100 M Q1 queries per step through
+    PHASH_MAP::get_freq.  Nothing of the product is imported or executed in this arm: torch (data generation only),
+    the oracle's canonical 23-mer counter (the counting stage in front of the index build) and oracle/_ref binaries."""
     rank, world, local = dist_setup(args)
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     import torch
-    from aindex_b200 import capi
-    if not torch.cuda.is_available():
-        _emit({"impl": "reference", "unavailable": "index setup for config C2 needs the GPU builder (no GPU visible)"})
+    harness = ref_harness_path()
+    if harness is None:
+        _emit({"impl": "reference", "unavailable": "oracle/_ref/bin/ref_harness missing (the reference was not compiled into oracle/_ref)"})
         return
-    dev = torch.device("cuda", 0)
-    ctx = capi.Context(0)
-    # setup only (untimed): the same index and the same Q1 queries as our arm
-    reads = make_reads(torch, dev, args.genome, args.reads, 150, 1, 2)
-    mphf, index, checker_t, tf_t, n_keys = build_index(torch, capi, ctx, reads)
-    del reads
-    sample = args.cpu_sample or min(args.queries, 1_000_000 * threads)
-    q = make_queries(torch, dev, args.queries, 3)[:sample].cpu().numpy()
-    tmpdir = tempfile.mkdtemp(prefix="aix_ref_", dir=_tmp_root())
-    try:
-        prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
-        del index, mphf, checker_t, tf_t
-        ctx.close()
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    cache = ref_index_cache_dir(args)
+    t0 = time.perf_counter()
+    if not os.path.exists(os.path.join(cache, "meta.json")):
+        reads = make_reads(torch, dev, args.genome, args.reads, 150, 1, 2)  # the generator and seeds of our arm
+        reads_np = reads.cpu().numpy().reshape(-1)
+        del reads
+        meta = build_reference_index_c2(args, reads_np, cache)
+        del reads_np
+    else:
+        meta = json.load(open(os.path.join(cache, "meta.json")))
+    if meta is None:
+        _emit({"impl": "reference", "unavailable": "reference tools missing under oracle/_ref/bin"})
+        return
+    prefix = os.path.join(cache, "c2.23")
+    n_q = args.cpu_sample or args.queries  # the whole batch of our arm per step (same_config)
+    q = make_queries(torch, dev, args.queries, 3)[:n_q].cpu().numpy()
+    if dev.type == "cuda":
         torch.cuda.empty_cache()
-        kind, secs, _ = cpu_query_runs(prefix, q, threads, args.warmup + args.steps)
+    setup_s = time.perf_counter() - t0
+    qdir = tempfile.mkdtemp(prefix="aix_ref_", dir=_tmp_root(4 << 30))
+    try:
+        qf, of = os.path.join(qdir, "q1.bin"), os.path.join(qdir, "out.bin")
+        q.tofile(qf)
+        del q
+        r = subprocess.run([harness, "tf23", prefix + ".pf", prefix + ".tf.bin", prefix + ".kmers.bin", qf, str(n_q),
+                            str(threads), of, str(args.warmup + args.steps)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        if r.returncode != 0:
+            _emit({"impl": "reference", "unavailable": f"ref_harness failed with exit code {r.returncode}"})
+            return
+        secs = [float(l.split()[0].split("=")[1]) for l in r.stdout.splitlines() if l.startswith("seconds=")]
+        hits = int(np.count_nonzero(np.fromfile(of, dtype=np.uint32)))
     finally:
-        shutil.rmtree(tmpdir, ignore_errors=True)
+        shutil.rmtree(qdir, ignore_errors=True)
     timed = secs[args.warmup:] if len(secs) > args.warmup else secs
     s_per_step = float(np.mean(timed))
-    v = sample / s_per_step
+    v = n_q / s_per_step
     line = {"impl": "reference", "metric": "23-mer batch tf queries/s", "value": v, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C2: 23-mer index over 10M synthetic 150bp reads; random batch tf queries (Q1, ~100% miss)",
-                       "reads": args.reads, "genome_bp": args.genome, "index_keys": n_keys,
-                       "queries_per_step": sample, "note": "bounded sample of the 100M-query batch per step; CPU only"},
-            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": kind,
-                             "sample": f"{sample} Q1 queries per step, {threads} std::threads over PHASH_MAP::get_freq (src/hash.hpp:123-140)"},
-            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": c2_config(args, max(1, args.gpus), meta["index_keys"]),
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "reference",
+                             "sample": f"{n_q} Q1 queries per step (the whole batch of one GPU of our arm), {threads} std::threads over "
+                                       f"PHASH_MAP::get_freq (src/hash.hpp:123-140); the rate of this one host does not depend on --gpus"},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": {"index": {"keys": meta["index_keys"], "hit_fraction": hits / n_q, **{k: meta[k] for k in meta if k.endswith("_s")},
+                                "built_by": meta.get("built_by")},
+                      "setup_s": setup_s, "data_generated_on": dev.type}}
     _emit(line)
 
 

@@ -239,3 +239,12 @@ def cpu_count_run(reads_np, threads, tmpdir):
     return None
 
 
+
+
+def _wrap_device_i64(torch, ptr, n, dev):
+    """torch view of a device buffer owned by libaindex_cuda (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device=dev)

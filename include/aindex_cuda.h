@@ -308,6 +308,12 @@ int aix_canonical23_count_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t l
 int aix_canonical23_result_dev(aix_ctx *ctx, const uint64_t **kmers_dev,
                                const uint32_t **counts_dev, uint64_t *n);
 
+/* the counting stage's output files (scripts/compute_aindex.py:140-200; jellyfish dump / kmer_counter format):
+ * dat_path = "KMER\tCOUNT\n" lines (input of the reference's compute_index, hash.cpp:696-701), keys_path = "KMER\n" lines
+ * (input of compute_mphf_seq); either may be NULL.  kmers / counts are HOST arrays (as returned by aix_canonical23_count). */
+int aix_write_dat(aix_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, const char *dat_path,
+                  const char *keys_path);
+
 /* ---- building blocks of the two builders above, exposed for tests and callers that hold keys in HBM ------- */
 /* stable LSD radix sort of n u64 keys on bits [begin_bit, end_bit) (hand-written, csrc/radix_sort.cu; replaces the
  * `sort` of scripts/compute_aindex.py:140-182 and the per-bucket ordering of the 1-thread worker, hash.cpp:1006-1051).

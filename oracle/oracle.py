@@ -376,6 +376,8 @@ def canonical23_count(reads, threads: int = 0):
     a = _bytes_arr(reads)
     kp, cp = C.c_void_p(), C.c_void_p()
     n = int(lib().orc_canonical23_count(_ptr(a), a.size, threads or (os.cpu_count() or 1), C.byref(kp), C.byref(cp)))
+    if not kp.value:  # image shorter than one window
+        return np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint32)
     try:
         kmers = np.ctypeslib.as_array(C.cast(kp, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
         counts = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint32)), shape=(max(n, 1),))[:n].copy()

@@ -14,6 +14,9 @@
 //       queries.bin = nq x 23 ASCII bytes; out.bin = nq x uint32; prints one "seconds=" line per rep
 //   ref_harness lookup13 <pf> <threads> <out.bin>
 //       mphf lookup of all 4^13 13-mers in numeric order -> uint32 perm
+//   ref_harness tf13 <pf> <tf.bin> <threads> <out.bin> <count> [reps]
+//       get_tf_value_13mer (python_wrapper.cpp:482-503: length / ACGT check, HASHER::lookup, tf gather,
+//       uint32 narrowing) of the 13-mers with 2-bit values 0 .. count-1 -> count x uint32
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -103,8 +106,55 @@ static int cmd_lookup13(int argc, char **argv) {
     return 0;
 }
 
+static int cmd_tf13(int argc, char **argv) {
+    if (argc < 7) return 2;
+    HASHER h;
+    {
+        std::ifstream is(argv[2], std::ios::binary);
+        if (!is) return 3;
+        h.load(is);
+    }
+    const uint64_t N = 1ull << 26;
+    std::vector<uint64_t> tf(N);
+    {
+        std::ifstream in(argv[3], std::ios::binary);
+        in.read((char *)tf.data(), (std::streamsize)(N * 8));
+        if ((uint64_t)in.gcount() != N * 8) { fprintf(stderr, "short tf file\n"); return 3; }
+    }
+    unsigned threads = (unsigned)atoi(argv[4]);
+    if (threads == 0) threads = 1;
+    uint64_t count = strtoull(argv[6], nullptr, 10);
+    if (count > N) count = N;
+    int reps = argc > 7 ? atoi(argv[7]) : 1;
+    std::vector<uint32_t> out(count);
+    for (int r = 0; r < reps; ++r) {
+        double t1 = now_s();
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < threads; ++t) {
+            th.emplace_back([&, t]() {
+                emphf::stl_string_adaptor ad;
+                std::string s(13, 'A');
+                for (uint64_t v = count * t / threads; v < count * (t + 1) / threads; ++v) {
+                    get_bitset_dna13((uint32_t)v, s, 13);
+                    bool ok = s.size() == 13;
+                    for (char c : s) ok = ok && (c == 'A' || c == 'C' || c == 'G' || c == 'T');
+                    uint64_t id = ok ? h.lookup(s, ad) : N;
+                    out[v] = id < N ? (uint32_t)tf[id] : 0u;
+                }
+            });
+        }
+        for (auto &x : th) x.join();
+        printf("seconds=%.6f queries=%llu threads=%u\n", now_s() - t1, (unsigned long long)count, threads);
+        fflush(stdout);
+    }
+    std::ofstream o(argv[5], std::ios::binary);
+    o.write((const char *)out.data(), (std::streamsize)(count * 4));
+    return 0;
+}
+
 int main(int argc, char **argv) {
-    if (argc < 2) { fprintf(stderr, "usage: ref_harness tf23|lookup13 ...\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: ref_harness tf23|lookup13|tf13 ...\n"); return 2; }
+    if (!strcmp(argv[1], "tf13")) return cmd_tf13(argc, argv);
     if (!strcmp(argv[1], "tf23")) return cmd_tf23(argc, argv);
     if (!strcmp(argv[1], "lookup13")) return cmd_lookup13(argc, argv);
     return 2;

@@ -4,7 +4,8 @@ the very inputs the headline numbers are measured on.
 
   C2  100 M random + 20 M half-hit 23-mer queries on the 50 M-key index
   C3  one GPU's shard of the 13-mer counting job: 25 M x 150 bp reads (3.45 G windows)
-  C4  coverage of 1 M x 10 kb sequences;  C5  positions index over 50 M reads (tests/bench_configs.py)
+  C4  coverage of 1 M x 10 kb sequences;  C5  positions index over 50 M reads (bench_configs.py)
+  C2' the same 50 M-key index built by the UNMODIFIED reference tools from the GPU-counted .dat
 """
 import os
 import sys
@@ -16,7 +17,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 @pytest.fixture(scope="module")
@@ -174,18 +174,98 @@ def test_c3_full_size_shard_properties(env):
             shutil.rmtree(tmp, ignore_errors=True)
 
 
+def test_c2_reference_built_index(env):
+    """north_star: "MPHF construction reuses the reference's emphf output, so index files are interchangeable".
+    The C2 table counted on the GPU is written as the reference's text files (aix_write_dat), the UNMODIFIED
+    compute_mphf_seq + compute_index build {pf, kmers.bin, tf.bin} from them (cached in /dev/shm, ~2-3 min once),
+    the files are loaded with aix_index23_load_prefix, and 100 M Q1 + 20 M Q2 answers must equal the GPU-built
+    index's; 3 M of them are compared with the reference's own get_freq on the reference-built files."""
+    import json
+    import shutil
+    import time
+    from oracle import oracle as O
+    t, capi, ctx, bench = env.torch, env.capi, env.ctx, env.bench
+    binp = os.path.join(ROOT, "oracle", "_ref", "bin")
+    if not (os.path.exists(os.path.join(binp, "compute_mphf_seq")) and os.path.exists(os.path.join(binp, "compute_index"))):
+        pytest.skip("reference tools not compiled under oracle/_ref")
+    reads = bench.make_reads(t, env.dev, 50_000_000, 10_000_000, 150, 1, 2)
+    mphf, index, checker_t, tf_t, n = bench.build_index(t, capi, ctx, reads)
+    cache = os.path.join(_tmp_root() or "/tmp", "aix_test_cache_c2_gpucounted")
+    prefix = os.path.join(cache, "c2.23")
+    if not os.path.exists(os.path.join(cache, "meta.json")):
+        os.makedirs(cache, exist_ok=True)
+        lib = capi.lib()
+        kmers, counts = ctx.canonical23_count(reads.cpu().numpy().reshape(-1))
+        # the GPU table equals the CPU definition (tests/analyze_kmers.py) on a 200 k-read slice, and its totals at full size
+        ok, oc = O.canonical23_count(reads[:200_000].cpu().numpy().reshape(-1))
+        gk, gc = ctx.canonical23_count(reads[:200_000].cpu().numpy().reshape(-1))
+        assert np.array_equal(ok, gk) and np.array_equal(oc, gc)
+        assert kmers.size == n and int(counts.sum()) == 10_000_000 * 128 and bool(np.all(kmers[1:] > kmers[:-1]))
+        t0 = time.perf_counter()
+        ctx.write_dat(kmers, counts, prefix + ".dat", prefix + ".kmers")
+        t1 = time.perf_counter()
+        import subprocess
+        subprocess.check_call([os.path.join(binp, "compute_mphf_seq"), prefix + ".kmers", prefix + ".pf"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t2 = time.perf_counter()
+        subprocess.check_call([os.path.join(binp, "compute_index"), prefix + ".dat", prefix + ".pf", prefix, str(os.cpu_count() or 1), "0"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t3 = time.perf_counter()
+        os.unlink(prefix + ".dat")
+        os.unlink(prefix + ".kmers")
+        with open(os.path.join(cache, "meta.json"), "w") as f:
+            json.dump({"index_keys": int(kmers.size), "write_dat_s": t1 - t0, "compute_mphf_seq_s": t2 - t1, "compute_index_s": t3 - t2}, f)
+        del kmers, counts
+    meta = json.load(open(os.path.join(cache, "meta.json")))
+    assert meta["index_keys"] == n
+    ref_ix = capi.Index23.load_prefix(ctx, prefix)
+    assert ref_ix.info["canonical_only"] is True and ref_ix.info["n"] == n
+    # the reference's tf / checker arrays are the GPU fill's, re-indexed by the other MPHF: same multiset of (kmer, tf)
+    rk = np.fromfile(prefix + ".kmers.bin", dtype=np.uint64)
+    rt = np.fromfile(prefix + ".tf.bin", dtype=np.uint32)
+    o1, o2 = np.argsort(rk), np.argsort(checker_t.cpu().numpy().view(np.uint64))
+    assert np.array_equal(rk[o1], checker_t.cpu().numpy().view(np.uint64)[o2]) and np.array_equal(rt[o1], tf_t.cpu().numpy().view(np.uint32)[o2])
+    del rk, rt, o1, o2
+    q2 = t.cat([bench.make_hit_queries(t, env.dev, reads, 10_000_000, 4), bench.make_queries(t, env.dev, 10_000_000, 5)])
+    del reads
+    t.cuda.empty_cache()
+    q1 = bench.make_queries(t, env.dev, 100_000_000, 3)
+    rates = {}
+    for name, q in (("q1", q1), ("q2", q2)):
+        nq = q.shape[0]
+        a, b = t.empty(nq, device=env.dev, dtype=t.int32), t.empty(nq, device=env.dev, dtype=t.int32)
+        index.query_dev(q.data_ptr(), 23, None, nq, capi.Q_TF, a.data_ptr())
+        ref_ix.query_dev(q.data_ptr(), 23, None, nq, capi.Q_TF, b.data_ptr())
+        ctx.sync()
+        assert t.equal(a, b), f"{name}: reference-built index answers differ from the GPU-built index's"
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record(env.stream)
+        for _ in range(5):
+            ref_ix.query_dev(q.data_ptr(), 23, None, nq, capi.Q_TF, b.data_ptr())
+        e1.record(env.stream)
+        ctx.sync()
+        rates[name] = nq / (e0.elapsed_time(e1) / 5 / 1e3)
+        if name == "q2":
+            assert bool((b[:10_000_000] > 0).all().item())
+    print(f"[reference-built C2 index] {n} keys, Q1 {rates['q1'] / 1e9:.1f} G q/s, Q2 {rates['q2'] / 1e9:.1f} G q/s; "
+          f"compute_mphf_seq {meta['compute_mphf_seq_s']:.0f} s, compute_index {meta['compute_index_s']:.0f} s")
+    mix = np.concatenate([q1[:1_000_000].cpu().numpy(), q2[:1_000_000].cpu().numpy(), q2[-1_000_000:].cpu().numpy()])
+    kind, secs, res = bench.cpu_query_runs(prefix, mix, os.cpu_count() or 1, 1)
+    assert kind == "reference" and np.array_equal(res, ref_ix.query(mix))
+
+
 @pytest.mark.parametrize("config", ["c4", "c5"])
 def test_c4_c5_full_size(env, config):
-    """tests/bench_configs.py at scale 1.0: every full-size property and every comparison with the
+    """bench_configs.py at scale 1.0: every full-size property and every comparison with the
     oracle / the compiled reference must hold (the timings it also takes are not asserted)."""
     import bench_configs
     env.torch.cuda.empty_cache()
-    args = types.SimpleNamespace(scale=1.0)
+    args = types.SimpleNamespace(scale=1.0, checks=True, e2e=True, cpu=True)
     line = {"c4": bench_configs.run_c4, "c5": bench_configs.run_c5}[config](env.ctx, env.stream, env.dev, args)
     assert all(line["checks"].values()), line["checks"]
     cb = line["cpu_baseline"]
     if cb is not None:
         assert all(v for k, v in cb.items() if k.endswith("equal") or k.startswith("results_equal") or "_equal" in k), cb
-    if "e2e" in line:
+    if line.get("e2e"):
         assert line["e2e"]["matches_device_path"]
     env.torch.cuda.empty_cache()

@@ -104,3 +104,19 @@ def test_positions_build_regimes_vs_oracle(capi, oracle, ctx, golden_dir, regime
         gi, gp = ix.positions_build(img)
         wi, wp = oix.positions_build(img)
         assert np.array_equal(gi, wi) and np.array_equal(gp, wp)
+
+
+def test_write_dat_equals_the_oracle_writer(capi, oracle, ctx, golden_dir, tmp_path):
+    """aix_canonical23_count + aix_write_dat = the counting stage's text output; byte-equal to the oracle's"""
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    k, c = ctx.canonical23_count(reads)
+    ok, oc = oracle.canonical23_count(reads)
+    assert np.array_equal(k, ok) and np.array_equal(c, oc)
+    c = c.copy()
+    c[:3] = [1, 4294967295, 1000000]  # every digit count
+    gd, gk, od, okp = (str(tmp_path / n) for n in ("g.dat", "g.kmers", "o.dat", "o.kmers"))
+    ctx.write_dat(k, c, gd, gk)
+    oracle.write_dat(k, c, od, okp)
+    assert open(gd, "rb").read() == open(od, "rb").read() and open(gk, "rb").read() == open(okp, "rb").read()
+    ctx.write_dat(k[:0], c[:0], gd, None)
+    assert os.path.getsize(gd) == 0

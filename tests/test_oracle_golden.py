@@ -186,3 +186,39 @@ def test_get_freq_matches_tf(oracle, idx23):
         u = int(idx23.checker[i])
         assert idx23.get_freq(u) == int(idx23.tf[i])
         assert idx23.get_freq(oracle.reverse_dna23(u)) == int(idx23.tf[i])
+
+
+def test_oracle_canonical23_table_matches_the_golden_index(oracle, golden_dir, tmp_path):
+    """orc_canonical23_count (rolling, threaded) against the table the golden index was built from: the brute-force
+    Python definition of tests/analyze_kmers.py (tests/golden/make_golden.py::canonical_counts) -> compute_index,
+    i.e. the reference-built .kmers.bin / .tf.bin hold exactly these (k-mer, count) pairs."""
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    checker = np.fromfile(os.path.join(golden_dir, "idx23.kmers.bin"), dtype=np.uint64)
+    tf = np.fromfile(os.path.join(golden_dir, "idx23.tf.bin"), dtype=np.uint32)
+    order = np.argsort(checker)
+    for threads in (1, 3, 8):
+        k, c = oracle.canonical23_count(reads, threads=threads)
+        assert np.array_equal(k, checker[order]) and np.array_equal(c, tf[order])
+    # windows broken by 'N', '~', lower case and line ends; inputs shorter than k
+    odd = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTA\nACGTNACGTACGTACGTACGTACGTACGTACG~TTTTTTTTTTTTTTTTTTTTTTTTa\nAC", dtype=np.uint8)
+    k, c = oracle.canonical23_count(odd, threads=2)
+    want = {}
+    b = odd.tobytes()
+    L = oracle.lib()
+    for i in range(len(b) - 22):
+        w = b[i:i + 23]
+        if w.strip(b"ACGT"):
+            continue
+        u = L.orc_dna23_bitset(w, 23)
+        m = min(u, L.orc_reverse_dna23(u))
+        want[m] = want.get(m, 0) + 1
+    assert dict(zip(k.tolist(), c.tolist())) == want
+    assert oracle.canonical23_count(b"ACGT")[0].size == 0
+    # the text files: "KMER\tCOUNT\n" / "KMER\n" in table order
+    dat, keys = str(tmp_path / "t.dat"), str(tmp_path / "t.kmers")
+    oracle.write_dat(k, c, dat, keys)
+    lines = open(dat, "rb").read().split(b"\n")[:-1]
+    assert len(lines) == k.size and open(keys, "rb").read() == b"".join(l.split(b"\t")[0] + b"\n" for l in lines)
+    for ln, kv, cv in zip(lines, k, c):
+        s, n = ln.split(b"\t")
+        assert L.orc_dna23_bitset(s, 23) == int(kv) and int(n) == int(cv) and len(s) == 23
