@@ -27,7 +27,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-ccbin", CXX, "--expt-relaxed-constexpr",
               "-diag-suppress", "177,550"] + os.environ.get("AIX_EXTRA_NVCC_FLAGS", "").split()
 CU_SOURCES = ["ctx.cu", "mphf.cu", "tf_query.cu", "count13.cu", "codec.cu", "coverage.cu",
-              "mphf_build.cu", "positions.cu", "radix_sort.cu"]
+              "mphf_build.cu", "positions.cu", "radix_sort.cu", "multi.cu"]
 
 
 def _newer(target: str, deps) -> bool:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "aix_ctx_stream": (_vp, [_vp]),
     "aix_ctx_sync": (_i, [_vp]),
     "aix_ctx_launch_count": (_u64, [_vp]),
+    "aix_ctx_trim": (_i, [_vp]),
     "aix_host_alloc": (_i, [_vp, C.c_size_t, _pp]),
     "aix_host_free": (_i, [_vp, _vp]),
     "aix_version": (C.c_char_p, []),
@@ -81,6 +82,8 @@ SIGNATURES = {
     "aix_probe23_dev": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "aix_probes_bucket_dev": (_i, [_vp, _vp, _u64, _vp, _i, _vp, _vp, _vp]),
     "aix_get_freq23": (_i, [_vp, _vp, _vp, _u64, _vp]),
+    "aix_get_freq23_packed": (_i, [_vp, _vp, _vp, _u64, _vp]),
+    "aix_get_freq23_packed_dev": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "aix_index13_upload": (_i, [_vp, _vp, _vp, _pp]),
     "aix_index13_destroy": (None, [_vp, _vp]),
     "aix_index13_tf_direct": (_i, [_vp, _vp, _vp]),
@@ -100,6 +103,14 @@ SIGNATURES = {
     "aix_count13_peers_open": (_i, [_vp, _vp, _i, _i]),
     "aix_count13_reduce_peers_dev": (_i, [_vp, _u64, _u64, _vp]),
     "aix_count13_peers_close": (_i, [_vp]),
+    "aix_multi_create": (_i, [_i, _vp, _pp]),
+    "aix_multi_destroy": (None, [_vp]),
+    "aix_multi_size": (_i, [_vp]),
+    "aix_multi_ctx": (_vp, [_vp, _i]),
+    "aix_multi_peer_access": (_i, [_vp]),
+    "aix_multi_last_error": (C.c_char_p, [_vp]),
+    "aix_count13_multi": (_i, [_vp, _vp, _vp, _u64, _i, _vp, C.POINTER(CountStats)]),
+    "aix_count13_multi_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(CountStats)]),
     "aix_coverage": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _u32, _vp]),
     "aix_coverage_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _u64, _i, _u32, _vp]),
     "aix_positions_total23": (_i, [_vp, _vp, _vp]),
@@ -210,6 +221,10 @@ class Context:
     def sync(self):
         self.check(lib().aix_ctx_sync(self._h))
 
+    def trim(self):
+        """return the memory the builders' pool has cached to the driver"""
+        self.check(lib().aix_ctx_trim(self._h))
+
     def pinned(self, shape, dtype) -> np.ndarray:
         """numpy array backed by cudaHostAlloc memory (freed when the array is collected)."""
         dtype = np.dtype(dtype)
@@ -286,6 +301,19 @@ class Context:
         counts = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
         self.check(lib().aix_write_dat(self._h, _p(kmers), _p(counts), kmers.size,
                                        os.fsencode(dat_path) if dat_path else None, os.fsencode(keys_path) if keys_path else None))
+
+
+def pack23(kmers) -> np.ndarray:
+    """uint8[q, 23] upper-case ACGT records -> uint8[q, 6] dna_bitset records (dna_bitseq.hpp:22-61: 4 bases per byte,
+    first base in bits 7:6, non-ACGT -> A; the last two bits are zero).  Host-side helper for the 6-byte query form."""
+    recs, _ = as_records(kmers, 23)
+    code = np.zeros(256, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = np.zeros((recs.shape[0], 24), dtype=np.uint8)
+    c[:, :23] = code[recs[:, :23]]
+    c = c.reshape(-1, 6, 4)
+    return ((c[:, :, 0] << 6) | (c[:, :, 1] << 4) | (c[:, :, 2] << 2) | c[:, :, 3]).astype(np.uint8)
 
 
 def _free_pinned(ptr):
@@ -456,6 +484,13 @@ class Index23:
         u = np.ascontiguousarray(ukmers, dtype=np.uint64)
         out = np.zeros(u.size, dtype=np.uint32)
         self.ctx.check(lib().aix_get_freq23(self.ctx.handle, self._h, _p(u), u.size, _p(out)))
+        return out
+
+    def get_freq_packed(self, packed6) -> np.ndarray:
+        """tf of 23-mers given as uint8[q, 6] dna_bitset records (pack23)"""
+        p6 = np.ascontiguousarray(packed6, dtype=np.uint8).reshape(-1, 6)
+        out = np.zeros(p6.shape[0], dtype=np.uint32)
+        self.ctx.check(lib().aix_get_freq23_packed(self.ctx.handle, self._h, _p(p6), p6.shape[0], _p(out)))
         return out
 
     def coverage(self, seqs, offs=None, cutoff: int = 0) -> np.ndarray:

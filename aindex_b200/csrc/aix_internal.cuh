@@ -55,6 +55,7 @@ struct aix_positions {
     uint64_t n_indices = 0, n_positions = 0;
     uint64_t *indices_dev = nullptr;
     uint64_t *positions_dev = nullptr;
+    bool pooled = false;  // arrays come from the ctx's memory pool (built on the device) rather than cudaMalloc (uploaded)
 };
 
 struct DevBuf {
@@ -71,6 +72,11 @@ struct aix_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     DevBuf scratch[8];                  // grow-only device scratch, indexed by role
+    // stream-ordered pool for the large, short-lived buffers of the builders (sort keys, status words, ...): freed
+    // blocks stay in the pool (release threshold = max), so a second build does not pay the driver's map / unmap of
+    // 100 GB again (measured: 50-700 ms per build with cudaMalloc / cudaFree, more while NVML is being polled).
+    // aix_ctx_trim() hands the cached memory back.
+    cudaMemPool_t pool = nullptr;
     void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
@@ -80,6 +86,7 @@ struct aix_ctx {
     bool c13_active = false;
     void *c13_peer[16][3] = {};         // IPC-mapped {hist32, hist64, stats} of every rank (own entries = own buffers)
     int c13_n_peers = 0, c13_my_rank = 0;
+    bool c13_peer_ipc = true;           // false: the table holds plain device pointers of other ctxs of this process (multi.cu)
     aix_count_stats c13_range_invalid = {0, 0, 0, 0};
     // canonical23 result kept between the two passes
     uint64_t *c23_kmers_dev = nullptr;
@@ -118,6 +125,20 @@ struct aix_ctx {
         return AIX_OK;
     }
 };
+
+static inline cudaError_t aix_pool_alloc(aix_ctx *ctx, void **p, size_t bytes, cudaStream_t st) {
+    if (!ctx->pool) return cudaMalloc(p, bytes ? bytes : 1);
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, st);
+}
+template <typename T>
+static inline cudaError_t aix_pool_alloc(aix_ctx *ctx, T **p, size_t bytes, cudaStream_t st) {
+    return aix_pool_alloc(ctx, (void **)p, bytes, st);
+}
+static inline void aix_pool_free(aix_ctx *ctx, void *p, cudaStream_t st) {
+    if (!p) return;
+    if (ctx && ctx->pool) cudaFreeAsync(p, st);
+    else cudaFree(p);
+}
 
 #define AIX_CUDA(ctx, call)                                                                      \
     do {                                                                                         \

@@ -926,13 +926,14 @@ int aix_count13_ipc_export(aix_ctx *ctx, void *handles_out) {
 int aix_count13_peers_close(aix_ctx *ctx) {
     if (!ctx) return AIX_ERR_ARG;
     cudaSetDevice(ctx->device);
-    for (int p = 0; p < ctx->c13_n_peers; ++p) {
+    for (int p = 0; p < ctx->c13_n_peers && ctx->c13_peer_ipc; ++p) {
         if (p == ctx->c13_my_rank) continue;
         for (int k = 0; k < 3; ++k)
             if (ctx->c13_peer[p][k]) cudaIpcCloseMemHandle(ctx->c13_peer[p][k]);
     }
     memset(ctx->c13_peer, 0, sizeof ctx->c13_peer);
     ctx->c13_n_peers = 0;
+    ctx->c13_peer_ipc = true;
     return AIX_OK;
 }
 

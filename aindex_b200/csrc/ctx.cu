@@ -39,6 +39,20 @@ int aix_ctx_create(int device, aix_ctx **out) {
         delete ctx;
         return AIX_ERR_CUDA;
     }
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+            uint64_t keep = ~0ULL;
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+            ctx->pool = nullptr;  // builders fall back to cudaMalloc / cudaFree
+        }
+    }
     for (auto &ev : ctx->ev) {
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
             g_create_error = "cudaEventCreate failed";
@@ -65,6 +79,7 @@ void aix_ctx_destroy(aix_ctx *ctx) {
     if (ctx->c23_counts_dev) cudaFree(ctx->c23_counts_dev);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->xfer[0]) cudaStreamDestroy(ctx->xfer[0]);
     if (ctx->xfer[1]) cudaStreamDestroy(ctx->xfer[1]);
@@ -82,6 +97,14 @@ int aix_ctx_sync(aix_ctx *ctx) {
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[0]));
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->xfer[1]));
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AIX_OK;
+}
+
+int aix_ctx_trim(aix_ctx *ctx) {
+    if (!ctx) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pool) AIX_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
     return AIX_OK;
 }
 

@@ -307,13 +307,14 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
     unsigned long long *indices = nullptr, *positions = nullptr, *tiles = nullptr, *emit_scratch = nullptr, *run_start = nullptr;
     uint64_t *keys = nullptr, *alt = nullptr;
     auto cleanup_tmp = [&]() {
-        cudaFree(tiles); cudaFree(emit_scratch); cudaFree(run_start); cudaFree(keys); cudaFree(alt);
+        aix_pool_free(ctx, tiles, st); aix_pool_free(ctx, emit_scratch, st); aix_pool_free(ctx, run_start, st);
+        aix_pool_free(ctx, keys, st); aix_pool_free(ctx, alt, st);
         tiles = emit_scratch = run_start = nullptr;
         keys = alt = nullptr;
     };
     auto cleanup = [&]() {
         cleanup_tmp();
-        cudaFree(indices); cudaFree(positions);
+        aix_pool_free(ctx, indices, st); aix_pool_free(ctx, positions, st);
     };
 #define PB_CUDA(call)                                                                                   \
     do {                                                                                                \
@@ -326,8 +327,8 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         }                                                                                               \
     } while (0)
     AixTrace trace(st, "positions build");
-    PB_CUDA(cudaMalloc(&indices, (n + 1) * 8));
-    PB_CUDA(cudaMalloc(&tiles, scan_scratch_bytes(n)));
+    PB_CUDA(aix_pool_alloc(ctx, &indices, (n + 1) * 8, st));
+    PB_CUDA(aix_pool_alloc(ctx, &tiles, scan_scratch_bytes(n), st));
     int rc = exclusive_scan(ctx, st, tf, n, indices, tiles);
     if (rc != AIX_OK) { cleanup(); return rc; }
     unsigned long long total = 0;
@@ -337,7 +338,7 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
     const uint64_t n_win_end = len >= (uint64_t)K ? len - K + 1 : 0;
     const bool any_window = n && total && start < n_win_end;
     if (!any_window) {
-        PB_CUDA(cudaMalloc(&positions, (total ? total : 1) * 8));
+        PB_CUDA(aix_pool_alloc(ctx, &positions, (total ? total : 1) * 8, st));
         PB_CUDA(cudaMemsetAsync(positions, 0, (total ? total : 1) * 8, st));
         PB_CUDA(cudaStreamSynchronize(st));
     } else {
@@ -351,12 +352,12 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         const uint64_t e_tiles = (n_win + kEmitTile - 1) / kEmitTile;
         if (e_tiles >= (1ull << 31)) { cleanup(); return ctx->fail(AIX_ERR_ARG, "positions build: reads image too large"); }
         // emit scratch: [0] n_valid, [1] tile counter, [2] bad flag, [8 ...] one look-back word per tile
-        PB_CUDA(cudaMalloc(&emit_scratch, (8 + e_tiles) * 8));
+        PB_CUDA(aix_pool_alloc(ctx, &emit_scratch, (8 + e_tiles) * 8, st));
         unsigned long long n_valid = 0;
         uint64_t cap = total;  // the normal case needs exactly `total` keys; more valid windows than that = general case
         for (int attempt = 0; attempt < 2; ++attempt) {
-            PB_CUDA(cudaMalloc(&keys, cap * 8));
-            PB_CUDA(cudaMalloc(&alt, cap * 8));
+            PB_CUDA(aix_pool_alloc(ctx, &keys, cap * 8, st));
+            PB_CUDA(aix_pool_alloc(ctx, &alt, cap * 8, st));
             PB_CUDA(cudaMemsetAsync(emit_scratch, 0, (8 + e_tiles) * 8, st));
             positions_emit_kernel<K><<<(unsigned)e_tiles, kEmitThreads, 0, st>>>(id, md, reads_dev, start, n_win_end, pos_bits, keys, cap,
                                                                                 emit_scratch + 8, (unsigned int *)(emit_scratch + 1), emit_scratch);
@@ -367,7 +368,7 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
             if (n_valid <= cap) break;
             // more occurrences in the reads than the index's tf sums to (index counted on other reads): all of them
             // must be ordered before the first tf of every bucket can be picked -- emit again with room for all
-            cudaFree(keys); cudaFree(alt);
+            aix_pool_free(ctx, keys, st); aix_pool_free(ctx, alt, st);
             keys = alt = nullptr;
             cap = n_valid;
         }
@@ -389,16 +390,16 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
         }
         if (!bad) {  // every bucket exactly full: the low words of the sorted keys are positions[]
             positions = (unsigned long long *)spare;
-            cudaFree(sorted);
+            aix_pool_free(ctx, sorted, st);
             keys = alt = nullptr;
             trace.mark("check + low words -> positions[] (one pass, out of place)");
         } else {
-            cudaFree(spare);
+            aix_pool_free(ctx, spare, st);
             if (sorted == keys) alt = nullptr; else keys = nullptr;
-            PB_CUDA(cudaMalloc(&positions, total * 8));
+            PB_CUDA(aix_pool_alloc(ctx, &positions, total * 8, st));
             PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
             if (n_valid) {
-                PB_CUDA(cudaMalloc(&run_start, n * 8));
+                PB_CUDA(aix_pool_alloc(ctx, &run_start, n * 8, st));
                 positions_run_start_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, run_start);
                 positions_clip_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(tf, sorted, n_valid, pos_bits, run_start, indices, positions);
                 ctx->launches += 2;
@@ -438,8 +439,8 @@ static int build_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
     e = cudaMemcpyAsync(indices_out, indices, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && total) e = cudaMemcpyAsync(positions_out, positions, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(indices);
-    cudaFree(positions);
+    aix_pool_free(ctx, indices, ctx->stream);
+    aix_pool_free(ctx, positions, ctx->stream);
     if (e != cudaSuccess) return ctx->fail(AIX_ERR_CUDA, "positions build: download: %s", cudaGetErrorString(e));
     return AIX_OK;
 }
@@ -473,6 +474,7 @@ static int build_dev_impl(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_
     uint64_t total = 0;
     AIX_TRY((build_core<K>(ctx, id, md, tf, n, reads_dev, len, start, &indices, &positions, &total)));
     aix_positions *p = new aix_positions();
+    p->pooled = true;
     p->n_indices = n + 1;
     p->n_positions = total;
     p->indices_dev = (uint64_t *)indices;
@@ -601,8 +603,13 @@ int aix_positions_upload(aix_ctx *ctx, const uint64_t *indices, uint64_t n_indic
 void aix_positions_destroy(aix_ctx *ctx, aix_positions *p) {
     if (!p) return;
     if (ctx) cudaSetDevice(ctx->device);
-    if (p->indices_dev) cudaFree(p->indices_dev);
-    if (p->positions_dev) cudaFree(p->positions_dev);
+    if (p->pooled && ctx) {
+        aix_pool_free(ctx, p->indices_dev, ctx->stream);
+        aix_pool_free(ctx, p->positions_dev, ctx->stream);
+    } else {
+        if (p->indices_dev) cudaFree(p->indices_dev);  // cudaFree also takes pool memory (it synchronises first)
+        if (p->positions_dev) cudaFree(p->positions_dev);
+    }
     delete p;
 }
 

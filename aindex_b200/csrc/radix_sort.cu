@@ -268,7 +268,7 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     const size_t front = (size_t)kRsMaxPasses * kRsMaxRadix * 8 * 2 + 64;
     const size_t status_bytes = (size_t)tiles * ((size_t)1 << plan.bits) * 8;
     unsigned char *scratch = nullptr;
-    cudaError_t e = cudaMalloc(&scratch, front + status_bytes);
+    cudaError_t e = aix_pool_alloc(ctx, &scratch, front + status_bytes, st);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return ctx->fail(AIX_ERR_NOMEM, "radix sort scratch (%zu bytes): %s", front + status_bytes, cudaGetErrorString(e));
@@ -279,7 +279,7 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     unsigned long long *status = (unsigned long long *)(scratch + front);
     auto fail = [&](cudaError_t err, const char *what) {
         cudaGetLastError();
-        cudaFree(scratch);
+        aix_pool_free(ctx, scratch, st);
         return ctx->fail(AIX_ERR_CUDA, "radix sort %s: %s", what, cudaGetErrorString(err));
     };
     if ((e = cudaMemsetAsync(scratch, 0, front, st)) != cudaSuccess) return fail(e, "memset");
@@ -306,8 +306,8 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
         uint64_t *t = src; src = dst; dst = t;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "launch");
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "run");
-    cudaFree(scratch);
+    aix_pool_free(ctx, scratch, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return ctx->fail(AIX_ERR_CUDA, "radix sort run: %s", cudaGetErrorString(e));
     trace.mark("free scratch");
     *sorted = src;
     return AIX_OK;
@@ -321,11 +321,11 @@ int rle_u64(aix_ctx *ctx, cudaStream_t st, const uint64_t *sorted, uint64_t n, u
     unsigned long long *tile_off = nullptr, *starts = nullptr;
     auto fail = [&](cudaError_t err, const char *what) {
         cudaGetLastError();
-        cudaFree(tile_off);
-        cudaFree(starts);
+        aix_pool_free(ctx, tile_off, st);
+        aix_pool_free(ctx, starts, st);
         return ctx->fail(err == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA, "run-length %s: %s", what, cudaGetErrorString(err));
     };
-    cudaError_t e = cudaMalloc(&tile_off, scan_scratch_bytes(n));
+    cudaError_t e = aix_pool_alloc(ctx, &tile_off, scan_scratch_bytes(n), st);
     if (e != cudaSuccess) return fail(e, "scratch");
     scan_reduce_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(HeadFlag{sorted}, n, tile_off);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_off, tiles);
@@ -333,14 +333,14 @@ int rle_u64(aix_ctx *ctx, cudaStream_t st, const uint64_t *sorted, uint64_t n, u
     unsigned long long n_runs = 0;
     if ((e = cudaMemcpyAsync(&n_runs, tile_off + tiles, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "copy");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "count");
-    if ((e = cudaMalloc(&starts, (n_runs + 1) * 8)) != cudaSuccess) return fail(e, "starts");
+    if ((e = aix_pool_alloc(ctx, &starts, (n_runs + 1) * 8, st)) != cudaSuccess) return fail(e, "starts");
     rle_heads_kernel<<<(unsigned)tiles, kScanBlock, 0, st>>>(sorted, n, tile_off, uniq, starts);
     rle_counts_kernel<<<aix_grid(n_runs, 256), 256, 0, st>>>(starts, n_runs, n, counts);
     ctx->launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "launch");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "run");
-    cudaFree(tile_off);
-    cudaFree(starts);
+    aix_pool_free(ctx, tile_off, st);
+    aix_pool_free(ctx, starts, st);
     *n_runs_out = n_runs;
     return AIX_OK;
 }

@@ -169,6 +169,36 @@ __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(
     }
 }
 
+// get_freq for 23-mers held as 6-byte dna_bitset records (dna_bitseq.hpp:22-61: 4 bases per byte, first base in
+// bits 7:6; 23 bases = 46 bits + 2 zero bits): the smallest form a query batch can cross PCIe in (6 B instead of 23).
+// The 46-bit value is get_dna23_bitset of the string, so this is PHASH_MAP::get_freq(uint64_t) (hash.hpp:123-140).
+template <bool kCanon>
+__global__ void __launch_bounds__(256) get_freq23_packed6_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ packed,
+                                                               uint64_t q, uint32_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const uint16_t *p = reinterpret_cast<const uint16_t *>(packed + i * 6);  // 6 i is even: 2-byte aligned
+    const uint32_t h0 = __ldcs(p), h1 = __ldcs(p + 1), h2 = __ldcs(p + 2);
+    // big-endian 48-bit number >> 2
+    const uint64_t be = ((uint64_t)__byte_perm(h0, 0, 0x3301) << 32) | ((uint64_t)__byte_perm(h1, 0, 0x3301) << 16) |
+                        (uint64_t)__byte_perm(h2, 0, 0x3301);
+    const uint64_t u = be >> 2, r = revcomp23(u);
+    uint32_t res = 0, tf;
+    if (kCanon) {
+        const bool fwd = u <= r;
+        const uint64_t h = mphf_lookup23(m, fwd ? r : u);  // hashes the ASCII string of min(u, r)
+        if (probe23(ix, h, fwd ? u : r, tf)) res = tf;
+    } else {
+        const uint64_t ha = mphf_lookup23(m, r);
+        if (probe23(ix, ha, u, tf)) res = tf;
+        else {
+            const uint64_t hb = mphf_lookup23(m, u);
+            if (probe23(ix, hb, r, tf)) res = tf;
+        }
+    }
+    __stcs(out + i, res);
+}
+
 // K3, generic records (any stride, per-record lengths)
 template <int kMode, bool kCanon>
 __global__ void __launch_bounds__(kQBlock) tf23_generic_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
@@ -853,6 +883,31 @@ int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, 
                                   AIX_LAUNCH_CHECK(ctx);
                                   return AIX_OK;
                               });
+}
+
+static int launch_packed6(aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *r, uint64_t nq, void *o) {
+    Index23Dev id = ix->dev();
+    MphfDev md = ix->mphf->dev();
+    if (ix->canonical_only) get_freq23_packed6_kernel<true><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, r, nq, (uint32_t *)o);
+    else get_freq23_packed6_kernel<false><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, r, nq, (uint32_t *)o);
+    AIX_LAUNCH_CHECK(ctx);
+    return AIX_OK;
+}
+
+int aix_get_freq23_packed(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *packed, uint64_t q, uint32_t *out) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    return run_record_batches(ctx, packed, 6, nullptr, q, out, 4,
+                              [&](cudaStream_t st, const uint8_t *r, const uint8_t *, uint64_t nq, void *o) {
+                                  return launch_packed6(ctx, ix, st, r, nq, o);
+                              });
+}
+
+int aix_get_freq23_packed_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *packed_dev, uint64_t q, uint32_t *out_dev) {
+    if (!ctx || !ix) return AIX_ERR_ARG;
+    if (q == 0) return AIX_OK;
+    if (!packed_dev || !out_dev) return ctx->fail(AIX_ERR_ARG, "null buffer");
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_packed6(ctx, ix, ctx->stream, packed_dev, q, out_dev);
 }
 
 int aix_index13_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *tf64, aix_index13 **out) {

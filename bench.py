@@ -330,7 +330,7 @@ def run_ours(args):
     # clocks are sampled from before the warm-up until the last timed region (tf23 device pass,
     # e2e, 13-mer counting) has ended
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("AIX_BENCH_NO_SAMPLER"):  # (diagnosis only: a run without the sampler has no clocks record)
         sampler.start()
         time.sleep(0.3)
     for _ in range(max(args.warmup, 3)):
@@ -411,10 +411,48 @@ def run_ours(args):
         e2e_packed = {"value": world * args.queries / p_s, "unit": "queries/s", "ms_per_step": p_s * 1e3,
                       "h2d_bytes_per_step": int(args.queries * 8 * world), "d2h_bytes_per_step": int(args.queries * 4 * world),
                       "api": "aix_get_freq23 (packed uint64 k-mers)", "matches_string_path": bool(np.array_equal(po, o_host))}
-        del pk, po
+        del pk
+        # the 6-byte dna_bitset record form (aix_get_freq23_packed): 6 B per query over PCIe
+        p6 = ctx.pinned((args.queries, 6), np.uint8)
+        for s0 in range(0, args.queries, 20_000_000):
+            s1 = min(args.queries, s0 + 20_000_000)
+            c = torch.zeros((s1 - s0, 24), device=dev, dtype=torch.uint8)
+            c[:, :23] = code[q_dev[s0:s1].long()].to(torch.uint8)
+            c = c.reshape(-1, 6, 4)
+            torch.from_numpy(p6[s0:s1]).copy_((c[:, :, 0] << 6) | (c[:, :, 1] << 4) | (c[:, :, 2] << 2) | c[:, :, 3])
+            del c
+        torch.cuda.synchronize()
+        ctx.check(lib.aix_get_freq23_packed(ctx.handle, index._h, p6.ctypes.data, args.queries, po.ctypes.data))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.check(lib.aix_get_freq23_packed(ctx.handle, index._h, p6.ctypes.data, args.queries, po.ctypes.data))
+        barrier()
+        p6_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        e2e_packed6 = {"value": world * args.queries / p6_s, "unit": "queries/s", "ms_per_step": p6_s * 1e3,
+                       "h2d_bytes_per_step": int(args.queries * 6 * world), "d2h_bytes_per_step": int(args.queries * 4 * world),
+                       "api": "aix_get_freq23_packed (6-byte dna_bitset records)", "matches_string_path": bool(np.array_equal(po, o_host))}
+        # what the bus can do: one pinned host -> device copy of the query buffer, timed alone (per rank, then summed)
+        stage = torch.empty(args.queries * 23, device=dev, dtype=torch.uint8)
+        hq = torch.from_numpy(q_host.reshape(-1))
+        stage.copy_(hq, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        stage.copy_(hq, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_s = max_over_ranks(time.perf_counter() - t0)
+        h2d_peak = world * args.queries * 23 / h2d_s / 1e9
+        for blk in (e2e, e2e_packed, e2e_packed6):
+            gbs = (blk["h2d_bytes_per_step"] + blk["d2h_bytes_per_step"]) / (blk["ms_per_step"] / 1e3) / 1e9
+            blk["pcie"] = {"h2d_plus_d2h_gbs": gbs, "pinned_h2d_copy_peak_gbs": h2d_peak, "utilisation_vs_h2d_peak": gbs / h2d_peak,
+                           "note": "both directions are counted against a one-direction copy peak (full duplex): > 1 is possible; "
+                                   "the e2e rate is a bus number, the kernel takes 1.75 ms of the step"}
+        del p6, po, stage, hq
     else:
         q_host = None
         e2e_packed = None
+        e2e_packed6 = None
 
     # ---- parity legs that need the queries still in HBM (untimed except where a value is reported) ---------
     ref_built = reference_built_index_check(torch, capi, ctx, stream, args, q_dev, out_dev, n_keys) if rank == 0 else None
@@ -447,7 +485,7 @@ def run_ours(args):
     # ---- 13-mer counting (second half of the metric), per-GPU shard of C3 -------------------------
     extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries,
                        "canonical_only": index.info["canonical_only"]},
-             "tf23_q2_half_hits": q2, "tf23_packed_e2e": e2e_packed, "setup_s": setup_s,
+             "tf23_q2_half_hits": q2, "tf23_packed_e2e": e2e_packed, "tf23_packed6_e2e": e2e_packed6, "setup_s": setup_s,
              "reference_built_index": ref_built, "sharded_index23": sharded}
     creads = None
     if args.count_reads > 0:

@@ -116,7 +116,9 @@ def build_index(torch, capi, ctx, reads):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md: -lms 200).  A faster poll
+    contends with the driver for its lock: at -lms 50 the cudaMalloc / cudaFree of the 100 GB the positions build
+    uses took up to 10x longer (profiles/r02_c5_trace.txt)."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -132,7 +134,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="aix_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

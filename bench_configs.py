@@ -399,6 +399,7 @@ def run_c5(ctx, stream, dev, args=None):
     del pout, counts, offs, win, j
     pos.close()
     del indices, positions
+    ctx.trim()  # the builders' pool keeps ~100 GB of freed blocks for the next build: hand them back before torch needs HBM
     torch.cuda.empty_cache()
 
     # ---- the reference compute_aindex on a read subsample with its own index (1 thread = parity order), and the
@@ -461,6 +462,7 @@ def run_c5(ctx, stream, dev, args=None):
                "matches_device_path": bool(np.array_equal(i_host, di) and np.array_equal(p_host, dp))}
         del r_host, i_host, p_host
     del reads, sub_t
+    ctx.trim()
     return {"config": "C5", "workload": f"positions index over {n_reads} x 150 bp reads ({n_keys} keys, {total_occ} occurrences) + {nq} position queries",
             "metric": "positions-index occurrences/s", "value": total_occ / (build_ms / 1e3), "unit": "occurrences/s",
             "ms_per_step": build_ms, "build_wall_s": build_wall, "index_build_s": index_s,

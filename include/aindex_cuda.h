@@ -59,6 +59,10 @@ int aix_ctx_device(const aix_ctx *ctx);
 /* the CUDA stream (cudaStream_t) the *_dev entry points launch on */
 void *aix_ctx_stream(const aix_ctx *ctx);
 int aix_ctx_sync(aix_ctx *ctx);
+/* The builders (positions index, canonical table, sort) take their large temporaries from a per-ctx CUDA memory pool that
+ * keeps freed blocks for the next call; aix_ctx_trim returns the cached memory to the driver (e.g. before another
+ * library needs the HBM). */
+int aix_ctx_trim(aix_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t aix_ctx_launch_count(const aix_ctx *ctx);
 /* pinned host memory for the e2e paths */
@@ -176,6 +180,12 @@ int aix_probes_bucket_dev(aix_ctx *ctx, const uint64_t *probes_dev, uint64_t n_p
 int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q,
                    uint32_t *out);
 
+/* the same for k-mers held as 6-byte dna_bitset records (dna_bitseq.hpp:22-61: 4 bases per byte, first base in bits 7:6,
+ * 23 bases + 2 zero bits; aix_pack_2bit of the 23 characters): 6 B per query over PCIe instead of 23 */
+int aix_get_freq23_packed(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *packed, uint64_t q, uint32_t *out);
+int aix_get_freq23_packed_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *packed_dev, uint64_t q,
+                              uint32_t *out_dev);
+
 /* ---- 13-mer index: AindexWrapper 13-mer mode ----------------------------------- */
 /* load_13mer_index (python_wrapper.cpp:404-437): tf64 = the 4^13 x u64 .tf.bin */
 int aix_index13_upload(aix_ctx *ctx, const aix_mphf *m, const uint64_t *tf64, aix_index13 **out);
@@ -237,6 +247,31 @@ int aix_count13_peers_open(aix_ctx *ctx, const void *handles /* n_ranks x 192 by
                            int my_rank);
 int aix_count13_reduce_peers_dev(aix_ctx *ctx, uint64_t v_begin, uint64_t v_end, uint64_t *out_dev);
 int aix_count13_peers_close(aix_ctx *ctx);
+
+/* ---- several GPUs of one box from one process (host code stays C++: no torch, no NCCL) ------------------------ */
+/* Kmer13Counter::count_kmers_from_file (count_kmers13.cpp:277-353) spawns num_threads workers over one table
+ * (:305-309); aix_multi maps the workers to GPUs: one ctx + one host thread per GPU, peer access between all pairs.
+ * n_dev <= 0 = every visible GPU; dev_ids == NULL = devices 0 .. n_dev-1. */
+typedef struct aix_multi aix_multi;
+int aix_multi_create(int n_dev, const int *dev_ids, aix_multi **out);
+void aix_multi_destroy(aix_multi *mg);
+int aix_multi_size(const aix_multi *mg);
+aix_ctx *aix_multi_ctx(aix_multi *mg, int i);
+/* 1 when every pair of the GPUs has peer access (the exchange step then runs as one kernel per GPU over NVLink peer
+ * pointers), 0 when ranges are moved with cudaMemcpyPeer instead */
+int aix_multi_peer_access(const aix_multi *mg);
+const char *aix_multi_last_error(const aix_multi *mg);
+/* aix_count13 over all GPUs of mg: the file image is cut at record boundaries (one shard per GPU), every GPU counts
+ * its shard into its own direct-address histogram, GPU r sums k-mer range r over all GPUs (the reduce-scatter of
+ * SURVEY 8(e)) and permutes it into .tf.bin order; tf_out / stats as aix_count13.  m = an MPHF uploaded on any ctx
+ * (its host arrays are re-uploaded to every GPU).  The number of GPUs must divide 4^13 (1, 2, 4, 8, 16). */
+int aix_count13_multi(aix_multi *mg, const aix_mphf *m, const uint8_t *bytes, uint64_t len, int fmt, uint64_t *tf_out,
+                      aix_count_stats *stats);
+/* the same with one shard per GPU already resident in that GPU's HBM (shards_dev[r] on the device of aix_multi_ctx(mg, r),
+ * each starting at a record start; fmt explicit).  tf_out == NULL stops after the exchange step: GPU r then holds the
+ * summed k-mer range r in aix_count13_hist_dev(aix_multi_ctx(mg, r)) -- the state an NCCL reduce-scatter leaves. */
+int aix_count13_multi_dev(aix_multi *mg, const aix_mphf *m, const uint8_t *const *shards_dev, const uint64_t *lens, int fmt,
+                          uint64_t *tf_out, aix_count_stats *stats);
 
 /* ---- coverage: aindex/core/aindex.py:314-322 ------------------------------------- */
 /* n_seq sequences concatenated in `seqs`, sequence s = seqs[offs[s] .. offs[s+1]).

@@ -640,6 +640,37 @@ def test_positions23_overflow_and_underflow(capi, oracle, ctx, oidx23, golden_di
     assert np.array_equal(indices, oi) and np.array_equal(positions, op)
 
 
+def test_get_freq_packed6_equals_string_path(capi, oracle, ctx, idx23, oidx23):
+    """the 6-byte dna_bitset record form (aix_get_freq23_packed): same answers as the 23-byte string path and as
+    PHASH_MAP::get_freq(uint64_t) restated in the oracle; record layout = aix_pack_2bit of the 23 characters"""
+    rng = np.random.default_rng(77)
+    n = 300_001  # not a multiple of the block size
+    km = ctx.decode(oidx23.checker[rng.integers(0, oidx23.n, size=n)], 23)
+    km[::3] = rng.choice(ACGT, size=(len(km[::3]), 23))
+    flip = rng.random(n) < 0.5
+    km[flip] = ctx.decode(ctx.revcomp(ctx.encode(km[flip], 23), 23), 23)
+    p6 = capi.pack23(km)
+    assert p6.shape == (n, 6)
+    for i in (0, 1, 77):
+        assert np.array_equal(p6[i], ctx.pack_2bit(km[i]))  # dna_bitset ctor layout
+    got = idx23.get_freq_packed(p6)
+    assert np.array_equal(got, idx23.query(km))
+    u = ctx.encode(km, 23)
+    assert np.array_equal(got[:4000], np.array([oidx23.get_freq(int(x)) for x in u[:4000]], dtype=np.uint32))
+    assert (got > 0).sum() > n // 2
+    assert idx23.get_freq_packed(p6[:0]).size == 0
+    # a non-canonical index takes the two-probe order
+    sel = np.arange(0, oidx23.n, 2)
+    chk = oidx23.checker.copy()
+    chk[sel] = ctx.revcomp(chk[sel], 23)
+    m = capi.Mphf.from_arrays(ctx, oidx23.mphf.n, oidx23.mphf.hash_domain, oidx23.mphf.seed, oidx23.mphf.words, oidx23.mphf.block_ranks)
+    ix2 = capi.Index23.upload(ctx, m, chk, oidx23.tf)
+    assert not ix2.info["canonical_only"]
+    o2 = oracle.Index23(oidx23.mphf, chk, oidx23.tf)
+    assert np.array_equal(ix2.get_freq_packed(p6[:4000]), np.array([o2.get_freq(int(x)) for x in u[:4000]], dtype=np.uint32))
+    assert np.array_equal(ix2.get_freq_packed(p6), ix2.get_freq(u))
+
+
 # ---------------------------------------------------------------------------- size-independent properties
 def test_large_batch_properties(capi, ctx, idx23, oidx23):
     """2 M queries through the chunked host pipeline: revcomp invariance, total == 2 x tf,
