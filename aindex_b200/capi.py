@@ -465,7 +465,8 @@ class Index23:
     def layout(self):
         a = np.zeros(4, dtype=np.uint64)
         self.ctx.check(lib().aix_index23_layout(self._h, _p(a)))
-        return {"fp_bits": int(a[0]), "fp_bytes": int(a[1]), "mphf_bytes": int(a[2]), "mphf_compact": bool(a[3])}
+        return {"fp_bits": int(a[0]), "fp_bytes": int(a[1]), "mphf_bytes": int(a[2]), "mphf_compact": int(a[3]) >= 1,
+                "records": ("wide", "compact", "fused")[int(a[3])]}
 
     def query(self, kmers, mode: int = Q_TF, out: Optional[np.ndarray] = None) -> np.ndarray:
         recs, lens = as_records(kmers)

@@ -27,6 +27,7 @@ struct aix_mphf {
         d.magic = hash_domain > 1 ? (uint64_t)((((unsigned __int128)1) << 64) / hash_domain) : ~0ULL;
         d.recs = recs_dev;
         d.crecs = crecs_dev;
+        d.frecs = nullptr;
         return d;
     }
 };
@@ -38,6 +39,14 @@ struct aix_index23 {
     uint4 *recs_dev = nullptr;  // {checker lo, checker hi, tf, 0}
     uint8_t *fp_dev = nullptr;  // fingerprint tier (may be null)
     int fp_bits = 0;            // 8 or 4 when fp_dev is set
+    uint4 *frecs_dev = nullptr; // fused MPHF + 4-bit fingerprint records (device_common.cuh); replaces the tier when set
+    uint64_t frecs_bytes = 0;
+    // the MPHF as this index's kernels see it: the fused records when they exist
+    aix::MphfDev mphf_dev() const {
+        aix::MphfDev d = mphf->dev();
+        d.frecs = frecs_dev;
+        return d;
+    }
     aix::Index23Dev dev() const {
         aix::Index23Dev d;
         d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev; d.fp = fp_dev; d.fp_bits = fp_bits;

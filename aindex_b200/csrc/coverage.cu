@@ -151,7 +151,7 @@ static int coverage_on(aix_ctx *ctx, cudaStream_t st, int slot, const aix_index2
     MphfDev md = {};
     if (k == 23) {
         id = ix23->dev();
-        md = ix23->mphf->dev();
+        md = ix23->mphf_dev();
         // coverage is hit-dominated (sequences of the indexed organism): the fingerprint tier would add a
         // dependent L2 round trip in front of nearly every HBM record load.  AIX_COVERAGE_TIER=1 keeps it.
         const char *e = getenv("AIX_COVERAGE_TIER");

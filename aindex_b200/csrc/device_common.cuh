@@ -31,7 +31,16 @@ struct MphfDev {
     uint64_t magic;     // floor(2^64 / hash_domain)
     const ulonglong2 *recs;  // wide:    recs[w] = { words[w], rank of pair 32*w }
     const uint4 *crecs;      // compact: crecs[r] = { pairs 48r..48r+47 (96 bits), rank of pair 48*r }; nullptr = wide
+    // fused (owned by an aix_index23, nullptr otherwise): frecs[r] = { pairs 16r..16r+15 (32 bits), 16 x 4-bit
+    // fingerprint of the key assigned to each node (64 bits), rank of pair 16*r }.  The membership filter rides in
+    // the record the lookup loads anyway: 3 scattered L2 requests per query instead of 4 (L1TEX was the limiter at
+    // 85 %, profiles/r01_tf23_ncu.txt), node / 16 is a shift, and rank needs one popcount.  1.23 B / key.
+    const uint4 *frecs;
 };
+// mphf_eval on the fused layout returns the id with the fingerprint of the chosen node in the top byte; probe23
+// strips it (its h argument is a reference) before anyone else sees the id.
+constexpr uint64_t kFusedTagShift = 56;
+constexpr uint64_t kFusedIdMask = (1ULL << kFusedTagShift) - 1;
 
 struct Index23Dev {
     uint64_t n;
@@ -194,7 +203,28 @@ __device__ __forceinline__ uint64_t mphf_eval_compact(const MphfDev &m, uint64_t
     return (uint64_t)rank;
 }
 
+// fused records: the chosen node (global pair index) is returned through *node when asked for (index upload)
+__device__ __forceinline__ uint64_t mphf_eval_fused(const MphfDev &m, uint64_t a, uint64_t b, uint64_t c, uint32_t *node = nullptr) {
+    const uint32_t d = (uint32_t)m.hash_domain;
+    const uint32_t n0 = fastmod32(a, d, m.magic);
+    const uint32_t n1 = d + fastmod32(b, d, m.magic);
+    const uint32_t n2 = 2u * d + fastmod32(c, d, m.magic);
+    const uint4 r0 = ld_evict_last_u32x4(&m.frecs[n0 >> 4]);
+    const uint4 r1 = ld_evict_last_u32x4(&m.frecs[n1 >> 4]);
+    const uint4 r2 = ld_evict_last_u32x4(&m.frecs[n2 >> 4]);
+    const uint32_t v = ((r0.x >> ((n0 & 15u) * 2u)) & 3u) + ((r1.x >> ((n1 & 15u) * 2u)) & 3u) + ((r2.x >> ((n2 & 15u) * 2u)) & 3u);
+    const uint32_t hidx = (0x24924u >> (2u * v)) & 3u;  // v % 3 for v <= 9
+    const uint4 r = hidx == 0 ? r0 : (hidx == 1 ? r1 : r2);
+    const uint32_t nd = hidx == 0 ? n0 : (hidx == 1 ? n1 : n2);
+    const uint32_t p = nd & 15u;
+    const uint32_t rank = r.w + nonzero_pairs32(r.x & ((1u << (2u * p)) - 1u));  // 2p <= 30
+    const uint32_t fp = ((p < 8u ? r.y : r.z) >> ((p & 7u) * 4u)) & 15u;
+    if (node) *node = nd;
+    return (uint64_t)rank | ((uint64_t)(0x10u | fp) << kFusedTagShift);
+}
+
 __device__ __forceinline__ uint64_t mphf_eval(const MphfDev &m, uint64_t a, uint64_t b, uint64_t c) {
+    if (m.frecs != nullptr) return mphf_eval_fused(m, a, b, c);
     if (m.crecs != nullptr) return mphf_eval_compact(m, a, b, c);
     const uint64_t d = m.hash_domain;
     uint64_t n0 = fastmod(a, d, m.magic);
@@ -294,10 +324,19 @@ __device__ __forceinline__ uint64_t mphf_lookup13(const MphfDev &m, uint32_t rc_
     return mphf_eval(m, a, b, c);
 }
 
-// checker/tf probe: returns true and *tf when slot h holds `kmer`
-__device__ __forceinline__ bool probe23(const Index23Dev &ix, uint64_t h, uint64_t kmer, uint32_t &tf) {
+// checker/tf probe: returns true and *tf when slot h holds `kmer`.  h comes straight from mphf_eval: on the fused
+// layout its top byte carries the fingerprint of the chosen node, which is checked and stripped here.
+// own_string = the string that was hashed is the ASCII form of `kmer` (then a stored kmer was reached through the node
+// the MPHF assigned to it, and the fused fingerprint of that node is its own).  The reference also compares slots
+// reached by hashing OTHER bytes (raw strings with non-ACGT characters, python_wrapper.cpp:610-622): those probes
+// pass own_string = false and go straight to the full compare, as does every probe of a layout with no filter.
+__device__ __forceinline__ bool probe23(const Index23Dev &ix, uint64_t &h, uint64_t kmer, uint32_t &tf, bool own_string = true) {
+    const uint32_t tag = (uint32_t)(h >> kFusedTagShift);
+    h &= kFusedIdMask;
     if (h >= ix.n) return false;
-    if (ix.fp != nullptr) {
+    if (tag & 0x10u) {
+        if (own_string && (tag & 15u) != fingerprint4(kmer)) return false;
+    } else if (ix.fp != nullptr) {  // the separate tier is indexed by slot: valid whichever bytes led to the slot
         uint32_t f;
         if (ix.fp_bits == 8) {
             asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(ix.fp + h), "l"(l2_policy_evict_last()));

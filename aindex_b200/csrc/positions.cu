@@ -61,7 +61,7 @@ __device__ __forceinline__ uint64_t bucket23(const Index23Dev &ix, const MphfDev
     if (us <= rs) {
         jenkins_short(m.seed, r0, r1, r2, 23u, a, b, c);
         h = mphf_eval(m, a, b, c);
-        return probe23(ix, h, us, tf) ? h : kNoBucket;
+        return probe23(ix, h, us, tf, false) ? h : kNoBucket;  // raw bytes were hashed
     }
     h = mphf_lookup23(m, us);
     return probe23(ix, h, rs, tf) ? h : kNoBucket;
@@ -226,7 +226,7 @@ __global__ void positions_query_kernel(Index23Dev ix, MphfDev m, const unsigned 
             if (cmp_words23(w[0], w[1], w[2], v0, v1, v2) <= 0) {
                 jenkins_short(m.seed, w[0], w[1], w[2], 23u, a, b, c);
                 uint64_t hh = mphf_eval(m, a, b, c);
-                if (probe23(ix, hh, us, tf)) h = hh;
+                if (probe23(ix, hh, us, tf, false)) h = hh;  // raw bytes were hashed
             } else {
                 jenkins_short(m.seed, v0, v1, v2, 23u, a, b, c);
                 uint64_t hh = mphf_eval(m, a, b, c);
@@ -531,7 +531,7 @@ int aix_positions_total13(aix_ctx *ctx, const aix_index13 *ix, uint64_t *total) 
 int aix_positions_build23(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *reads, uint64_t len, uint64_t *indices_out,
                           uint64_t *positions_out) {
     if (!ctx || !ix || !indices_out || (len && !reads)) return AIX_ERR_ARG;
-    return build_impl<23>(ctx, ix->dev(), ix->mphf->dev(), TfFromRecs{ix->recs_dev}, ix->n, reads, len, indices_out, positions_out);
+    return build_impl<23>(ctx, ix->dev(), ix->mphf_dev(), TfFromRecs{ix->recs_dev}, ix->n, reads, len, indices_out, positions_out);
 }
 
 int aix_positions_build13(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *reads, uint64_t len, uint64_t *indices_out,
@@ -544,7 +544,7 @@ int aix_positions_build13(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *re
 int aix_positions_build23_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *reads_dev, uint64_t len,
                               aix_positions **out) {
     if (!ctx || !ix || !out || (len && !reads_dev)) return AIX_ERR_ARG;
-    return build_dev_impl<23>(ctx, ix->dev(), ix->mphf->dev(), TfFromRecs{ix->recs_dev}, ix->n, reads_dev, len, out);
+    return build_dev_impl<23>(ctx, ix->dev(), ix->mphf_dev(), TfFromRecs{ix->recs_dev}, ix->n, reads_dev, len, out);
 }
 
 int aix_positions_build13_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *reads_dev, uint64_t len,
@@ -628,7 +628,7 @@ int aix_positions_query_dev(aix_ctx *ctx, const aix_index23 *ix23, const aix_ind
     MphfDev md;
     if (k == 23) {
         id = ix23->dev();
-        md = ix23->mphf->dev();
+        md = ix23->mphf_dev();
         positions_query_kernel<23><<<aix_grid(q, 128), 128, 0, st>>>(
             id, md, (const unsigned long long *)p->indices_dev, p->n_indices, (const unsigned long long *)p->positions_dev,
             p->n_positions, recs_dev, stride, lens_dev, q, (unsigned long long *)counts_dev,

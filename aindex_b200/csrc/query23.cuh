@@ -129,7 +129,7 @@ __device__ __forceinline__ void query23(const Index23Dev &ix, const MphfDev &m, 
             else jenkins_bytes(m.seed, p, len, a, b, c);
             uint64_t h1 = mphf_eval(m, a, b, c);
             uint32_t tf;
-            if (probe23(ix, h1, ustrict, tf)) {
+            if (probe23(ix, h1, ustrict, tf, false)) {  // raw bytes were hashed, not the string of ustrict
                 hit.strand = 1; hit.h = h1; hit.tf = tf;
             } else {
                 uint64_t h2 = mphf_lookup23(m, ustrict);  // ASCII of rstrict
@@ -182,7 +182,7 @@ __device__ __forceinline__ void query23(const Index23Dev &ix, const MphfDev &m, 
             if (len <= 23u) jenkins_short(m.seed, r0, r1, r2, len, a, b, c);
             else jenkins_bytes(m.seed, p, len, a, b, c);
             uint64_t h1 = mphf_eval(m, a, b, c);
-            if (probe23(ix, h1, ustrict, tf)) res = h1;
+            if (probe23(ix, h1, ustrict, tf, valid)) res = h1;  // a valid query's raw bytes are the string of ustrict
         } else {
             uint64_t a, b, c;
             jenkins_short(m.seed, v0, v1, v2, 23u, a, b, c);
@@ -209,7 +209,7 @@ __device__ __forceinline__ Hit find23_window(const Index23Dev &ix, const MphfDev
     jenkins_short(m.seed, r0, r1, r2, 23u, a, b, c);
     uint64_t h1 = mphf_eval(m, a, b, c);
     uint32_t tf;
-    if (probe23(ix, h1, us, tf)) {
+    if (probe23(ix, h1, us, tf, false)) {  // raw bytes were hashed
         hit.strand = 1; hit.h = h1; hit.tf = tf;
     } else {
         uint64_t h2 = mphf_lookup23(m, us);

@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(256) get_freq23_packed6_kernel(Index23Dev ix, 
     uint32_t res = 0, tf;
     if (kCanon) {
         const bool fwd = u <= r;
-        const uint64_t h = mphf_lookup23(m, fwd ? r : u);  // hashes the ASCII string of min(u, r)
+        uint64_t h = mphf_lookup23(m, fwd ? r : u);  // hashes the ASCII string of min(u, r)
         if (probe23(ix, h, fwd ? u : r, tf)) res = tf;
     } else {
-        const uint64_t ha = mphf_lookup23(m, r);
+        uint64_t ha = mphf_lookup23(m, r);
         if (probe23(ix, ha, u, tf)) res = tf;
         else {
-            const uint64_t hb = mphf_lookup23(m, u);
+            uint64_t hb = mphf_lookup23(m, u);
             if (probe23(ix, hb, r, tf)) res = tf;
         }
     }
@@ -232,7 +232,7 @@ __global__ void get_freq23_kernel(Index23Dev ix, MphfDev m, const uint64_t *__re
         // reverse probe only rl < lo -- one probe of min(lo, rl), same answer
         const bool fwd = lo <= rl;
         if (!fwd || k == lo) {
-            const uint64_t h = mphf_lookup23(m, fwd ? rl : lo);  // hashes the ASCII string of min(lo, rl)
+            uint64_t h = mphf_lookup23(m, fwd ? rl : lo);  // hashes the ASCII string of min(lo, rl)
             if (probe23(ix, h, fwd ? lo : rl, tf)) res = tf;
         }
         out[i] = res;
@@ -405,6 +405,44 @@ __global__ void index23_pack_kernel(const uint64_t *__restrict__ checker, const 
         }
     }
     if ((c >> 46) != 0 || c > revcomp23(c)) *non_canonical = 1;
+}
+
+// fused records, step 1: pair values and ranks (record r = half-word r of the bit-pair vector; fingerprints zero)
+__global__ void fused_layout_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ block_ranks,
+                                    uint64_t n_words, uint64_t n_recs, uint4 *__restrict__ frecs) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_recs) return;
+    const uint64_t w = r >> 1;
+    uint32_t half = 0, rank = 0;
+    if (w < n_words) {
+        const uint64_t blk = w >> 4;
+        uint64_t rk = block_ranks[blk];
+        for (uint64_t i = blk << 4; i < w; ++i) rk += nonzero_pairs64(words[i]);
+        const uint64_t x = words[w];
+        if (r & 1) { rk += nonzero_pairs32((uint32_t)x); half = (uint32_t)(x >> 32); }
+        else half = (uint32_t)x;
+        rank = (uint32_t)rk;
+    }
+    frecs[r] = make_uint4(half, 0u, 0u, rank);
+}
+
+// step 2: the 4-bit fingerprint of every stored k-mer goes to the node the MPHF assigns to it.  A k-mer whose own
+// hash does not lead back to its slot (inconsistent files) can never be found by a lookup, so it gets none.
+__global__ void fused_fingerprint_kernel(MphfDev m, const uint64_t *__restrict__ checker, uint64_t n, uint4 *__restrict__ frecs) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint64_t k = checker[h];
+    // the string a lookup hashes for a stored value is the ASCII form of its low 46 bits (get_bitset_dna23); values with
+    // bits above that are only ever compared by get_freq(uint64_t), which hashes the same string (hash.hpp:123-140)
+    uint64_t w0, w1, w2, a, b, c;
+    ascii_words23_from_rc(revcomp23(k & ((1ULL << 46) - 1)), w0, w1, w2);
+    jenkins_short(m.seed, w0, w1, w2, 23u, a, b, c);
+    uint32_t node = 0;
+    const uint64_t id = mphf_eval_fused(m, a, b, c, &node) & kFusedIdMask;
+    if (id != h) return;
+    uint32_t *words = reinterpret_cast<uint32_t *>(frecs + (node >> 4));
+    const uint32_t p = node & 15u;
+    atomicOr(words + (p < 8u ? 1 : 2), fingerprint4(k) << ((p & 7u) * 4u));
 }
 
 __global__ void tf13_direct_kernel(MphfDev m, const uint64_t *__restrict__ tf_mphf, uint64_t *__restrict__ tf_direct) {
@@ -589,7 +627,7 @@ template <int kMode>
 static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
                           const uint8_t *lens, uint64_t q, void *out) {
     Index23Dev id = ix->dev();
-    MphfDev md = ix->mphf->dev();
+    MphfDev md = ix->mphf_dev();
     const bool fixed = (stride == 23 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
     if (fixed && tf23_kernel_choice() == 1 && q >= 32) {
         const uint64_t n_tiles = q / 32;
@@ -703,9 +741,45 @@ int aix_index23_upload_dev(aix_ctx *ctx, const aix_mphf *m, const uint64_t *chec
     uint64_t fp_budget = 72ull << 20;  // measured: C2 (50 M keys, 70.5 MB with 8-bit fingerprints) still runs best with 8 bits (profiles/r01_tf23_sweep.txt)
     if (const char *e = getenv("AIX_FP_TIER_MAX_BYTES")) fp_budget = strtoull(e, nullptr, 10);
     uint64_t fp_bytes = 0;
-    if (n && n + m->layout_bytes <= fp_budget) { ix->fp_bits = 8; fp_bytes = n; }
+    // fused layout (fingerprints inside the MPHF records, 3 scattered requests per query instead of 4): when the
+    // 16-byte-per-16-nodes records fit the L2 budget.  AIX_INDEX23_LAYOUT=tier|fused overrides (A/B runs, tests).
+    bool fused = n && n == m->n && m->crecs_dev != nullptr && m->bv_size + 32 <= (64ull << 20);  // (a slice of a sharded index keeps the slot-indexed tier)
+    if (const char *e = getenv("AIX_INDEX23_LAYOUT")) {
+        if (!strcmp(e, "tier")) fused = false;
+        else if (!strcmp(e, "fused")) fused = n && n == m->n && m->bv_size < (1ull << 32) && m->hash_domain < (1ull << 31) && m->n < (1ull << 32);
+    }
+    if (getenv("AIX_FP_TIER_BITS")) fused = false;  // an explicit tier request is a tier request
+    if (fused) {
+        const uint64_t n_recs = (m->bv_size + 15) / 16 + 1;
+        uint64_t *words_dev = nullptr, *ranks_dev = nullptr;
+        cudaError_t ef = cudaMalloc(&ix->frecs_dev, n_recs * sizeof(uint4));
+        if (ef == cudaSuccess) ef = cudaMalloc(&words_dev, (m->n_words ? m->n_words : 1) * 8);
+        if (ef == cudaSuccess) ef = cudaMalloc(&ranks_dev, (m->n_blocks ? m->n_blocks : 1) * 8);
+        if (ef == cudaSuccess) ef = cudaMemcpyAsync(words_dev, m->words.data(), m->n_words * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (ef == cudaSuccess) ef = cudaMemcpyAsync(ranks_dev, m->block_ranks.data(), m->n_blocks * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (ef == cudaSuccess) {
+            fused_layout_kernel<<<aix_grid(n_recs, 256), 256, 0, ctx->stream>>>(words_dev, ranks_dev, m->n_words, n_recs, ix->frecs_dev);
+            MphfDev md = m->dev();
+            md.frecs = ix->frecs_dev;
+            fused_fingerprint_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(md, checker_dev, n, ix->frecs_dev);
+            ctx->launches += 2;
+            ef = cudaStreamSynchronize(ctx->stream);
+        }
+        cudaFree(words_dev);
+        cudaFree(ranks_dev);
+        if (ef != cudaSuccess) {  // no room: keep the separate tier logic below
+            cudaGetLastError();
+            cudaFree(ix->frecs_dev);
+            ix->frecs_dev = nullptr;
+            fused = false;
+        } else {
+            ix->frecs_bytes = n_recs * sizeof(uint4);
+        }
+    }
+    if (fused) { /* no separate tier */ }
+    else if (n && n + m->layout_bytes <= fp_budget) { ix->fp_bits = 8; fp_bytes = n; }
     else if (n && (n + 1) / 2 + m->layout_bytes <= fp_budget) { ix->fp_bits = 4; fp_bytes = (n + 1) / 2; }
-    if (const char *e = getenv("AIX_FP_TIER_BITS")) {  // test / experiment hook: 0, 4 or 8
+    if (const char *e = fused ? nullptr : getenv("AIX_FP_TIER_BITS")) {  // test / experiment hook: 0, 4 or 8
         int b = atoi(e);
         ix->fp_bits = (b == 4 || b == 8) ? b : 0;
         fp_bytes = ix->fp_bits == 8 ? n : (ix->fp_bits == 4 ? (n + 1) / 2 : 0);
@@ -783,6 +857,7 @@ void aix_index23_destroy(aix_ctx *ctx, aix_index23 *ix) {
     if (ctx) cudaSetDevice(ctx->device);
     if (ix->recs_dev) cudaFree(ix->recs_dev);
     if (ix->fp_dev) cudaFree(ix->fp_dev);
+    if (ix->frecs_dev) cudaFree(ix->frecs_dev);
     delete ix;
 }
 
@@ -795,10 +870,10 @@ int aix_index23_info(const aix_index23 *ix, uint64_t info[2]) {
 
 int aix_index23_layout(const aix_index23 *ix, uint64_t info[4]) {
     if (!ix || !info) return AIX_ERR_ARG;
-    info[0] = (uint64_t)ix->fp_bits;
-    info[1] = ix->fp_bits == 8 ? ix->n : (ix->fp_bits == 4 ? (ix->n + 1) / 2 : 0);
-    info[2] = ix->mphf->layout_bytes;
-    info[3] = ix->mphf->crecs_dev ? 1 : 0;
+    info[0] = ix->frecs_dev ? 4u : (uint64_t)ix->fp_bits;
+    info[1] = ix->frecs_dev ? 0 : (ix->fp_bits == 8 ? ix->n : (ix->fp_bits == 4 ? (ix->n + 1) / 2 : 0));
+    info[2] = ix->frecs_dev ? ix->frecs_bytes : ix->mphf->layout_bytes;
+    info[3] = ix->frecs_dev ? 2 : (ix->mphf->crecs_dev ? 1 : 0);
     return AIX_OK;
 }
 
@@ -875,7 +950,7 @@ int aix_probe23_dev(aix_ctx *ctx, const aix_index23 *shard, const uint64_t *prob
 int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, uint64_t q, uint32_t *out) {
     if (!ctx || !ix) return AIX_ERR_ARG;
     Index23Dev id = ix->dev();
-    MphfDev md = ix->mphf->dev();
+    MphfDev md = ix->mphf_dev();
     return run_record_batches(ctx, (const uint8_t *)ukmers, 8, nullptr, q, out, 4,
                               [&](cudaStream_t st, const uint8_t *r, const uint8_t *, uint64_t nq, void *o) {
                                   if (ix->canonical_only) get_freq23_kernel<true><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, (const uint64_t *)r, nq, (uint32_t *)o);
@@ -887,7 +962,7 @@ int aix_get_freq23(aix_ctx *ctx, const aix_index23 *ix, const uint64_t *ukmers, 
 
 static int launch_packed6(aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *r, uint64_t nq, void *o) {
     Index23Dev id = ix->dev();
-    MphfDev md = ix->mphf->dev();
+    MphfDev md = ix->mphf_dev();
     if (ix->canonical_only) get_freq23_packed6_kernel<true><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, r, nq, (uint32_t *)o);
     else get_freq23_packed6_kernel<false><<<aix_grid(nq, 256), 256, 0, st>>>(id, md, r, nq, (uint32_t *)o);
     AIX_LAUNCH_CHECK(ctx);

@@ -133,9 +133,9 @@ void aix_index23_destroy(aix_ctx *ctx, aix_index23 *ix);
 /* info[0] = n, info[1] = 1 if every stored k-mer is canonical (enables the one-probe
  * path, which is result-identical) */
 int aix_index23_info(const aix_index23 *ix, uint64_t info[2]);
-/* HBM/L2 layout chosen at upload: info[0] = fingerprint-tier bits per key (0 = no
- * tier, 4, 8), info[1] = tier bytes, info[2] = MPHF record bytes, info[3] = 1 for the compact
- * (48 pairs + u32 rank) MPHF records, 0 for the wide ones */
+/* HBM/L2 layout chosen at upload: info[0] = fingerprint bits per key (0 = none, 4, 8), info[1] = bytes of
+ * the separate fingerprint tier (0 when the fingerprints ride inside the MPHF records), info[2] = MPHF record bytes,
+ * info[3] = 0 wide MPHF records, 1 compact (48 pairs + u32 rank), 2 fused (16 pairs + 16 x 4-bit fingerprint + u32 rank) */
 int aix_index23_layout(const aix_index23 *ix, uint64_t info[4]);
 /* index fill on the GPU (replaces compute_index / index_hash_pp, hash.cpp:671-723,
  * :779-881): checker_out[h] = kmers[i], tf_out[h] = counts[i], h = mphf(kmers[i]) */

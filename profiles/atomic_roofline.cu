@@ -38,6 +38,61 @@ __global__ void gather16_kernel(const uint4 *__restrict__ idx, uint64_t n4, cons
     out[i] = a.x ^ b.y ^ c.z ^ d.w;
 }
 
+// (3) the shape of one 23-mer lookup with everything but the memory requests removed: 23 streamed bytes in and 4 bytes
+//     out per thread, kRec scattered 16-byte loads from an L2-resident record table (the MPHF records, evict_last) and
+//     kByte scattered 1-byte loads from a second L2-resident table (the fingerprint tier).  Indices come from a 3-step
+//     integer mix of the streamed bytes.  Its rate is the L1TEX / L2 request ceiling of the lookup kernel:
+//     tier layout = (3, 1), fused layout = (3, 0).
+template <int kRec, int kByte>
+__global__ void __launch_bounds__(256) lookup_shape_kernel(const uint8_t *__restrict__ recs, uint64_t q, const uint4 *__restrict__ table,
+                                                         uint32_t rec_mask, const uint8_t *__restrict__ bytes, uint32_t byte_mask,
+                                                         uint32_t *__restrict__ out) {
+    __shared__ __align__(16) uint32_t tile[(256 * 23 + 16) / 4 + 4];
+    const uint64_t q0 = (uint64_t)blockIdx.x * 256;
+    const uint4 *src = reinterpret_cast<const uint4 *>(recs + q0 * 23);
+    for (int v = threadIdx.x; v < 368; v += 256) reinterpret_cast<uint4 *>(tile)[v] = __ldcs(src + v);  // 256 * 23 = 368 * 16
+    __syncthreads();
+    const uint64_t i = q0 + threadIdx.x;
+    if (i >= q) return;
+    const uint32_t w = (threadIdx.x * 23u) >> 2;
+    uint32_t x = tile[w] ^ (tile[w + 2] * 0x9E3779B9u) ^ (tile[w + 4] * 0x85EBCA6Bu);
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < kRec; ++r) {
+        x = x * 0x2C1B3C6Du + 0x297A2D39u;
+        uint4 v;
+        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(table + ((x >> 7) & rec_mask)), "l"(p));
+        acc ^= v.x + v.w;
+    }
+#pragma unroll
+    for (int r = 0; r < kByte; ++r) {
+        x = x * 0x2C1B3C6Du + 0x297A2D39u;
+        uint32_t f;
+        asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(bytes + ((x >> 5) & byte_mask)), "l"(p));
+        acc += f;
+    }
+    __stcs(out + i, acc);
+}
+
+template <int kRec, int kByte>
+static void run_lookup_shape(const uint8_t *recs, uint64_t q, const uint4 *table, uint32_t rec_mask, const uint8_t *bytes,
+                             uint32_t byte_mask, uint32_t *out, cudaEvent_t a, cudaEvent_t b) {
+    float best = 1e30f;
+    for (int it = 0; it < 6; ++it) {
+        cudaEventRecord(a);
+        lookup_shape_kernel<kRec, kByte><<<(unsigned)(q / 256), 256>>>(recs, q, table, rec_mask, bytes, byte_mask, out);
+        cudaEventRecord(b);
+        CK(cudaEventSynchronize(b));
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (it > 1 && ms < best) best = ms;
+    }
+    printf("lookup_shape recs16=%d bytes1=%d record_table_MiB=%u byte_table_MiB=%u ms=%.3f Gqueries/s=%.2f\n", kRec, kByte,
+           (unsigned)(((uint64_t)rec_mask + 1) * 16 >> 20), (unsigned)(((uint64_t)byte_mask + 1) >> 20), best, q / (best * 1e-3) / 1e9);
+}
+
 int main(int argc, char **argv) {
     if (argc > 1) {  // optional: L2 fetch granularity in bytes (32 / 64 / 128)
         CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1])));
@@ -80,6 +135,21 @@ int main(int argc, char **argv) {
             if (it && ms < best) best = ms;
         }
         printf("gather16 table_MiB=%u ms=%.3f Ggathers/s=%.2f\n", (1u << log2_entries) * 16 >> 20, best, n / (best * 1e-3) / 1e9);
+    }
+    {   // the lookup's request shape: 100 Mi queries of 23 bytes, record table 16 / 32 / 64 MiB, byte table 32 / 64 MiB
+        const uint64_t q = 100ull << 20;
+        uint8_t *recs, *bytes;
+        CK(cudaMalloc(&recs, q * 23 + 64));
+        CK(cudaMalloc(&bytes, 64ull << 20));
+        gen_keys<<<(unsigned)((q * 23 / 4 + 255) / 256), 256>>>((uint32_t *)recs, q * 23 / 4, 0xFFFFFFFFu, 99);
+        CK(cudaMemset(bytes, 1, 64ull << 20));
+        CK(cudaDeviceSynchronize());
+        run_lookup_shape<3, 1>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, (32u << 20) - 1, out, a, b);  // 16 MiB + 32 MiB
+        run_lookup_shape<3, 1>(recs, q, (const uint4 *)table, (1u << 21) - 1, bytes, (64u << 20) - 1, out, a, b);  // 32 MiB + 64 MiB (> L2 share)
+        run_lookup_shape<3, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);                // 16 MiB
+        run_lookup_shape<3, 0>(recs, q, (const uint4 *)table, (1u << 22) - 1, bytes, 0, out, a, b);                // 64 MiB (the fused C2 records: 61.5 MB)
+        run_lookup_shape<4, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
+        run_lookup_shape<2, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
     }
     return 0;
 }

@@ -757,7 +757,7 @@ def test_tf23_layout_and_kernel_variants(capi, oracle, ctx, oidx23, monkeypatch,
                               oidx23.mphf.block_ranks)
     ix = capi.Index23.upload(ctx, m, oidx23.checker, oidx23.tf)
     lay = ix.layout
-    assert lay["fp_bits"] == fp_bits and lay["mphf_compact"] == (wide == 0)
+    assert lay["fp_bits"] == fp_bits and lay["mphf_compact"] == (wide == 0) and lay["records"] != "fused"
     rng = np.random.default_rng(100 + 10 * wide + fp_bits + kernel)
     # raw mphf ids (keys and non-keys) must not depend on the record shape
     q = _mixed_queries(rng, oidx23, 3000)
@@ -774,5 +774,57 @@ def test_tf23_layout_and_kernel_variants(capi, oracle, ctx, oidx23, monkeypatch,
             assert np.array_equal(ix.query(r23, mode), oidx23.batch(r23, None, omode)), f"fixed mode {mode} nq {nq}"
     cov_in = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "idx23.reads"), dtype=np.uint8)[:3000]
     assert np.array_equal(ix.coverage(cov_in), oidx23.coverage(cov_in))
+    ix.close()
+    m.close()
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_tf23_fused_layout(capi, oracle, ctx, oidx23, monkeypatch, kernel, golden_dir):
+    """The fused layout (16 pair values + 16 x 4-bit fingerprints + rank per 16-byte MPHF record; the default when the
+    records fit L2): every query mode, ragged batches, odd strings whose raw bytes are hashed (their probes must skip the
+    node's fingerprint), values with bits above 46 through get_freq, coverage, positions build and positions query --
+    all equal to the oracle and to the separate-tier layout."""
+    monkeypatch.setenv("AIX_TF23_KERNEL", str(kernel))
+    monkeypatch.setenv("AIX_INDEX23_LAYOUT", "fused")
+    m = capi.Mphf.from_arrays(ctx, oidx23.mphf.n, oidx23.mphf.hash_domain, oidx23.mphf.seed, oidx23.mphf.words,
+                              oidx23.mphf.block_ranks)
+    ix = capi.Index23.upload(ctx, m, oidx23.checker, oidx23.tf)
+    lay = ix.layout
+    assert lay["fp_bits"] == 4 and lay["fp_bytes"] == 0 and lay["records"] == "fused"
+    rng = np.random.default_rng(300 + kernel)
+    q = _mixed_queries(rng, oidx23, 6000)
+    recs, lens = oracle.pack_queries(q, stride=64)
+    modes = ((capi.Q_TF, oracle.MODE_TF), (capi.Q_TOTAL, oracle.MODE_TOTAL), (capi.Q_BOTH, oracle.MODE_BOTH),
+             (capi.Q_PFID, oracle.MODE_PFID), (capi.Q_STRAND, oracle.MODE_STRAND), (capi.Q_KID, oracle.MODE_KID))
+    for mode, omode in modes:
+        assert np.array_equal(ix.query(q, mode), oidx23.batch(recs, lens, omode)), f"generic mode {mode}"
+    for nq in (1, 31, 33, 8192, 50_021):
+        qq = [x for x in _mixed_queries(rng, oidx23, 2 * nq) if len(x) == 23][:nq]
+        r23 = np.frombuffer(b"".join(qq), dtype=np.uint8).reshape(len(qq), 23).copy()
+        for mode, omode in modes:
+            assert np.array_equal(ix.query(r23, mode), oidx23.batch(r23, None, omode)), f"fixed mode {mode} nq {nq}"
+    # every stored k-mer is found on both strands (no false negative from a node's fingerprint)
+    km = ctx.decode(oidx23.checker, 23)
+    assert np.array_equal(ix.query(km), oidx23.tf)
+    assert np.array_equal(ix.query(ctx.decode(ctx.revcomp(oidx23.checker, 23), 23)), oidx23.tf)
+    assert np.array_equal(ix.get_freq(oidx23.checker), oidx23.tf)
+    assert np.array_equal(ix.get_freq_packed(capi.pack23(km)), oidx23.tf)
+    # stored values with bits above 46 (only get_freq(uint64_t) can name them): own fingerprints, still exact
+    chk = oidx23.checker.copy()
+    chk[::5] |= np.uint64(1) << np.uint64(50)
+    ix2 = capi.Index23.upload(ctx, m, chk, oidx23.tf)
+    o2 = oracle.Index23(oidx23.mphf, chk, oidx23.tf)
+    probe = np.concatenate([chk[:400], oidx23.checker[:400]])
+    assert np.array_equal(ix2.get_freq(probe), np.array([o2.get_freq(int(x)) for x in probe], dtype=np.uint32))
+    ix2.close()
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    assert np.array_equal(ix.coverage(reads[:5000]), oidx23.coverage(reads[:5000]))
+    noisy = reads[:5000].copy()
+    noisy[::97] = ord("N")
+    noisy[50::131] = ord("a")
+    assert np.array_equal(ix.coverage(noisy), oidx23.coverage(noisy))
+    gi, gp = ix.positions_build(reads)
+    assert np.array_equal(gi, np.fromfile(os.path.join(golden_dir, "idx23.indices.bin"), dtype=np.uint64))
+    assert np.array_equal(gp, np.fromfile(os.path.join(golden_dir, "idx23.index.bin"), dtype=np.uint64))
     ix.close()
     m.close()
