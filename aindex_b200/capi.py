@@ -68,6 +68,10 @@ SIGNATURES = {
     "aix_revcomp_kmers": (_i, [_vp, _vp, _u64, _i, _vp]),
     "aix_pack_2bit": (_i, [_vp, _vp, _u64, _vp]),
     "aix_rolling_kmers": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp]),
+    "aix_rolling_kmers_dev": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp]),
+    "aix_pack_2bit_dev": (_i, [_vp, _vp, _u64, _vp]),
+    "aix_ukmers": (_i, [_vp, _vp, _u64, _vp, _u64, _i, _vp]),
+    "aix_ukmers_dev": (_i, [_vp, _vp, _u64, _vp, _u64, _i, _vp]),
     "aix_index23_upload": (_i, [_vp, _vp, _vp, _vp, _u64, _pp]),
     "aix_index23_upload_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _pp]),
     "aix_index23_load_prefix": (_i, [_vp, C.c_char_p, _pp, _pp]),
@@ -266,6 +270,14 @@ class Context:
         a = _bytes(seq)
         out = np.zeros((a.size + 3) // 4, dtype=np.uint8)
         self.check(lib().aix_pack_2bit(self._h, _p(a), a.size, _p(out)))
+        return out
+
+    def ukmers(self, packed, n_bases: int, pos, k: int) -> np.ndarray:
+        """dna_bitset::ukmer(pos, k) for every position of `pos` (packed = pack_2bit of the sequence)"""
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        ps = np.ascontiguousarray(pos, dtype=np.uint64)
+        out = np.zeros(ps.size, dtype=np.uint64)
+        self.check(lib().aix_ukmers(self._h, _p(pk), n_bases, _p(ps), ps.size, k, _p(out)))
         return out
 
     def rolling_kmers(self, data, k: int):

@@ -529,6 +529,7 @@ static uint64_t c23_pass_capacity(uint64_t reserve_bytes) {
 }
 
 static int c23_single_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t n_win, uint64_t *n_out) {
+    AixTrace trace(ctx->stream, "canonical23 count");
     uint64_t *keys = nullptr, *keys_alt = nullptr;
     uint32_t *cnts = nullptr;
     auto cleanup = [&]() { cudaFree(keys); cudaFree(keys_alt); cudaFree(cnts); };
@@ -539,8 +540,10 @@ static int c23_single_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len,
         cudaGetLastError(); cleanup();
         return ctx->fail(AIX_ERR_NOMEM, "canonical23 buffers: %s", cudaGetErrorString(e));
     }
+    trace.mark("allocate keys + spare + counts");
     canonical23_kernel<<<aix_grid((n_win + kCanRoll - 1) / kCanRoll, 128), 128, 0, ctx->stream>>>(reads_dev, len, keys);
     ctx->launches++;
+    trace.mark("emit canonical k-mers");
     uint64_t *uniq = nullptr, n = 0;
     int rc = c23_sort_rle(ctx, keys, keys_alt, cnts, n_win, 47, &uniq, &n)  /* 46 k-mer bits + the bit that sets the all-ones sentinel apart */;
     if (rc != AIX_OK) { cleanup(); return rc; }
@@ -553,7 +556,9 @@ static int c23_single_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len,
         if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_kmers_dev, uniq, n * 8, cudaMemcpyDeviceToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(ctx->c23_counts_dev, cnts, n * 4, cudaMemcpyDeviceToDevice);
     }
+    trace.mark("sort + run-length + copy out");
     cleanup();
+    trace.mark("free buffers");
     if (e != cudaSuccess) {
         cudaGetLastError();
         return ctx->fail(AIX_ERR_NOMEM, "canonical23 result: %s", cudaGetErrorString(e));

@@ -98,24 +98,31 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
         const uint32_t idx = wbase + j * 32;
         key[j] = idx < tile_n ? (uint64_t)__ldcs((const unsigned long long *)(in + tile_base + idx)) : ~0ull;
     }
-    // rank inside the warp: lanes with the same digit form a group (match_any); the group's lowest lane
-    // reserves the group's slots in the warp's histogram, members follow in lane order
+    // rank inside the warp: lanes with the same digit form a group (match_any).  Every lane of a group reads the digit's
+    // running count of this warp (one broadcast LDS), the group's lowest lane then adds the group size.  The matches
+    // of eight items are issued back to back (MATCH.ANY has a long latency: it was 30 % of the stall samples when
+    // each one sat in front of the shared-memory update that depends on it, profiles/r02_c5sort_ncu.txt).
     uint32_t *my_hist = whist + warp * radix;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
-        const bool valid = wbase + j * 32 < tile_n;
-        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & mask) : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader && valid) {
-            base = my_hist[d];
-            my_hist[d] = base + __popc(peers);
+    for (int j0 = 0; j0 < kRsItems; j0 += 8) {
+        uint32_t peers[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool valid = wbase + (j0 + u) * 32 < tile_n;
+            const uint32_t d = valid ? ((uint32_t)(key[j0 + u] >> shift) & mask) : 0xFFFFFFFFu;
+            peers[u] = __match_any_sync(0xFFFFFFFFu, d);
         }
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        pos[j] = (uint16_t)(base + __popc(peers & lt));
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool valid = wbase + (j0 + u) * 32 < tile_n;
+            const uint32_t d = (uint32_t)(key[j0 + u] >> shift) & mask;
+            const uint32_t base = valid ? my_hist[d] : 0u;
+            __syncwarp();
+            if (valid && (peers[u] & lt) == 0u) my_hist[d] = base + __popc(peers[u]);
+            __syncwarp();
+            pos[j0 + u] = (uint16_t)(base + __popc(peers[u] & lt));
+        }
     }
     __syncthreads();
     // per digit: exclusive prefix over the warps, tile total; publish the aggregate at once

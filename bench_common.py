@@ -98,19 +98,32 @@ def make_hit_queries(torch, dev, reads, n, seed):
 
 def build_index(torch, capi, ctx, reads):
     """reads (device tensor) -> canonical 23-mer table -> GPU MPHF -> {checker, tf} fill.
-    Returns (mphf, index, checker_dev, tf_dev, n)."""
+    Returns (mphf, index, checker_dev, tf_dev, n).  AIX_TRACE=1 prints the phase times on stderr."""
     import ctypes as C
     lib = capi.lib()
+    trace = bool(os.environ.get("AIX_TRACE"))
+    t = [time.perf_counter()]
+
+    def mark(what):
+        if trace:
+            ctx.sync()
+            t.append(time.perf_counter())
+            sys.stderr.write(f"[aix trace] build_index: {what:<60s} {(t[-1] - t[-2]) * 1e3:9.3f} ms\n")
+
     n = C.c_uint64()
     ctx.check(lib.aix_canonical23_count_dev(ctx.handle, reads.data_ptr(), reads.numel(), C.byref(n)))
     kp, cp = C.c_void_p(), C.c_void_p()
     ctx.check(lib.aix_canonical23_result_dev(ctx.handle, C.byref(kp), C.byref(cp), None))
     n = int(n.value)
+    mark("canonical 23-mer table (emit + sort + run-length)")
     mphf = capi.Mphf.build_dev(ctx, kp.value, n, 23)
+    mark("MPHF construction (parallel peeling)")
     checker = torch.empty(n, device=reads.device, dtype=torch.int64)
     tf = torch.empty(n, device=reads.device, dtype=torch.int32)
     ctx.check(lib.aix_index23_fill_dev(ctx.handle, mphf._h, kp.value, cp.value, n, checker.data_ptr(), tf.data_ptr()))
+    mark("checker / tf fill")
     index = capi.Index23.upload_dev(ctx, mphf, checker.data_ptr(), tf.data_ptr(), n)
+    mark("index upload (records + fused MPHF records / fingerprint tier)")
     return mphf, index, checker, tf, n
 
 

@@ -113,11 +113,20 @@ int aix_decode_kmers(aix_ctx *ctx, const uint64_t *values, uint64_t q, int k, ui
 int aix_revcomp_kmers(aix_ctx *ctx, const uint64_t *values, uint64_t q, int k, uint64_t *out);
 /* dna_bitset ctor (dna_bitseq.hpp:22-61): 4 bases per byte, MSB first, non-ACGT -> A */
 int aix_pack_2bit(aix_ctx *ctx, const uint8_t *seq, uint64_t len, uint8_t *packed_out);
+int aix_pack_2bit_dev(aix_ctx *ctx, const uint8_t *seq_dev, uint64_t len, uint8_t *packed_dev);
+/* dna_bitset::ukmer(pos, k) (dna_bitseq.hpp:124-151), batched: out[i] = the k bases (k <= 32) that start at base pos[i] of
+ * the packed sequence, as a 2k-bit number (first base in the top bits).  Bases at or past n_bases read as A. */
+int aix_ukmers(aix_ctx *ctx, const uint8_t *packed, uint64_t n_bases, const uint64_t *pos, uint64_t q, int k, uint64_t *out);
+int aix_ukmers_dev(aix_ctx *ctx, const uint8_t *packed_dev, uint64_t n_bases, const uint64_t *pos_dev, uint64_t q, int k,
+                   uint64_t *out_dev);
 /* rolling canonical k-mers of a reads buffer: for every window start i in [0,len-k]
  * fwd_out[i], rc_out[i] (either may be NULL) and valid_out[i] = 1 iff all k characters
  * are upper-case ACGT (the loop of hash.cpp:1006-1032 without the lookup) */
 int aix_rolling_kmers(aix_ctx *ctx, const uint8_t *bytes, uint64_t len, int k, uint64_t *fwd_out,
                       uint64_t *rc_out, uint8_t *valid_out);
+/* device form: bytes_dev 16-byte aligned and readable up to the next multiple of 16 past len */
+int aix_rolling_kmers_dev(aix_ctx *ctx, const uint8_t *bytes_dev, uint64_t len, int k, uint64_t *fwd_dev,
+                          uint64_t *rc_dev, uint8_t *valid_dev);
 
 /* ---- 23-mer index: PHASH_MAP + AindexWrapper 23-mer queries --------------------- */
 /* load_hash (hash.cpp:367-450): checker = .kmers.bin (u64[n]), tf = .tf.bin (u32[n]) */

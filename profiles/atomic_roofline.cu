@@ -77,6 +77,94 @@ __global__ void __launch_bounds__(256) lookup_shape_kernel(const uint8_t *__rest
     __stcs(out + i, acc);
 }
 
+// the same requests behind the input path of tf23_stream_kernel (csrc/tf_query.cu): every warp owns a 3-slot ring of
+// 32-query tiles (736 B) filled by cp.async.bulk two tiles ahead, one mbarrier per slot, no CTA barrier
+template <int kRec, int kByte>
+__global__ void __launch_bounds__(256) lookup_shape_stream_kernel(const uint8_t *__restrict__ recs, uint64_t n_tiles, const uint4 *__restrict__ table,
+                                                                uint32_t rec_mask, const uint8_t *__restrict__ bytes, uint32_t byte_mask,
+                                                                uint32_t *__restrict__ out) {
+    constexpr int kWarps = 8, kStages = 3, kSlot = 768, kTilesPerWarp = 16;
+    constexpr uint32_t kTileBytes = 736;
+    __shared__ __align__(128) uint8_t ring[kWarps][kStages][kSlot];
+    __shared__ __align__(8) uint64_t bars[kWarps][kStages];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&ring[wid][0][0]), bar0 = (uint32_t)__cvta_generic_to_shared(&bars[wid][0]);
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * (kWarps * kTilesPerWarp) + wid;
+    if (tile0 >= n_tiles) return;
+    const uint64_t left = n_tiles - tile0;
+    const uint32_t my_tiles = left >= (uint64_t)(kWarps * kTilesPerWarp) ? (uint32_t)kTilesPerWarp : (uint32_t)((left + kWarps - 1) / kWarps);
+    uint64_t pol_in, pol_keep;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    constexpr uint32_t kStride = kWarps * kTileBytes;
+    const uint8_t *src = recs + tile0 * kTileBytes;
+    auto fill = [&](uint32_t s, const uint8_t *from) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(kTileBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(ring0 + (uint32_t)kSlot * s), "l"(from), "r"(kTileBytes), "r"(bar0 + 8u * s), "l"(pol_in) : "memory");
+    };
+    if (lane == 0)
+        for (int s = 0; s < kStages - 1; ++s)
+            if ((uint32_t)s < my_tiles) fill(s, src + (uint64_t)kStride * s);
+    src += (uint64_t)kStride * (kStages - 1);
+    uint64_t i = tile0 * 32u + lane;
+    uint32_t slot = 0, phase = 0;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        if (lane == 0 && it + (kStages - 1) < my_tiles) fill(slot == 0 ? kStages - 1 : slot - 1, src);
+        src += kStride;
+        uint32_t done;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
+        } while (!done);
+        const uint32_t a = ring0 + (uint32_t)kSlot * slot + ((lane * 23u) & ~3u);
+        uint32_t x0, x2, x4;
+        asm volatile("ld.shared.u32 %0, [%3];\nld.shared.u32 %1, [%3+8];\nld.shared.u32 %2, [%3+16];" : "=r"(x0), "=r"(x2), "=r"(x4) : "r"(a) : "memory");
+        __syncwarp();
+        uint32_t x = x0 ^ (x2 * 0x9E3779B9u) ^ (x4 * 0x85EBCA6Bu), acc = 0;
+#pragma unroll
+        for (int r = 0; r < kRec; ++r) {
+            x = x * 0x2C1B3C6Du + 0x297A2D39u;
+            uint4 v;
+            asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "l"(table + ((x >> 7) & rec_mask)), "l"(pol_keep));
+            acc ^= v.x + v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < kByte; ++r) {
+            x = x * 0x2C1B3C6Du + 0x297A2D39u;
+            uint32_t f;
+            asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(f) : "l"(bytes + ((x >> 5) & byte_mask)), "l"(pol_keep));
+            acc += f;
+        }
+        __stcs(out + i, acc);
+        i += (uint64_t)kWarps * 32u;
+        if (++slot == kStages) { slot = 0; phase ^= 1u; }
+    }
+}
+
+template <int kRec, int kByte>
+static void run_lookup_shape_stream(const uint8_t *recs, uint64_t q, const uint4 *table, uint32_t rec_mask, const uint8_t *bytes,
+                                    uint32_t byte_mask, uint32_t *out, cudaEvent_t a, cudaEvent_t b) {
+    float best = 1e30f;
+    const uint64_t n_tiles = q / 32, grid = (n_tiles + 127) / 128;
+    for (int it = 0; it < 6; ++it) {
+        cudaEventRecord(a);
+        lookup_shape_stream_kernel<kRec, kByte><<<(unsigned)grid, 256>>>(recs, n_tiles, table, rec_mask, bytes, byte_mask, out);
+        cudaEventRecord(b);
+        CK(cudaEventSynchronize(b));
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (it > 1 && ms < best) best = ms;
+    }
+    printf("lookup_shape_stream recs16=%d bytes1=%d record_table_MiB=%u byte_table_MiB=%u ms=%.3f Gqueries/s=%.2f\n", kRec, kByte,
+           (unsigned)(((uint64_t)rec_mask + 1) * 16 >> 20), (unsigned)(((uint64_t)byte_mask + 1) >> 20), best, q / (best * 1e-3) / 1e9);
+}
+
 template <int kRec, int kByte>
 static void run_lookup_shape(const uint8_t *recs, uint64_t q, const uint4 *table, uint32_t rec_mask, const uint8_t *bytes,
                              uint32_t byte_mask, uint32_t *out, cudaEvent_t a, cudaEvent_t b) {
@@ -150,6 +238,12 @@ int main(int argc, char **argv) {
         run_lookup_shape<3, 0>(recs, q, (const uint4 *)table, (1u << 22) - 1, bytes, 0, out, a, b);                // 64 MiB (the fused C2 records: 61.5 MB)
         run_lookup_shape<4, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
         run_lookup_shape<2, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
+        // the same with the TMA-ring input path of the product kernel: the request ceiling of tf23_stream_kernel
+        run_lookup_shape_stream<3, 1>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, (32u << 20) - 1, out, a, b);
+        run_lookup_shape_stream<3, 1>(recs, q, (const uint4 *)table, (1u << 21) - 1, bytes, (64u << 20) - 1, out, a, b);
+        run_lookup_shape_stream<3, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
+        run_lookup_shape_stream<3, 0>(recs, q, (const uint4 *)table, (1u << 22) - 1, bytes, 0, out, a, b);
+        run_lookup_shape_stream<2, 0>(recs, q, (const uint4 *)table, (1u << 20) - 1, bytes, 0, out, a, b);
     }
     return 0;
 }

@@ -83,6 +83,51 @@ def test_jenkins_and_codec(oracle, ctx):
             assert int(valid[i]) == (1 if not w.strip(b"ACGT") else 0)
 
 
+@pytest.mark.parametrize("n", [0, 1, 3, 15, 16, 17, 511, 512, 513, 100_003])
+def test_pack2bit_vector_kernel_and_ukmer(oracle, ctx, n):
+    """dna_bitset ctor (vector kernel over the aligned bulk + generic tail) and dna_bitset::ukmer against the oracle
+    (dna_bitseq.hpp:22-61, 124-151), ragged lengths around the 16-byte vector and the 512-byte warp tile"""
+    rng = np.random.default_rng(n + 1)
+    seq = rng.choice(np.frombuffer(b"ACGTNacgt\n~", dtype=np.uint8), size=n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .02, .01, .01]).tobytes()
+    packed = ctx.pack_2bit(seq)
+    assert np.array_equal(packed, oracle.dna_bitset_pack(seq))
+    if n >= 40:
+        for k in (1, 13, 23, 31, 32):
+            pos = np.unique(np.concatenate([rng.integers(0, n - k + 1, size=200), [0, n - k]])).astype(np.uint64)
+            got = ctx.ukmers(packed, n, pos, k)
+            want = np.array([oracle.dna_bitset_ukmer(packed, int(p), k) for p in pos], dtype=np.uint64)
+            assert np.array_equal(got, want)
+        # past the end of the sequence: missing bases read as A
+        got = ctx.ukmers(packed, n, np.array([n - 5, n - 1, n, n + 7], dtype=np.uint64), 23)
+        full = oracle.dna_bitset_pack(seq + b"A" * 64)
+        assert np.array_equal(got, np.array([oracle.dna_bitset_ukmer(full, p, 23) for p in (n - 5, n - 1, n, n + 7)], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("k", [13, 23])
+def test_rolling_vector_kernel_every_window(oracle, ctx, k, monkeypatch):
+    """rolling forward / reverse-complement k-mers (128-bit loads + shuffles + staged stores): EVERY window of a buffer
+    that crosses warp tiles (512 windows), with separators and lower case, single call and forced chunks"""
+    rng = np.random.default_rng(k)
+    n = 20_000 + k
+    seq = rng.choice(np.frombuffer(b"ACGTNa\n~", dtype=np.uint8), size=n, p=[.24, .24, .24, .24, .01, .01, .01, .01])
+    enc = oracle.dna23_bitset if k == 23 else oracle.dna13_bitset
+    rev = oracle.reverse_dna23 if k == 23 else oracle.reverse_dna13
+    b = seq.tobytes()
+    want_f = np.array([enc(b[i:i + k]) for i in range(n - k + 1)], dtype=np.uint64)
+    want_r = np.array([rev(int(v)) for v in want_f], dtype=np.uint64)
+    want_v = np.array([0 if b[i:i + k].strip(b"ACGT") else 1 for i in range(n - k + 1)], dtype=np.uint8)
+    for chunk in (None, "4096", "528"):
+        if chunk:
+            monkeypatch.setenv("AIX_ROLLING_CHUNK", chunk)
+        fwd, rcv, valid = ctx.rolling_kmers(seq, k)
+        assert np.array_equal(fwd, want_f) and np.array_equal(rcv, want_r) and np.array_equal(valid, want_v)
+    monkeypatch.delenv("AIX_ROLLING_CHUNK")
+    for m in (k - 1, k, k + 1, 15 + k, 16 + k, 512 + k - 1, 512 + k):
+        fwd, rcv, valid = ctx.rolling_kmers(seq[:m], k)
+        w = max(0, m - k + 1)
+        assert np.array_equal(fwd, want_f[:w]) and np.array_equal(rcv, want_r[:w]) and np.array_equal(valid, want_v[:w])
+
+
 def test_mphf_lookup_golden(capi, ctx, idx23, g23, pf13, oracle):
     recs, lens = g23["recs"], g23["lens"]
     assert np.array_equal(idx23.mphf.lookup(_queries(recs, lens)), g23["hash"])
