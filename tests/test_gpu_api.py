@@ -302,3 +302,100 @@ def test_multi_gpu_count_and_queries():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29571", os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _multi(capi, n, dev_ids=None):
+    import ctypes as C
+    lib = capi.lib()
+    h = C.c_void_p()
+    ids = (C.c_int * n)(*dev_ids) if dev_ids else None
+    rc = lib.aix_multi_create(n, ids, C.byref(h))
+    assert rc == 0, lib.aix_multi_last_error(None)
+    return h
+
+
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_count13_multi_single_process(pf13, golden_dir, tmp_path, ranks):
+    """aix_count13_multi: N contexts / host threads in ONE process, sharded input, exchange over peer pointers, permute.
+    On a 1-GPU box the N contexts share device 0 (the peer pointers are then ordinary device pointers), which exercises
+    the same sharding, exchange and permutation code; with >= N GPUs it runs one context per GPU.  Results must equal the
+    single-context path and the reference's count_kmers13 goldens, for plain text, FASTQ and FASTA."""
+    import ctypes as C
+    import torch
+    from aindex_b200 import capi
+    lib = capi.lib()
+    n_dev = torch.cuda.device_count()
+    ids = list(range(ranks)) if n_dev >= ranks else [0] * ranks
+    mg = _multi(capi, ranks, ids)
+    try:
+        assert lib.aix_multi_size(mg) == ranks
+        ctx0 = capi.Context.__new__(capi.Context)
+        ctx0._h = C.c_void_p(lib.aix_multi_ctx(mg, 0))
+        m13 = capi.Mphf.load(ctx0, pf13)
+        single = capi.Context(0)
+        m13s = capi.Mphf.load(single, pf13)
+        rng = np.random.default_rng(17)
+        acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+        genome = rng.choice(acgt, size=30_000)
+        reads = []
+        for i in range(4000):
+            st = int(rng.integers(0, genome.size - 120))
+            r = genome[st:st + int(rng.integers(5, 120))].tobytes()
+            if i % 37 == 0:
+                r = r[:3] + b"N" + r[4:]
+            reads.append(r)
+        plain = b"\n".join(reads) + b"\n"
+        fastq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+        fasta = b"".join(b">s%d desc\n%s\n" % (i, b"\n".join(r[j:j + 60] for j in range(0, len(r), 60))) for i, r in enumerate(reads))
+        long_line = b"\n".join([genome.tobytes()] * 3) + b"\n"  # lines far longer than a shard: cuts fall on the few newlines
+        for name, img, fmt in (("plain", plain, capi.FMT_PLAIN), ("fastq", fastq, capi.FMT_DETECT), ("fasta", fasta, capi.FMT_DETECT),
+                               ("long", long_line, capi.FMT_PLAIN), ("tiny", b"ACGTACGTACGTACGTA\n", capi.FMT_PLAIN), ("empty", b"", capi.FMT_PLAIN)):
+            a = np.frombuffer(img, dtype=np.uint8)
+            tf = np.zeros(1 << 26, dtype=np.uint64)
+            st = capi.CountStats()
+            rc = lib.aix_count13_multi(mg, m13._h, a.ctypes.data if a.size else None, a.size, fmt, tf.ctypes.data, C.byref(st))
+            assert rc == 0, (name, lib.aix_multi_last_error(mg))
+            want, wst = single.count13(m13s, a, fmt)
+            assert np.array_equal(tf, want), name
+            assert st.as_dict() == wst, (name, st.as_dict(), wst)
+        # the reference's own fixture
+        g = np.load(os.path.join(golden_dir, "golden13.npz"))
+        if "plain_reads" in g.files:
+            a = g["plain_reads"]
+            tf = np.zeros(1 << 26, dtype=np.uint64)
+            st = capi.CountStats()
+            assert lib.aix_count13_multi(mg, m13._h, a.ctypes.data, a.size, capi.FMT_PLAIN, tf.ctypes.data, C.byref(st)) == 0
+            assert np.array_equal(tf, single.count13(m13s, a, capi.FMT_PLAIN)[0])
+        m13s.close()
+        single.close()
+    finally:
+        # ctx0 is borrowed from the aix_multi: never let its wrapper destroy it
+        try:
+            if m13._h:
+                lib.aix_mphf_destroy(ctx0._h, m13._h)
+                m13._h = C.c_void_p()
+        except NameError:
+            pass
+        try:
+            ctx0._h = C.c_void_p()
+        except NameError:
+            pass
+        lib.aix_multi_destroy(mg)
+
+
+def test_count_kmers13_tool_uses_every_gpu(pf13, g13, tmp_path):
+    """the drop-in binary: same file as the single-GPU run whatever the thread (= GPU) argument"""
+    binp = os.path.join(ROOT, "aindex_b200", "bin", "count_kmers13")
+    rng = np.random.default_rng(23)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    img = b"".join(rng.choice(acgt, size=int(rng.integers(20, 200))).tobytes() + b"\n" for _ in range(3000))
+    inp = tmp_path / "reads.txt"
+    inp.write_bytes(img)
+    outs = []
+    for th in ("1", "16"):
+        out = tmp_path / f"o{th}.tf.bin"
+        r = subprocess.run([binp, str(inp), pf13, str(out), th], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert "GPUs:" in r.stdout
+        outs.append(np.fromfile(out, dtype=np.uint64))
+    assert np.array_equal(outs[0], outs[1]) and int(outs[0].sum()) > 0
