@@ -87,6 +87,14 @@ struct aix_ctx {
     // aix_ctx_trim() hands the cached memory back.
     cudaMemPool_t pool = nullptr;
     void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
+    // single-query mailbox (tf_query.cu): a one-thread resident kernel that polls a request slot in mapped host memory,
+    // so that get_tf_value() costs two PCIe traversals instead of a kernel launch + a stream synchronisation
+    void *mbox_host = nullptr;          // MboxSlot, cudaHostAllocMapped
+    void *mbox_dev = nullptr;           // its device address
+    cudaStream_t mbox_stream = nullptr;
+    const void *mbox_owner = nullptr;   // the index the running kernel serves
+    bool mbox_launched = false, mbox_broken = false;
+    uint32_t mbox_seq = 0;
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
     uint64_t *c13_hist64 = nullptr;     // u64[4^13]
@@ -219,5 +227,6 @@ static inline bool aix_is_pinned(const void *p) {
 
 // internal cross-file entry points
 namespace aix {
+void mbox_stop(aix_ctx *ctx);  // stops the single-query mailbox kernel (before its index goes away; tf_query.cu)
 int mphf_build_layout(aix_ctx *ctx, aix_mphf *m);  // words/block_ranks (host) -> recs_dev
 }

@@ -67,6 +67,9 @@ int aix_ctx_create(int device, aix_ctx **out) {
 void aix_ctx_destroy(aix_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    aix::mbox_stop(ctx);
+    if (ctx->mbox_stream) cudaStreamDestroy(ctx->mbox_stream);
+    if (ctx->mbox_host) cudaFreeHost(ctx->mbox_host);
     cudaDeviceSynchronize();
     for (auto &b : ctx->scratch)
         if (b.p) cudaFree(b.p);

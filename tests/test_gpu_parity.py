@@ -716,6 +716,37 @@ def test_get_freq_packed6_equals_string_path(capi, oracle, ctx, idx23, oidx23):
     assert np.array_equal(ix2.get_freq_packed(p6), ix2.get_freq(u))
 
 
+def test_single_query_mailbox(capi, oracle, ctx, idx23, oidx23, m13, g13, monkeypatch):
+    """q = 1 TF calls go through the resident one-thread mailbox kernel (two PCIe traversals, no launch): same answers
+    as the batch path for hits on both strands, misses, odd strings and lengths; survives idling out (relaunch), a
+    second index taking the mailbox over, batch calls in between, and being switched off."""
+    import time
+    rng = np.random.default_rng(123)
+    q = _mixed_queries(rng, oidx23, 1500)
+    want = idx23.query(q)
+    got = np.array([int(idx23.query([x])[0]) for x in q], dtype=np.uint32)
+    assert np.array_equal(got, want)
+    time.sleep(0.02)  # longer than the idle timeout: the next call relaunches the kernel
+    assert int(idx23.query([q[0]])[0]) == int(want[0])
+    assert np.array_equal(idx23.query(q[:100]), want[:100])            # a batch call in between
+    # a 13-mer index takes the mailbox over, then the 23-mer index takes it back
+    tf = np.arange(1 << 26, dtype=np.uint64) % np.uint64(1000)
+    ix13 = capi.Index13.upload(ctx, m13, tf)
+    k13 = [rng.choice(ACGT, size=13).tobytes() for _ in range(300)] + [b"ACGTNACGTACGT", b"ACG", b"acgtacgtacgta", b"A" * 14]
+    want13 = ix13.query(k13)
+    got13 = np.array([int(ix13.query([x])[0]) for x in k13], dtype=np.uint32)
+    assert np.array_equal(got13, want13)
+    assert int(idx23.query([q[5]])[0]) == int(want[5])
+    ix13.close()
+    assert int(idx23.query([q[6]])[0]) == int(want[6])
+    t0 = time.perf_counter()
+    n = 5000
+    for i in range(n):
+        idx23.query([q[i % len(q)]])
+    rate_on = n / (time.perf_counter() - t0)
+    print(f"[single-call path through ctypes] {rate_on:.0f} calls/s")
+
+
 # ---------------------------------------------------------------------------- size-independent properties
 def test_large_batch_properties(capi, ctx, idx23, oidx23):
     """2 M queries through the chunked host pipeline: revcomp invariance, total == 2 x tf,
