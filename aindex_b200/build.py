@@ -2,7 +2,7 @@
 
   aindex_b200/libaindex_cuda.so            CUDA kernels + C-ABI (include/aindex_cuda.h), sm_100a
   aindex_b200/core/aindex_cpp<EXT_SUFFIX>  pybind11 module mirroring the reference's aindex_cpp
-  aindex_b200/bin/{count_kmers13,compute_aindex,compute_aindex13}  GPU executables
+  aindex_b200/bin/{count_kmers13,compute_aindex,compute_aindex13,compute_reads}  drop-in executables
 
 nvcc cross-compiles without a GPU; the .so files are git-ignored and travel to the GPU box
 with the source snapshot.
@@ -93,7 +93,7 @@ def build_pybind(force: bool = False) -> str | None:
 def build_bins(force: bool = False):
     outs = []
     bindir = os.path.join(HERE, "bin")
-    for name in ("count_kmers13", "compute_aindex", "compute_aindex13"):
+    for name in ("count_kmers13", "compute_aindex", "compute_aindex13", "compute_reads"):
         src = os.path.join(CSRC, "tools", name + ".cpp")
         if not os.path.exists(src):
             continue

@@ -594,6 +594,49 @@ public:
         if (e > reads_size || s > e) return "";
         return std::string(reads + s, e - s);
     }
+    // batched forms (additions): the same lookups for whole arrays, GIL released, no per-read Python objects
+    py::tuple get_reads_by_rids(py::array_t<uint64_t, py::array::c_style | py::array::forcecast> rids) {
+        const uint64_t q = (uint64_t)rids.size();
+        const uint64_t *r = rids.data();
+        py::array_t<uint64_t> offs((py::ssize_t)q + 1);
+        uint64_t *o = offs.mutable_data();
+        o[0] = 0;
+        std::vector<std::pair<uint64_t, uint64_t>> span(q);
+        for (uint64_t i = 0; i < q; ++i) {  // get_read_by_rid (:666-675): "" for an unknown rid
+            uint64_t s = 0, e = 0;
+            if (r[i] < start_positions.size() && reads) {
+                s = start_positions[r[i]];
+                auto it = start2end.find(s);
+                e = it == start2end.end() ? s : it->second;
+                if (e > reads_size || s > e) s = e = 0;
+            }
+            span[i] = {s, e};
+            o[i + 1] = o[i] + (e - s);
+        }
+        std::string out((size_t)o[q], '\0');
+        {
+            py::gil_scoped_release nogil;
+            for (uint64_t i = 0; i < q; ++i)
+                if (span[i].second > span[i].first) memcpy(&out[(size_t)o[i]], reads + span[i].first, (size_t)(span[i].second - span[i].first));
+        }
+        return py::make_tuple(py::bytes(out), offs);
+    }
+    py::tuple get_rids_and_starts(py::array_t<uint64_t, py::array::c_style | py::array::forcecast> positions) {
+        const uint64_t q = (uint64_t)positions.size();
+        const uint64_t *p = positions.data();
+        py::array_t<uint64_t> rid((py::ssize_t)q), st((py::ssize_t)q);
+        uint64_t *pr = rid.mutable_data(), *ps = st.mutable_data();
+        const bool ok = aindex_loaded && !intervals.empty();
+        {
+            py::gil_scoped_release nogil;
+            for (uint64_t i = 0; i < q; ++i) {  // get_rid / get_start (:757-789), quirk 2.3#10 included
+                const Interval *iv = ok ? find_interval(p[i], p[i] + 1) : nullptr;
+                pr[i] = iv ? iv->rid : 0;
+                ps[i] = iv ? iv->start : 0;
+            }
+        }
+        return py::make_tuple(rid, st);
+    }
     std::string get_read(uint64_t start, uint64_t end, bool revcomp = false) {  // :677-698
         if (!reads || start >= reads_size || end >= reads_size || start > end) return "";
         std::string read(reads + start, end - start);
@@ -929,6 +972,10 @@ PYBIND11_MODULE(aindex_cpp, m) {
         .def("get_rid", &AindexWrapper::get_rid)
         .def("get_start", &AindexWrapper::get_start)
         .def("get_read_by_rid", &AindexWrapper::get_read_by_rid)
+        .def("get_reads_by_rids", &AindexWrapper::get_reads_by_rids, py::arg("rids"),
+             "batched get_read_by_rid: (concatenated bytes, uint64 offsets[q+1])")
+        .def("get_rids_and_starts", &AindexWrapper::get_rids_and_starts, py::arg("positions"),
+             "batched get_rid / get_start: (uint64 rids[q], uint64 starts[q])")
         .def("get_read", &AindexWrapper::get_read, py::arg("start"), py::arg("end"), py::arg("revcomp") = false)
         .def("get_reads_se_by_kmer", &AindexWrapper::get_reads_se_by_kmer)
         .def("get_positions", &AindexWrapper::get_positions)

@@ -107,6 +107,12 @@ def test_wrapper_positions_and_reads(wrapper, g23, golden_dir):
     assert [wrapper.get_start(int(p)) for p in gr["pos"]] == gr["start"].tolist()
     assert [wrapper.get_read_by_rid(int(r)).encode() for r in gr["read_rid"]] == gr["read_str"].tolist()
     assert [wrapper.get_read(int(a), int(b), bool(c)).encode() for a, b, c in gr["span"]] == gr["span_str"].tolist()
+    # batched forms agree with the single calls (which agree with the reference module's recorded answers)
+    rid_b, start_b = wrapper.get_rids_and_starts(gr["pos"].astype(np.uint64))
+    assert rid_b.tolist() == gr["rid"].tolist() and start_b.tolist() == gr["start"].tolist()
+    rr = np.concatenate([gr["read_rid"].astype(np.uint64), np.array([10**9], dtype=np.uint64)])  # + an unknown rid -> ""
+    blob, offs = wrapper.get_reads_by_rids(rr)
+    assert [blob[int(offs[i]):int(offs[i + 1])] for i in range(rr.size)] == gr["read_str"].tolist() + [b""]
     some = q[int(g23["pos_qidx"][0])]
     got = wrapper.get_reads_se_by_kmer(some, 5)
     assert 1 <= len(got) <= 5 and all(some in r or some.translate(comp)[::-1] in r for r in got)
