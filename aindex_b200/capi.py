@@ -35,6 +35,15 @@ class CountStats(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class MultiBuildStats(C.Structure):
+    _fields_ = [("total_ms", C.c_double), ("upload_scan_ms", C.c_double), ("emit_partition_ms", C.c_double),
+                ("exchange_ms", C.c_double), ("sort_finalize_ms", C.c_double), ("download_ms", C.c_double),
+                ("keys", C.c_uint64), ("peer_bytes", C.c_uint64), ("positions", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/aindex_cuda.h declares
@@ -115,6 +124,7 @@ SIGNATURES = {
     "aix_multi_last_error": (C.c_char_p, [_vp]),
     "aix_count13_multi": (_i, [_vp, _vp, _vp, _u64, _i, _vp, C.POINTER(CountStats)]),
     "aix_count13_multi_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(CountStats)]),
+    "aix_positions_build23_multi": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(MultiBuildStats)]),
     "aix_coverage": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _i, _u32, _vp]),
     "aix_coverage_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _u64, _i, _u32, _vp]),
     "aix_positions_total23": (_i, [_vp, _vp, _vp]),
@@ -135,6 +145,7 @@ SIGNATURES = {
     "aix_canonical23_result_dev": (_i, [_vp, _pp, _pp, _vp]),
     "aix_write_dat": (_i, [_vp, _vp, _vp, _u64, C.c_char_p, C.c_char_p]),
     "aix_sort_u64_dev": (_i, [_vp, _vp, _vp, _u64, _i, _i, C.POINTER(_i)]),
+    "aix_partition_u64_dev": (_i, [_vp, _vp, _vp, _u64, _vp, _i, _vp]),
     "aix_rle_u64_dev": (_i, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
 }
 

@@ -157,6 +157,12 @@ static inline void aix_pool_free(aix_ctx *ctx, void *p, cudaStream_t st) {
     else cudaFree(p);
 }
 
+struct aix_multi {  // multi.cu: one ctx (and one host thread at a time) per GPU of one box, one process
+    std::vector<aix_ctx *> ctx;
+    bool peer_ok = false;
+    std::string err;
+};
+
 #define AIX_CUDA(ctx, call)                                                                      \
     do {                                                                                         \
         cudaError_t e__ = (call);                                                                \

@@ -85,13 +85,14 @@ constexpr int kEmitThreads = 256;
 constexpr int kEmitItems = 8;
 constexpr int kEmitTile = kEmitThreads * kEmitItems;  // windows per CTA
 
-// keys[r] = (bucket << pos_bits) | (i + 1) for the r-th window (in order of i) that has a bucket.  The tile's
+// keys[r] = (bucket << pos_bits) | (pos_base + i + 1) for the r-th window (in order of i) that has a bucket (pos_base =
+// offset of this image inside the whole reads file when the file is sharded over GPUs, else 0).  The tile's
 // keys are staged in shared memory, counted with ballots in window order, and the tile's first output slot comes
 // from a decoupled look-back over the earlier tiles (scan.cuh).  Keys beyond `cap` are counted but not stored;
 // the last tile stores the grand total in *n_valid.
 template <int K>
 __global__ void __launch_bounds__(kEmitThreads) positions_emit_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ reads,
-                                                                    uint64_t start, uint64_t n_win_end, int pos_bits,
+                                                                    uint64_t start, uint64_t n_win_end, uint64_t pos_base, int pos_bits,
                                                                     uint64_t *__restrict__ keys, uint64_t cap,
                                                                     unsigned long long *__restrict__ status,
                                                                     unsigned int *__restrict__ tile_counter,
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kEmitThreads) positions_emit_kernel(Index23Dev
         const uint64_t i = base + (uint64_t)j * kEmitThreads + tid;
         uint64_t h = kNoBucket;
         if (i < n_win_end) h = K == 23 ? bucket23(ix, m, reads + i) : bucket13(m, reads + i);
-        s_key[j * kEmitThreads + tid] = h == kNoBucket ? ~0ULL : ((h << pos_bits) | (i + 1));
+        s_key[j * kEmitThreads + tid] = h == kNoBucket ? ~0ULL : ((h << pos_bits) | (pos_base + i + 1));
     }
     // every thread reads back its own keys only: no barrier needed before the ballots
     uint32_t rank[kEmitItems];
@@ -153,52 +154,68 @@ __global__ void __launch_bounds__(kEmitThreads) positions_emit_kernel(Index23Dev
 }
 
 // normal case, one pass over the sorted keys: positions[j] = low word of key j, written to the spare buffer (the
-// keys stay intact), and the test that makes this valid -- key j lies inside the bucket that owns slot j, for every
-// j; with n_valid == sum(tf) that means every bucket holds exactly its tf occurrences.  Two keys per thread.
-__global__ void __launch_bounds__(256) positions_finalize_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
-                                                               const unsigned long long *__restrict__ indices,
+// keys stay intact), and the test that makes this valid -- key j lies inside the bucket that owns slot slot_base + j,
+// for every j; with n_valid == number of slots that means every bucket holds exactly its tf occurrences.  (slot_base
+// = first slot of this GPU's bucket range when the index is built by several GPUs, else 0.)  Two keys per thread.
+__global__ void __launch_bounds__(256) positions_finalize_kernel(const uint64_t *__restrict__ sorted, uint64_t n, uint64_t slot_base,
+                                                               int pos_bits, const unsigned long long *__restrict__ indices,
                                                                uint64_t n_buckets, unsigned long long *__restrict__ positions,
                                                                int *__restrict__ bad) {
     const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (j >= n) return;
-    const uint64_t mask = (1ULL << pos_bits) - 1;
+    const uint64_t mask = (1ULL << pos_bits) - 1, s0 = slot_base + j;
     bool ok = true;
     if (j + 1 < n) {
         const ulonglong2 k = __ldcs((const ulonglong2 *)(sorted + j));  // 16-byte aligned: j is even
         const uint64_t h0 = k.x >> pos_bits, h1 = k.y >> pos_bits;
-        ok = h0 < n_buckets && h1 < n_buckets && j >= indices[h0] && j < indices[h0 + 1] && j + 1 >= indices[h1] &&
-             j + 1 < indices[h1 + 1];
+        ok = h0 < n_buckets && h1 < n_buckets && s0 >= indices[h0] && s0 < indices[h0 + 1] && s0 + 1 >= indices[h1] &&
+             s0 + 1 < indices[h1 + 1];
         __stcs((ulonglong2 *)(positions + j), make_ulonglong2(k.x & mask, k.y & mask));
     } else {
         const uint64_t k = sorted[j], h = k >> pos_bits;
-        ok = h < n_buckets && j >= indices[h] && j < indices[h + 1];
+        ok = h < n_buckets && s0 >= indices[h] && s0 < indices[h + 1];
         positions[j] = k & mask;
     }
     if (!ok) *bad = 1;
 }
 
-// general case: first sorted slot of every bucket that occurs ...
-__global__ void positions_run_start_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
+// general case: first sorted slot of every bucket that occurs (run_start is indexed by bucket - h_base) ...
+__global__ void positions_run_start_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits, uint64_t h_base,
                                            unsigned long long *__restrict__ run_start) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint64_t h = sorted[j] >> pos_bits;
-    if (j == 0 || (sorted[j - 1] >> pos_bits) != h) run_start[h] = j;
+    if (j == 0 || (sorted[j - 1] >> pos_bits) != h) run_start[h - h_base] = j;
 }
 
-// ... then the first tf[h] occurrences of every bucket go to positions[indices[h] ...]; the rest of the bucket
-// stays 0 (hash.cpp:1037-1041: slot >= tf is dropped; unfilled slots keep the zero of the allocation)
+// ... then the first tf[h] occurrences of every bucket go to positions[indices[h] - slot_base ...]; the rest of the
+// bucket stays 0 (hash.cpp:1037-1041: slot >= tf is dropped; unfilled slots keep the zero of the allocation)
 template <typename F>
-__global__ void positions_clip_kernel(F tf, const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits,
-                                      const unsigned long long *__restrict__ run_start,
+__global__ void positions_clip_kernel(F tf, const uint64_t *__restrict__ sorted, uint64_t n, int pos_bits, uint64_t h_base,
+                                      uint64_t slot_base, const unsigned long long *__restrict__ run_start,
                                       const unsigned long long *__restrict__ indices,
                                       unsigned long long *__restrict__ positions) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint64_t key = sorted[j];
     const uint64_t h = key >> pos_bits;
-    const uint64_t r = j - run_start[h];
-    if (r < tf(h)) positions[indices[h] + r] = key & ((1ULL << pos_bits) - 1);
+    const uint64_t r = j - run_start[h - h_base];
+    if (r < tf(h)) positions[indices[h] - slot_base + r] = key & ((1ULL << pos_bits) - 1);
+}
+
+// smallest bucket h with indices[h] >= target[r] (the owner boundaries of the multi-GPU build): one thread per target
+__global__ void positions_split_kernel(const unsigned long long *__restrict__ indices, uint64_t n_buckets,
+                                       const unsigned long long *__restrict__ target, int n_targets,
+                                       unsigned long long *__restrict__ out) {
+    const int r = threadIdx.x;
+    if (r >= n_targets) return;
+    uint64_t lo = 0, hi = n_buckets;  // indices has n_buckets + 1 entries, non-decreasing
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (indices[mid] >= target[r]) hi = mid;
+        else lo = mid + 1;
+    }
+    out[r] = lo;
 }
 
 // ---- K7 query ----------------------------------------------------------------------------
@@ -295,123 +312,160 @@ static int bit_length(uint64_t x) {
     return b;
 }
 
+#define PB_FAIL(ctx, e__) (ctx)->fail((e__) == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA, "positions build %s:%d: %s", \
+                                      __FILE__, __LINE__, cudaGetErrorString(e__))
+
+// One key per occurrence of the windows [start, n_win_end) of an image in HBM, in position order, into *keys_out (pool
+// memory, `cap` entries; *cap_io = 0 asks for the exact size: sum(tf) first, then the true count if that was too small).
+template <int K>
+static int emit_keys(aix_ctx *ctx, cudaStream_t st, Index23Dev id, MphfDev md, const uint8_t *reads_dev, uint64_t start, uint64_t n_win_end,
+                     uint64_t pos_base, int pos_bits, uint64_t first_cap, uint64_t **keys_out, uint64_t *cap_out, uint64_t *n_valid_out) {
+    *keys_out = nullptr;
+    *n_valid_out = 0;
+    const uint64_t n_win = n_win_end - start;
+    const uint64_t e_tiles = (n_win + kEmitTile - 1) / kEmitTile;
+    if (e_tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "positions build: reads image too large");
+    // emit scratch: [0] n_valid, [1] tile counter, [8 ...] one look-back word per tile
+    unsigned long long *scratch = nullptr;
+    uint64_t *keys = nullptr;
+    cudaError_t e = aix_pool_alloc(ctx, &scratch, (8 + e_tiles) * 8, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return PB_FAIL(ctx, e); }
+    unsigned long long n_valid = 0;
+    uint64_t cap = first_cap ? first_cap : 1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        e = aix_pool_alloc(ctx, &keys, cap * 8, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, (8 + e_tiles) * 8, st);
+        if (e == cudaSuccess) {
+            positions_emit_kernel<K><<<(unsigned)e_tiles, kEmitThreads, 0, st>>>(id, md, reads_dev, start, n_win_end, pos_base, pos_bits, keys, cap,
+                                                                                scratch + 8, (unsigned int *)(scratch + 1), scratch);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&n_valid, scratch, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            aix_pool_free(ctx, keys, st); aix_pool_free(ctx, scratch, st);
+            return PB_FAIL(ctx, e);
+        }
+        if (n_valid <= cap) break;
+        // more occurrences in the reads than the index's tf sums to (index counted on other reads): all of them must be
+        // ordered before the first tf of every bucket can be picked -- emit again with room for all
+        aix_pool_free(ctx, keys, st);
+        keys = nullptr;
+        cap = n_valid;
+    }
+    aix_pool_free(ctx, scratch, st);
+    *keys_out = keys;
+    *cap_out = cap;
+    *n_valid_out = n_valid;
+    return AIX_OK;
+}
+
+// Sorted keys -> the slots [slot_base, slot_base + slot_count) of positions[] (the buckets [h_base, h_base + h_count)).
+// `sorted` and `spare` (same capacity, may be null) are pool buffers that this function takes over: one of them becomes
+// *positions_out in the normal case.
+template <typename F>
+static int finish_sorted(aix_ctx *ctx, cudaStream_t st, F tf, uint64_t *sorted, uint64_t *spare, uint64_t spare_cap, uint64_t n_valid,
+                         uint64_t slot_base, uint64_t slot_count, uint64_t h_base, uint64_t h_count,
+                         const unsigned long long *indices, uint64_t n_buckets, int pos_bits, unsigned long long **positions_out) {
+    *positions_out = nullptr;
+    int *bad_dev = nullptr;
+    unsigned long long *positions = nullptr, *run_start = nullptr;
+    auto done = [&](cudaError_t e) {
+        cudaGetLastError();
+        aix_pool_free(ctx, sorted, st); aix_pool_free(ctx, spare, st); aix_pool_free(ctx, bad_dev, st);
+        aix_pool_free(ctx, positions, st); aix_pool_free(ctx, run_start, st);
+        return PB_FAIL(ctx, e);
+    };
+    cudaError_t e;
+    int bad = 1;
+    if (n_valid == slot_count && spare && spare_cap >= slot_count && slot_count) {
+        if ((e = aix_pool_alloc(ctx, &bad_dev, sizeof(int), st)) != cudaSuccess) return done(e);
+        if ((e = cudaMemsetAsync(bad_dev, 0, sizeof(int), st)) != cudaSuccess) return done(e);
+        positions_finalize_kernel<<<aix_grid((n_valid + 1) / 2, 256), 256, 0, st>>>(sorted, n_valid, slot_base, pos_bits, indices, n_buckets,
+                                                                                 (unsigned long long *)spare, bad_dev);
+        ctx->launches++;
+        if ((e = cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(e);
+    }
+    if (!bad) {  // every bucket exactly full: the low words of the sorted keys are positions[]
+        positions = (unsigned long long *)spare;
+        spare = nullptr;
+    } else {
+        aix_pool_free(ctx, spare, st);
+        spare = nullptr;
+        if ((e = aix_pool_alloc(ctx, &positions, (slot_count ? slot_count : 1) * 8, st)) != cudaSuccess) return done(e);
+        if ((e = cudaMemsetAsync(positions, 0, (slot_count ? slot_count : 1) * 8, st)) != cudaSuccess) return done(e);
+        if (n_valid) {
+            if ((e = aix_pool_alloc(ctx, &run_start, (h_count ? h_count : 1) * 8, st)) != cudaSuccess) return done(e);
+            positions_run_start_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, h_base, run_start);
+            positions_clip_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(tf, sorted, n_valid, pos_bits, h_base, slot_base, run_start, indices, positions);
+            ctx->launches += 2;
+            if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
+        }
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(e);
+    }
+    aix_pool_free(ctx, sorted, st); aix_pool_free(ctx, bad_dev, st); aix_pool_free(ctx, run_start, st);
+    *positions_out = positions;
+    return AIX_OK;
+}
+
 // Device part of the build.  reads_dev must be readable for 8 bytes past len (aligned word
 // loads of the last windows); `start` = first_start of the image.  On success *indices_dev
-// (u64[n+1]) and *positions_dev (u64[total], at least one element) are owned by the caller.
+// (u64[n+1]) and *positions_dev (u64[total], at least one element) are owned by the caller (pool memory).
 template <int K, typename F>
 static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n, const uint8_t *reads_dev, uint64_t len,
                       uint64_t start, unsigned long long **indices_dev, unsigned long long **positions_dev,
                       uint64_t *total_out) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    unsigned long long *indices = nullptr, *positions = nullptr, *tiles = nullptr, *emit_scratch = nullptr, *run_start = nullptr;
-    uint64_t *keys = nullptr, *alt = nullptr;
-    auto cleanup_tmp = [&]() {
-        aix_pool_free(ctx, tiles, st); aix_pool_free(ctx, emit_scratch, st); aix_pool_free(ctx, run_start, st);
-        aix_pool_free(ctx, keys, st); aix_pool_free(ctx, alt, st);
-        tiles = emit_scratch = run_start = nullptr;
-        keys = alt = nullptr;
+    unsigned long long *indices = nullptr, *positions = nullptr, *tiles = nullptr;
+    cudaError_t e = aix_pool_alloc(ctx, &indices, (n + 1) * 8, st);
+    if (e == cudaSuccess) e = aix_pool_alloc(ctx, &tiles, scan_scratch_bytes(n), st);
+    auto bail = [&](int rc) {
+        aix_pool_free(ctx, indices, st); aix_pool_free(ctx, tiles, st);
+        return rc;
     };
-    auto cleanup = [&]() {
-        cleanup_tmp();
-        aix_pool_free(ctx, indices, st); aix_pool_free(ctx, positions, st);
-    };
-#define PB_CUDA(call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e__ = (call);                                                                       \
-        if (e__ != cudaSuccess) {                                                                       \
-            cudaGetLastError();                                                                         \
-            cleanup();                                                                                  \
-            return ctx->fail(e__ == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA,           \
-                             "positions build %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
-        }                                                                                               \
-    } while (0)
+    if (e != cudaSuccess) { cudaGetLastError(); return bail(PB_FAIL(ctx, e)); }
     AixTrace trace(st, "positions build");
-    PB_CUDA(aix_pool_alloc(ctx, &indices, (n + 1) * 8, st));
-    PB_CUDA(aix_pool_alloc(ctx, &tiles, scan_scratch_bytes(n), st));
     int rc = exclusive_scan(ctx, st, tf, n, indices, tiles);
-    if (rc != AIX_OK) { cleanup(); return rc; }
+    if (rc != AIX_OK) return bail(rc);
     unsigned long long total = 0;
-    PB_CUDA(cudaMemcpyAsync(&total, indices + n, 8, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
+    e = cudaMemcpyAsync(&total, indices + n, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaGetLastError(); return bail(PB_FAIL(ctx, e)); }
+    aix_pool_free(ctx, tiles, st);
+    tiles = nullptr;
     trace.mark("prefix sum of tf");
     const uint64_t n_win_end = len >= (uint64_t)K ? len - K + 1 : 0;
     const bool any_window = n && total && start < n_win_end;
     if (!any_window) {
-        PB_CUDA(aix_pool_alloc(ctx, &positions, (total ? total : 1) * 8, st));
-        PB_CUDA(cudaMemsetAsync(positions, 0, (total ? total : 1) * 8, st));
-        PB_CUDA(cudaStreamSynchronize(st));
+        e = aix_pool_alloc(ctx, &positions, (total ? total : 1) * 8, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(positions, 0, (total ? total : 1) * 8, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaGetLastError(); aix_pool_free(ctx, positions, st); return bail(PB_FAIL(ctx, e)); }
     } else {
         // key = bucket << pos_bits | position (1-based byte offset <= len)
         const int pos_bits = bit_length(len), h_bits = bit_length(n - 1) ? bit_length(n - 1) : 1;
-        if (pos_bits + h_bits > 64) {
-            cleanup();
-            return ctx->fail(AIX_ERR_ARG, "positions build: %d position bits + %d bucket bits do not fit a 64-bit key", pos_bits, h_bits);
-        }
-        const uint64_t n_win = n_win_end - start;
-        const uint64_t e_tiles = (n_win + kEmitTile - 1) / kEmitTile;
-        if (e_tiles >= (1ull << 31)) { cleanup(); return ctx->fail(AIX_ERR_ARG, "positions build: reads image too large"); }
-        // emit scratch: [0] n_valid, [1] tile counter, [2] bad flag, [8 ...] one look-back word per tile
-        PB_CUDA(aix_pool_alloc(ctx, &emit_scratch, (8 + e_tiles) * 8, st));
-        unsigned long long n_valid = 0;
-        uint64_t cap = total;  // the normal case needs exactly `total` keys; more valid windows than that = general case
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            PB_CUDA(aix_pool_alloc(ctx, &keys, cap * 8, st));
-            PB_CUDA(aix_pool_alloc(ctx, &alt, cap * 8, st));
-            PB_CUDA(cudaMemsetAsync(emit_scratch, 0, (8 + e_tiles) * 8, st));
-            positions_emit_kernel<K><<<(unsigned)e_tiles, kEmitThreads, 0, st>>>(id, md, reads_dev, start, n_win_end, pos_bits, keys, cap,
-                                                                                emit_scratch + 8, (unsigned int *)(emit_scratch + 1), emit_scratch);
-            ctx->launches++;
-            PB_CUDA(cudaGetLastError());
-            PB_CUDA(cudaMemcpyAsync(&n_valid, emit_scratch, 8, cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaStreamSynchronize(st));
-            if (n_valid <= cap) break;
-            // more occurrences in the reads than the index's tf sums to (index counted on other reads): all of them
-            // must be ordered before the first tf of every bucket can be picked -- emit again with room for all
-            aix_pool_free(ctx, keys, st); aix_pool_free(ctx, alt, st);
-            keys = alt = nullptr;
-            cap = n_valid;
-        }
+        if (pos_bits + h_bits > 64)
+            return bail(ctx->fail(AIX_ERR_ARG, "positions build: %d position bits + %d bucket bits do not fit a 64-bit key", pos_bits, h_bits));
+        uint64_t *keys = nullptr, *alt = nullptr, cap = 0, n_valid = 0;
+        // the normal case needs exactly `total` keys; more valid windows than that = general case (second attempt inside)
+        rc = emit_keys<K>(ctx, st, id, md, reads_dev, start, n_win_end, 0, pos_bits, total, &keys, &cap, &n_valid);
+        if (rc != AIX_OK) return bail(rc);
         trace.mark("emit pass (lookup + ordered compaction of one key per occurrence)");
+        e = aix_pool_alloc(ctx, &alt, cap * 8, st);
+        if (e != cudaSuccess) { cudaGetLastError(); aix_pool_free(ctx, keys, st); return bail(PB_FAIL(ctx, e)); }
         uint64_t *sorted = keys;
         rc = radix_sort_u64(ctx, st, keys, alt, n_valid, pos_bits, pos_bits + h_bits, &sorted);
-        if (rc != AIX_OK) { cleanup(); return rc; }
+        if (rc != AIX_OK) { aix_pool_free(ctx, keys, st); aix_pool_free(ctx, alt, st); return bail(rc); }
         trace.mark("radix sort on the bucket bits");
-        int bad = 1;
         uint64_t *spare = sorted == keys ? alt : keys;
-        if (n_valid == total) {
-            int *bad_dev = (int *)(emit_scratch + 2);
-            PB_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
-            positions_finalize_kernel<<<aix_grid((n_valid + 1) / 2, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, indices, n,
-                                                                                     (unsigned long long *)spare, bad_dev);
-            ctx->launches++;
-            PB_CUDA(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaStreamSynchronize(st));
-        }
-        if (!bad) {  // every bucket exactly full: the low words of the sorted keys are positions[]
-            positions = (unsigned long long *)spare;
-            aix_pool_free(ctx, sorted, st);
-            keys = alt = nullptr;
-            trace.mark("check + low words -> positions[] (one pass, out of place)");
-        } else {
-            aix_pool_free(ctx, spare, st);
-            if (sorted == keys) alt = nullptr; else keys = nullptr;
-            PB_CUDA(aix_pool_alloc(ctx, &positions, total * 8, st));
-            PB_CUDA(cudaMemsetAsync(positions, 0, total * 8, st));
-            if (n_valid) {
-                PB_CUDA(aix_pool_alloc(ctx, &run_start, n * 8, st));
-                positions_run_start_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(sorted, n_valid, pos_bits, run_start);
-                positions_clip_kernel<<<aix_grid(n_valid, 256), 256, 0, st>>>(tf, sorted, n_valid, pos_bits, run_start, indices, positions);
-                ctx->launches += 2;
-                PB_CUDA(cudaGetLastError());
-            }
-            PB_CUDA(cudaStreamSynchronize(st));
-            trace.mark("general case: clip the sorted occurrences to tf per bucket");
-        }
+        rc = finish_sorted(ctx, st, tf, sorted, spare, cap, n_valid, 0, total, 0, n, indices, n, pos_bits, &positions);
+        if (rc != AIX_OK) return bail(rc);
+        trace.mark("check + low words -> positions[] (or clip to tf per bucket)");
     }
-#undef PB_CUDA
-    cleanup_tmp();
-    trace.mark("free scratch");
     *indices_dev = indices;
     *positions_dev = positions;
     *total_out = total;
@@ -679,3 +733,224 @@ int aix_positions_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13
 }
 
 }  // extern "C"
+
+// ---- positions build over several GPUs of one box ------------------------------------------------
+// Reference: fill_index_from_reads splits the byte range of the reads file over worker threads (hash.hpp:407-444), all
+// of them scattering into one positions array.  Here the workers are GPUs: GPU r looks up the windows that start in its
+// byte range (index replicated) and emits packed keys in position order; the buckets are cut into one contiguous range
+// per GPU with equal numbers of slots; every GPU partitions its keys by owner (one stable pass, radix_sort.cu) and
+// copies each part straight into the owner's buffer over NVLink (part of GPU r before part of GPU r + 1: positions stay
+// ascending); the owner sorts what it received on the bucket bits and owns that slice of positions[].
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+namespace {
+
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n, waiting = 0;
+    uint64_t gen = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const uint64_t g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+double ms_since(double t0) { return (AixTrace::now() - t0) * 1e3; }
+
+}  // namespace
+
+extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *const *ix, const uint8_t *reads, uint64_t len,
+                                           uint64_t *indices_out, uint64_t *positions_out, aix_multi_build_stats *stats) {
+    if (!mg || !ix || !indices_out || (len && !reads) || mg->ctx.empty()) return AIX_ERR_ARG;
+    const int n = (int)mg->ctx.size();
+    if (n > 16) { mg->err = "at most 16 GPUs"; return AIX_ERR_ARG; }
+    for (int r = 0; r < n; ++r)
+        if (!ix[r] || ix[r]->n != ix[0]->n) { mg->err = "every GPU needs its own upload of the same index"; return AIX_ERR_ARG; }
+    constexpr int K = 23;
+    const uint64_t nb = ix[0]->n;
+    const uint64_t n_win_end = len >= (uint64_t)K ? len - K + 1 : 0;
+    const uint64_t first = first_start(reads, len, K);
+    const int pos_bits = bit_length(len) ? bit_length(len) : 1, h_bits = bit_length(nb ? nb - 1 : 0) ? bit_length(nb ? nb - 1 : 0) : 1;
+    if (pos_bits + h_bits > 64) { mg->err = "position bits + bucket bits do not fit a 64-bit key"; return AIX_ERR_ARG; }
+    // byte ranges: windows that START in [c[r], c[r+1]) belong to GPU r (it also gets the K - 1 bytes that follow)
+    std::vector<uint64_t> c(n + 1);
+    for (int r = 0; r <= n; ++r) c[r] = first + (n_win_end > first ? (n_win_end - first) * (uint64_t)r / (uint64_t)n : 0);
+    struct PerGpu {
+        uint8_t *reads_dev = nullptr;
+        unsigned long long *indices = nullptr, *positions = nullptr;
+        uint64_t *keys = nullptr, *part = nullptr, *recv = nullptr, *alt = nullptr;
+        uint64_t n_valid = 0, recv_total = 0;
+    };
+    std::vector<PerGpu> g(n);
+    std::vector<uint64_t> counts((size_t)n * n, 0), bounds(n + 1, 0), slot_lo(n + 1, 0);
+    unsigned long long total = 0;
+    std::vector<int> rcs(n, AIX_OK);
+    std::vector<double> t_emit(n, 0), t_exch(n, 0), t_sort(n, 0), t_up(n, 0), t_down(n, 0);
+    HostBarrier bar(n);
+    auto any_failed = [&]() { for (int r = 0; r < n; ++r) if (rcs[r] != AIX_OK) return true; return false; };
+    const double t_all = AixTrace::now();
+    auto worker = [&](int r) {
+        aix_ctx *ctx = mg->ctx[r];
+        cudaStream_t st = ctx->stream;
+        PerGpu &me = g[r];
+        auto fail_cuda = [&](cudaError_t e) { cudaGetLastError(); rcs[r] = PB_FAIL(ctx, e); };
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) fail_cuda(e);
+        const uint64_t lo = c[r], hi = c[r + 1];
+        const uint64_t img_len = hi > lo ? (hi - lo) + K - 1 : 0;   // bytes [lo, hi + K - 1) <= len
+        double t0 = AixTrace::now();
+        // ---- phase 1: upload the shard, prefix sum of tf (every GPU keeps the offsets: its finalize pass needs them)
+        if (rcs[r] == AIX_OK) {
+            e = aix_pool_alloc(ctx, &me.reads_dev, img_len + 64, st);
+            if (e == cudaSuccess && img_len) e = cudaMemcpyAsync(me.reads_dev, reads + lo, img_len, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(me.reads_dev + img_len, '\n', 64, st);
+            unsigned long long *tiles = nullptr;
+            if (e == cudaSuccess) e = aix_pool_alloc(ctx, &me.indices, (nb + 1) * 8, st);
+            if (e == cudaSuccess) e = aix_pool_alloc(ctx, &tiles, scan_scratch_bytes(nb), st);
+            if (e != cudaSuccess) fail_cuda(e);
+            else {
+                int rc = exclusive_scan(ctx, st, TfFromRecs{ix[r]->recs_dev}, nb, me.indices, tiles);
+                if (rc != AIX_OK) rcs[r] = rc;
+            }
+            aix_pool_free(ctx, tiles, st);
+            if (rcs[r] == AIX_OK && r == 0) {
+                // owner boundaries: equal numbers of slots per GPU
+                e = cudaMemcpyAsync(&total, me.indices + nb, 8, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                unsigned long long *tgt = nullptr;
+                std::vector<unsigned long long> h_t(2 * (n + 1));
+                for (int o = 0; o <= n; ++o) h_t[o] = (unsigned long long)((unsigned __int128)total * (unsigned)o / (unsigned)n);
+                if (e == cudaSuccess) e = aix_pool_alloc(ctx, &tgt, 2 * (n + 1) * 8, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(tgt, h_t.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) {
+                    positions_split_kernel<<<1, 32, 0, st>>>(me.indices, nb, tgt, n + 1, tgt + (n + 1));
+                    ctx->launches++;
+                    e = cudaMemcpyAsync(h_t.data() + (n + 1), tgt + (n + 1), (n + 1) * 8, cudaMemcpyDeviceToHost, st);
+                }
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) {
+                    for (int o = 0; o <= n; ++o) bounds[o] = h_t[n + 1 + o];
+                    bounds[0] = 0;
+                    bounds[n] = nb;
+                    for (int o = 1; o < n; ++o) if (bounds[o] < bounds[o - 1]) bounds[o] = bounds[o - 1];
+                    for (int o = 0; o <= n && e == cudaSuccess; ++o)
+                        e = cudaMemcpyAsync(&slot_lo[o], me.indices + bounds[o], 8, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                }
+                aix_pool_free(ctx, tgt, st);
+                if (e != cudaSuccess) fail_cuda(e);
+            }
+            if (rcs[r] == AIX_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail_cuda(e);
+        }
+        t_up[r] = ms_since(t0);
+        bar.wait();
+        // ---- phase 2: emit keys in position order, partition them by owner
+        t0 = AixTrace::now();
+        if (!any_failed() && hi > lo && nb && total) {
+            uint64_t cap = 0;
+            int rc = emit_keys<K>(ctx, st, ix[r]->dev(), ix[r]->mphf_dev(), me.reads_dev, 0, hi - lo, lo, pos_bits, hi - lo, &me.keys, &cap, &me.n_valid);
+            if (rc == AIX_OK) {
+                e = aix_pool_alloc(ctx, &me.part, (me.n_valid ? me.n_valid : 1) * 8, st);
+                if (e != cudaSuccess) fail_cuda(e);
+                else {
+                    std::vector<uint64_t> kb(n);
+                    for (int o = 0; o < n; ++o) kb[o] = bounds[o] << pos_bits;
+                    rc = partition_by_range(ctx, st, me.keys, me.part, me.n_valid, kb.data(), n, &counts[(size_t)r * n]);
+                }
+            }
+            if (rc != AIX_OK && rcs[r] == AIX_OK) rcs[r] = rc;
+            aix_pool_free(ctx, me.keys, st);
+            me.keys = nullptr;
+        }
+        aix_pool_free(ctx, me.reads_dev, st);
+        me.reads_dev = nullptr;
+        t_emit[r] = ms_since(t0);
+        bar.wait();
+        // ---- phase 3: every owner makes room for what it will receive
+        t0 = AixTrace::now();
+        if (!any_failed()) {
+            for (int s2 = 0; s2 < n; ++s2) me.recv_total += counts[(size_t)s2 * n + r];
+            e = aix_pool_alloc(ctx, &me.recv, (me.recv_total ? me.recv_total : 1) * 8, st);
+            if (e == cudaSuccess) e = aix_pool_alloc(ctx, &me.alt, (me.recv_total ? me.recv_total : 1) * 8, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) fail_cuda(e);
+        }
+        bar.wait();
+        // ---- phase 4: the exchange -- part o of this GPU goes to owner o, behind the parts of the GPUs before this one
+        if (!any_failed()) {
+            uint64_t seg = 0;
+            for (int o = 0; o < n && rcs[r] == AIX_OK; ++o) {
+                const uint64_t cnt = counts[(size_t)r * n + o];
+                uint64_t off = 0;
+                for (int s2 = 0; s2 < r; ++s2) off += counts[(size_t)s2 * n + o];
+                if (cnt) {
+                    e = o == r ? cudaMemcpyAsync(g[o].recv + off, me.part + seg, cnt * 8, cudaMemcpyDeviceToDevice, st)
+                               : cudaMemcpyPeerAsync(g[o].recv + off, mg->ctx[o]->device, me.part + seg, ctx->device, cnt * 8, st);
+                    if (e != cudaSuccess) fail_cuda(e);
+                }
+                seg += cnt;
+            }
+            if (rcs[r] == AIX_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail_cuda(e);
+        }
+        aix_pool_free(ctx, me.part, st);
+        me.part = nullptr;
+        t_exch[r] = ms_since(t0);
+        bar.wait();
+        // ---- phase 5: sort the received keys on the bucket bits, turn them into this GPU's slice of positions[]
+        t0 = AixTrace::now();
+        if (!any_failed()) {
+            uint64_t *sorted = me.recv;
+            int rc = radix_sort_u64(ctx, st, me.recv, me.alt, me.recv_total, pos_bits, pos_bits + h_bits, &sorted);
+            if (rc == AIX_OK) {
+                uint64_t *spare = sorted == me.recv ? me.alt : me.recv;
+                me.recv = me.alt = nullptr;  // finish_sorted takes both over
+                rc = finish_sorted(ctx, st, TfFromRecs{ix[r]->recs_dev}, sorted, spare, me.recv_total ? me.recv_total : 1, me.recv_total,
+                                   slot_lo[r], slot_lo[r + 1] - slot_lo[r], bounds[r], bounds[r + 1] - bounds[r], me.indices, nb, pos_bits,
+                                   &me.positions);
+            }
+            if (rc != AIX_OK) rcs[r] = rc;
+        }
+        t_sort[r] = ms_since(t0);
+        // ---- phase 6: download the slice (and the offsets, from GPU 0)
+        t0 = AixTrace::now();
+        if (rcs[r] == AIX_OK && !any_failed()) {
+            const uint64_t cnt = slot_lo[r + 1] - slot_lo[r];
+            e = cudaSuccess;
+            if (cnt && positions_out) e = cudaMemcpyAsync(positions_out + slot_lo[r], me.positions, cnt * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && r == 0) e = cudaMemcpyAsync(indices_out, me.indices, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) fail_cuda(e);
+        }
+        t_down[r] = ms_since(t0);
+        aix_pool_free(ctx, me.recv, st); aix_pool_free(ctx, me.alt, st);
+        aix_pool_free(ctx, me.positions, st); aix_pool_free(ctx, me.indices, st);
+        cudaStreamSynchronize(st);
+        bar.wait();
+    };
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < n; ++r) th.emplace_back(worker, r);
+        for (auto &x : th) x.join();
+    }
+    for (int r = 0; r < n; ++r)
+        if (rcs[r] != AIX_OK) { mg->err = aix_last_error(mg->ctx[r]); return rcs[r]; }
+    if (stats) {
+        auto mx = [&](const std::vector<double> &v) { double m = 0; for (double x : v) m = x > m ? x : m; return m; };
+        stats->total_ms = ms_since(t_all);
+        stats->upload_scan_ms = mx(t_up); stats->emit_partition_ms = mx(t_emit); stats->exchange_ms = mx(t_exch);
+        stats->sort_finalize_ms = mx(t_sort); stats->download_ms = mx(t_down);
+        uint64_t moved = 0, all = 0;
+        for (int r = 0; r < n; ++r)
+            for (int o = 0; o < n; ++o) { all += counts[(size_t)r * n + o]; if (o != r) moved += counts[(size_t)r * n + o]; }
+        stats->keys = all;
+        stats->peer_bytes = moved * 8;
+        stats->positions = total;
+    }
+    return AIX_OK;
+}

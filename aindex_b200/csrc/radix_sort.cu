@@ -19,6 +19,7 @@ constexpr int kRsItems = 16;
 constexpr int kRsMaxBits = 8;
 constexpr int kRsMaxRadix = 1 << kRsMaxBits;
 constexpr int kRsMaxPasses = 8;
+constexpr int kRsMaxRanges = 16;
 // stage[tile] (aliased by the per-warp histograms) + total[256] + dstart[256] + gbase[256]
 constexpr size_t rs_smem(int threads) { return (size_t)threads * kRsItems * 8 + kRsMaxRadix * 4 * 2 + kRsMaxRadix * 8; }
 
@@ -31,6 +32,42 @@ struct RsPlan {
         return w < bits ? w : bits;
     }
 };
+
+// the digit of a key: a bit field (the sort passes) or the index of the range that holds the key (stable partition
+// of packed keys by owner, positions.cu: range r = [bound[r], bound[r + 1]))
+struct BitsDigit {
+    int shift;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return (uint32_t)(k >> shift) & mask; }
+};
+struct RangeDigit {
+    unsigned long long bound[kRsMaxRanges];  // bound[0] = 0; entries from n_ranges on are unused
+    int n_ranges;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int r = 1; r < kRsMaxRanges; ++r)
+            if (r < n_ranges && k >= bound[r]) o = r;
+        return o;
+    }
+};
+
+// single-digit histogram for any digit functor (the range partition)
+template <typename Digit>
+__global__ void __launch_bounds__(512) rs_hist1_kernel(const uint64_t *__restrict__ keys, uint64_t n, Digit dg,
+                                                     unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t sh[kRsMaxRadix];
+    for (int i = threadIdx.x; i < kRsMaxRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per;
+    const uint64_t hi = lo + per < n ? lo + per : n;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[dg(keys[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRsMaxRadix; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
 
 // hist[p][d] += number of keys whose digit p is d, for every pass in one read of the keys
 __global__ void __launch_bounds__(512) rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, RsPlan plan,
@@ -65,9 +102,9 @@ __global__ void __launch_bounds__(kRsMaxRadix) rs_base_kernel(const unsigned lon
 
 // One digit pass.  Stable: equal digits keep their input order.  kRsThreads = 512 (8192-key tiles, 2 CTAs / SM) or
 // 256 (4096-key tiles, 4 CTAs / SM: same threads per SM, finer interleaving of the load / rank / look-back / store phases).
-template <int kRsThreads>
+template <int kRsThreads, typename Digit>
 __global__ void __launch_bounds__(kRsThreads, 1024 / kRsThreads)
-rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, int shift, int bits,
+rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, Digit dg, int bits,
                const unsigned long long *__restrict__ digit_base, unsigned long long *__restrict__ status,
                unsigned int *__restrict__ tile_counter) {
     constexpr int kRsTile = kRsThreads * kRsItems, kRsWarps = kRsThreads / 32;
@@ -81,7 +118,7 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
     __shared__ uint32_t s_wsum[kRsMaxRadix / 32];
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t radix = 1u << bits, mask = radix - 1u;
+    const uint32_t radix = 1u << bits;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (uint32_t i = tid; i < kRsWarps * radix; i += kRsThreads) whist[i] = 0;
     __syncthreads();
@@ -110,13 +147,13 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const bool valid = wbase + (j0 + u) * 32 < tile_n;
-            const uint32_t d = valid ? ((uint32_t)(key[j0 + u] >> shift) & mask) : 0xFFFFFFFFu;
+            const uint32_t d = valid ? dg(key[j0 + u]) : 0xFFFFFFFFu;
             peers[u] = __match_any_sync(0xFFFFFFFFu, d);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const bool valid = wbase + (j0 + u) * 32 < tile_n;
-            const uint32_t d = (uint32_t)(key[j0 + u] >> shift) & mask;
+            const uint32_t d = dg(key[j0 + u]);
             const uint32_t base = valid ? my_hist[d] : 0u;
             __syncwarp();
             if (valid && (peers[u] & lt) == 0u) my_hist[d] = base + __popc(peers[u]);
@@ -159,7 +196,7 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         if (wbase + j * 32 < tile_n) {
-            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+            const uint32_t d = dg(key[j]);
             pos[j] = (uint16_t)(pos[j] + my_hist[d] + s_dstart[d]);
         }
     }
@@ -195,7 +232,7 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
     __syncthreads();
     for (uint32_t i = tid; i < tile_n; i += kRsThreads) {
         const uint64_t k = stage[i];
-        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const uint32_t d = dg(k);
         out[s_gbase[d] + i] = k;
     }
 }
@@ -266,8 +303,9 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "radix sort: too many keys");
     static bool attr_set[64] = {};
     if (!attr_set[ctx->device & 63]) {
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(512)));
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<512, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(512)));
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, RangeDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
         attr_set[ctx->device & 63] = true;
     }
     AixTrace trace(st, "radix sort");
@@ -303,11 +341,11 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     for (int p = 0; p < plan.n_pass; ++p) {
         if ((e = cudaMemsetAsync(status, 0, (size_t)tiles * ((size_t)1 << plan.width(p)) * 8, st)) != cudaSuccess) return fail(e, "memset");
         if (threads == 256)
-            rs_pass_kernel<256><<<(unsigned)tiles, 256, smem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
-                                                                    base + p * kRsMaxRadix, status, counters + p);
+            rs_pass_kernel<256, BitsDigit><<<(unsigned)tiles, 256, smem, st>>>(src, dst, n, BitsDigit{plan.shift(p), (1u << plan.width(p)) - 1u}, plan.width(p),
+                                                                               base + p * kRsMaxRadix, status, counters + p);
         else
-            rs_pass_kernel<512><<<(unsigned)tiles, 512, smem, st>>>(src, dst, n, plan.shift(p), plan.width(p),
-                                                                    base + p * kRsMaxRadix, status, counters + p);
+            rs_pass_kernel<512, BitsDigit><<<(unsigned)tiles, 512, smem, st>>>(src, dst, n, BitsDigit{plan.shift(p), (1u << plan.width(p)) - 1u}, plan.width(p),
+                                                                               base + p * kRsMaxRadix, status, counters + p);
         ctx->launches++;
         trace.mark("digit pass");
         uint64_t *t = src; src = dst; dst = t;
@@ -317,6 +355,59 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return ctx->fail(AIX_ERR_CUDA, "radix sort run: %s", cudaGetErrorString(e));
     trace.mark("free scratch");
     *sorted = src;
+    return AIX_OK;
+}
+
+// Stable partition of n keys into n_ranges key ranges (bound[r] = first key of range r, bound[0] = 0): out = the keys
+// grouped by range in range order, input order kept inside a range; counts[r] = keys of range r (host array).
+int partition_by_range(aix_ctx *ctx, cudaStream_t st, const uint64_t *keys, uint64_t *out, uint64_t n, const uint64_t *bound,
+                       int n_ranges, uint64_t *counts) {
+    if (n_ranges < 1 || n_ranges > kRsMaxRanges) return ctx->fail(AIX_ERR_ARG, "partition: 1..%d ranges", kRsMaxRanges);
+    for (int r = 0; r < n_ranges; ++r) counts[r] = 0;
+    if (n == 0) return AIX_OK;
+    RangeDigit dg;
+    for (int r = 0; r < kRsMaxRanges; ++r) dg.bound[r] = r < n_ranges ? bound[r] : ~0ull;
+    dg.bound[0] = 0;
+    dg.n_ranges = n_ranges;
+    int bits = 1;
+    while ((1 << bits) < n_ranges) ++bits;
+    const uint64_t tiles = (n + 256 * kRsItems - 1) / (256 * kRsItems);
+    if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "partition: too many keys");
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, RangeDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
+        attr_set[ctx->device & 63] = true;
+    }
+    const size_t front = (size_t)kRsMaxRadix * 8 * 2 + 64;
+    const size_t status_bytes = (size_t)tiles * ((size_t)1 << bits) * 8;
+    unsigned char *scratch = nullptr;
+    cudaError_t e = aix_pool_alloc(ctx, &scratch, front + status_bytes, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_NOMEM, "partition scratch: %s", cudaGetErrorString(e));
+    }
+    unsigned long long *hist = (unsigned long long *)scratch, *base = hist + kRsMaxRadix;
+    unsigned int *counter = (unsigned int *)(base + kRsMaxRadix);
+    unsigned long long *status = (unsigned long long *)(scratch + front);
+    e = cudaMemsetAsync(scratch, 0, front + status_bytes, st);
+    unsigned hgrid = (unsigned)((n + 512ull * 64 - 1) / (512ull * 64));
+    const unsigned hmax = (unsigned)ctx->sm_count * 8u;
+    if (hgrid > hmax) hgrid = hmax;
+    if (hgrid < 1) hgrid = 1;
+    rs_hist1_kernel<RangeDigit><<<hgrid, 512, 0, st>>>(keys, n, dg, hist);
+    rs_base_kernel<<<1, kRsMaxRadix, 0, st>>>(hist, base);
+    rs_pass_kernel<256, RangeDigit><<<(unsigned)tiles, 256, rs_smem(256), st>>>(keys, out, n, dg, bits, base, status, counter);
+    ctx->launches += 3;
+    unsigned long long h[kRsMaxRanges];
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, hist, sizeof h, cudaMemcpyDeviceToHost, st);
+    aix_pool_free(ctx, scratch, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(AIX_ERR_CUDA, "partition: %s", cudaGetErrorString(e));
+    }
+    for (int r = 0; r < n_ranges; ++r) counts[r] = h[r];
     return AIX_OK;
 }
 
@@ -366,6 +457,13 @@ int aix_sort_u64_dev(aix_ctx *ctx, uint64_t *keys_dev, uint64_t *alt_dev, uint64
     AIX_TRY(radix_sort_u64(ctx, ctx->stream, keys_dev, alt_dev, n, begin_bit, end_bit, &sorted));
     *result_in_alt = sorted == alt_dev && sorted != keys_dev ? 1 : 0;
     return AIX_OK;
+}
+
+int aix_partition_u64_dev(aix_ctx *ctx, const uint64_t *keys_dev, uint64_t *out_dev, uint64_t n, const uint64_t *bounds,
+                          int n_ranges, uint64_t *counts_out) {
+    if (!ctx || !bounds || !counts_out || (n && (!keys_dev || !out_dev))) return AIX_ERR_ARG;
+    AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return partition_by_range(ctx, ctx->stream, keys_dev, out_dev, n, bounds, n_ranges, counts_out);
 }
 
 int aix_rle_u64_dev(aix_ctx *ctx, const uint64_t *sorted_dev, uint64_t n, uint64_t *uniq_dev, uint32_t *counts_dev,

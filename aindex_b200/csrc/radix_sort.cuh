@@ -14,4 +14,10 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
 int rle_u64(aix_ctx *ctx, cudaStream_t st, const uint64_t *sorted, uint64_t n, uint64_t *uniq, uint32_t *counts,
             uint64_t *n_runs);
 
+// Stable partition of n keys into n_ranges <= 16 key ranges (bound[r] = first key of range r; bound[0] is taken as 0):
+// out = the keys grouped by range, input order kept inside a range; counts[r] (host) = keys in range r.
+// Synchronises `st`.
+int partition_by_range(aix_ctx *ctx, cudaStream_t st, const uint64_t *keys, uint64_t *out, uint64_t n, const uint64_t *bound,
+                       int n_ranges, uint64_t *counts);
+
 }  // namespace aix

@@ -13,6 +13,10 @@
 // and a query is ~400 integer instructions, three independent 16-byte L2 loads (MPHF record), one
 // L2 byte (fingerprint) and one 16-byte HBM load ({checker, tf} record) when the fingerprint matches.
 // Latency is hidden by occupancy, not by intra-thread pipelining: the loads of a query depend on its hash.
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include "aix_internal.cuh"
 #include "batch_pipeline.cuh"
 #include "query23.cuh"
@@ -710,25 +714,28 @@ int launch_tf13(aix_ctx *ctx, const aix_index13 *ix, cudaStream_t st, const uint
 // host spins on the answer: two PCIe traversals per call.  The kernel bounds its own life (idle timeout on
 // %globaltimer AND a hard cap of empty polls), so an implicit device synchronisation elsewhere waits a millisecond at
 // most; the host relaunches it on demand and falls back to the launch path if it ever fails to answer.
+// Slot layout (192 bytes of mapped host memory).  Request: six 16-byte chunks, each = 12 payload bytes + the sequence
+// number; the host writes every chunk with ONE 16-byte store, the device reads the first three chunks per poll (one
+// PCIe round trip: the loads are issued together) and accepts a request when their tags agree, so no ordering between
+// chunks is needed.  Payload bytes 0..1 = length, kind (23 / 13); bytes 2.. = the query.  Response: ONE 64-bit word
+// {tf, sequence number} written with one store -- no fence, no second word.  `alive` is cleared by the kernel's last store.
 struct MboxSlot {
-    // request line (host writes the payload, then req_seq)
-    uint32_t req_seq, len, kind, quit;      // kind: 23 or 13
-    uint8_t bytes[48];
-    // response line (device writes value, then resp_seq)
-    uint32_t resp_seq, pad[3];
-    uint64_t value[2];
-    uint8_t fill[32];
+    uint32_t req[6][4];      // [c][0..2] payload, [c][3] tag
+    unsigned long long resp; // (seq << 32) | tf
+    uint32_t quit, alive;
+    uint8_t fill[80];
 };
-static_assert(sizeof(MboxSlot) == 128, "mailbox slot layout");
+static_assert(sizeof(MboxSlot) == 192, "mailbox slot layout");
+constexpr uint32_t kMboxPayload = 6 * 12 - 2;  // query bytes a request can carry
 
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint4 ld_relaxed_sys_u32x4(const void *p) {
     uint4 v;
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint64_t global_timer_ns() {
@@ -744,45 +751,55 @@ __global__ void __launch_bounds__(32) mailbox_kernel(Index23Dev ix, MphfDev m23,
     uint64_t t_last = global_timer_ns();
     uint32_t empty = 0;
     for (;;) {
-        const uint32_t s = ld_acquire_sys_u32(&slot->req_seq);
-        if (s == seen) {
-            if (ld_acquire_sys_u32(&slot->quit) != 0u) break;
-            if (++empty > max_empty_polls || global_timer_ns() - t_last > idle_ns) break;
+        const uint4 c0 = ld_relaxed_sys_u32x4(slot->req[0]), c1 = ld_relaxed_sys_u32x4(slot->req[1]), c2 = ld_relaxed_sys_u32x4(slot->req[2]);
+        const uint32_t s = c0.w;
+        if (s == seen || c1.w != s || c2.w != s) {  // nothing new (or a request half written: the next poll sees the rest)
+            if ((++empty & 15u) == 0u) {
+                if (ld_relaxed_sys_u32(&slot->quit) != 0u) break;
+                if (empty > max_empty_polls || global_timer_ns() - t_last > idle_ns) break;
+            }
             continue;
         }
-        const uint4 h = ld_relaxed_sys_u32x4(slot);  // {req_seq, len, kind, quit}
-        uint32_t b[12];
-        {
-            const uint4 x0 = ld_relaxed_sys_u32x4(slot->bytes), x1 = ld_relaxed_sys_u32x4(slot->bytes + 16),
-                        x2 = ld_relaxed_sys_u32x4(slot->bytes + 32);
-            b[0] = x0.x; b[1] = x0.y; b[2] = x0.z; b[3] = x0.w; b[4] = x1.x; b[5] = x1.y; b[6] = x1.z; b[7] = x1.w;
-            b[8] = x2.x; b[9] = x2.y; b[10] = x2.z; b[11] = x2.w;
+        uint32_t b[18];  // payload words
+        b[0] = c0.x; b[1] = c0.y; b[2] = c0.z; b[3] = c1.x; b[4] = c1.y; b[5] = c1.z; b[6] = c2.x; b[7] = c2.y; b[8] = c2.z;
+        const uint32_t len0 = b[0] & 0xFFu, kind = (b[0] >> 8) & 0xFFu;
+        const uint32_t len = len0 > kMboxPayload ? kMboxPayload : len0;
+#pragma unroll
+        for (int j = 9; j < 18; ++j) b[j] = 0;
+        if (len > 34u) {  // long odd strings: the other three chunks (their tags must agree as well)
+            uint4 c3, c4, c5;
+            do {
+                c3 = ld_relaxed_sys_u32x4(slot->req[3]); c4 = ld_relaxed_sys_u32x4(slot->req[4]); c5 = ld_relaxed_sys_u32x4(slot->req[5]);
+            } while (c3.w != s || c4.w != s || c5.w != s);
+            b[9] = c3.x; b[10] = c3.y; b[11] = c3.z; b[12] = c4.x; b[13] = c4.y; b[14] = c4.z; b[15] = c5.x; b[16] = c5.y; b[17] = c5.z;
         }
-        const uint32_t len = h.y > 48u ? 48u : h.y;
+        // the query bytes start at payload byte 2: realign into words
+        uint32_t q[17];
+#pragma unroll
+        for (int j = 0; j < 17; ++j) q[j] = __funnelshift_r(b[j], b[j + 1], 16);
         uint64_t res[2] = {0, 0};
-        if (h.z == 23u) {
+        if (kind == 23u) {
             const uint64_t mask2 = len >= 23u ? 0x00FFFFFFFFFFFFFFull : (len > 16u ? ((1ull << (8 * (len - 16u))) - 1) : 0ull);
             const uint64_t mask1 = len >= 16u ? ~0ull : (len > 8u ? ((1ull << (8 * (len - 8u))) - 1) : 0ull);
             const uint64_t mask0 = len >= 8u ? ~0ull : ((1ull << (8 * len)) - 1);
-            const uint64_t r0 = (((uint64_t)b[1] << 32) | b[0]) & mask0, r1 = (((uint64_t)b[3] << 32) | b[2]) & mask1,
-                           r2 = (((uint64_t)b[5] << 32) | b[4]) & mask2;
-            const uint8_t *p = reinterpret_cast<const uint8_t *>(b);
+            const uint64_t r0 = (((uint64_t)q[1] << 32) | q[0]) & mask0, r1 = (((uint64_t)q[3] << 32) | q[2]) & mask1,
+                           r2 = (((uint64_t)q[5] << 32) | q[4]) & mask2;
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(q);
             if (ix.canonical_only) query23<AIX_Q_TF, true>(ix, m23, r0, r1, r2, len, p, 0, res);
             else query23<AIX_Q_TF, false>(ix, m23, r0, r1, r2, len, p, 0, res);
         } else {
             const uint64_t mask1 = len >= 13u ? 0x000000FFFFFFFFFFull : (len > 8u ? ((1ull << (8 * (len - 8u))) - 1) : 0ull);
             const uint64_t mask0 = len >= 8u ? ~0ull : ((1ull << (8 * len)) - 1);
-            const uint64_t w0 = (((uint64_t)b[1] << 32) | b[0]) & mask0, w1 = (((uint64_t)b[3] << 32) | b[2]) & mask1;
+            const uint64_t w0 = (((uint64_t)q[1] << 32) | q[0]) & mask0, w1 = (((uint64_t)q[3] << 32) | q[2]) & mask1;
             query13<AIX_Q_TF>(m13, tf13_mphf, tf13_direct, w0, w1, len, 0, res);
         }
-        slot->value[0] = res[0];
-        slot->value[1] = res[1];
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&slot->resp_seq), "r"(s) : "memory");
+        const unsigned long long word = ((unsigned long long)s << 32) | (res[0] & 0xFFFFFFFFull);
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&slot->resp), "l"(word) : "memory");
         seen = s;
         empty = 0;
         t_last = global_timer_ns();
     }
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&slot->alive), "r"(0u) : "memory");
 }
 
 void mbox_stop(aix_ctx *ctx) {
@@ -806,9 +823,9 @@ static bool mbox_enabled() {
 
 // one TF query (k = 23 on ix23, or k = 13 on ix13) through the mailbox; false = not answered (caller takes the launch path)
 static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *rec, uint32_t len, uint32_t *out) {
-    if (!mbox_enabled() || ctx->mbox_broken || len > 48) return false;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
+    if (!mbox_enabled() || ctx->mbox_broken || len > kMboxPayload) return false;
     if (!ctx->mbox_host) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaHostAlloc(&ctx->mbox_host, sizeof(MboxSlot), cudaHostAllocMapped) != cudaSuccess ||
@@ -823,13 +840,16 @@ static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 
     MboxSlot *slot = (MboxSlot *)ctx->mbox_host;
     const void *owner = ix23 ? (const void *)ix23 : (const void *)ix13;
     auto launch = [&](uint32_t seen) -> bool {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
+        if (ctx->mbox_launched) cudaStreamSynchronize(ctx->mbox_stream);  // the previous kernel has said it is leaving
         Index23Dev id = {};
         MphfDev m23 = {}, m13 = {};
         const uint64_t *t_m = nullptr, *t_d = nullptr;
         if (ix23) { id = ix23->dev(); m23 = ix23->mphf_dev(); }
         else { m13 = ix13->mphf->dev(); t_m = ix13->tf_mphf_dev; t_d = ix13->tf_direct_dev; }
+        __atomic_store_n(&slot->alive, 1u, __ATOMIC_RELEASE);
         mailbox_kernel<<<1, 32, 0, ctx->mbox_stream>>>(id, m23, m13, t_m, t_d, (MboxSlot *)ctx->mbox_dev, seen,
-                                                       2000000ull /* 2 ms idle */, 200000u);
+                                                       2000000ull /* 2 ms idle */, 400000u);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) return false;
         ctx->mbox_launched = true;
@@ -837,35 +857,51 @@ static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 
         return true;
     };
     if (ctx->mbox_launched && ctx->mbox_owner != owner) mbox_stop(ctx);
-    if (ctx->mbox_launched && cudaStreamQuery(ctx->mbox_stream) == cudaSuccess) ctx->mbox_launched = false;  // it idled out
-    if (!ctx->mbox_launched && !launch(ctx->mbox_seq)) {
-        ctx->mbox_broken = true;
-        return false;
+    if (!ctx->mbox_launched || __atomic_load_n(&slot->alive, __ATOMIC_ACQUIRE) == 0u) {
+        if (!launch(ctx->mbox_seq)) {
+            ctx->mbox_broken = true;
+            return false;
+        }
     }
-    // request: payload first, then the sequence number
-    slot->len = len;
-    slot->kind = ix23 ? 23u : 13u;
-    memset(slot->bytes, 0, sizeof slot->bytes);
-    memcpy(slot->bytes, rec, len);
+    // request: six 16-byte chunks {12 payload bytes, sequence number}; the first three cover a 23-byte query
     const uint32_t seq = ++ctx->mbox_seq;
-    __atomic_store_n(&slot->req_seq, seq, __ATOMIC_RELEASE);
+    alignas(16) uint8_t pay[72] = {0};
+    pay[0] = (uint8_t)len;
+    pay[1] = ix23 ? 23 : 13;
+    memcpy(pay + 2, rec, len);
+    const int n_chunks = len > 34u ? 6 : 3;
+    for (int c = n_chunks - 1; c >= 0; --c) {  // chunk 0 (the one the poll looks at first) last
+        alignas(16) uint32_t w[4];
+        memcpy(w, pay + 12 * c, 12);
+        w[3] = seq;
+#if defined(__x86_64__)
+        _mm_store_si128((__m128i *)slot->req[c], _mm_load_si128((const __m128i *)w));  // one 16-byte store
+#else
+        memcpy(slot->req[c], w, 12);
+        __atomic_store_n(&slot->req[c][3], seq, __ATOMIC_RELEASE);  // tag after its payload
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_RELEASE);
     const double t0 = AixTrace::now();
     for (uint32_t spin = 1;; ++spin) {
-        if (__atomic_load_n(&slot->resp_seq, __ATOMIC_ACQUIRE) == seq) break;
-        if ((spin & 0x3FFFu) == 0) {
-            if (cudaStreamQuery(ctx->mbox_stream) == cudaSuccess) {  // the kernel ended (idle timeout raced with this request)
-                if (__atomic_load_n(&slot->resp_seq, __ATOMIC_ACQUIRE) == seq) break;
+        const unsigned long long r = __atomic_load_n(&slot->resp, __ATOMIC_ACQUIRE);
+        if ((uint32_t)(r >> 32) == seq) {
+            *out = (uint32_t)r;
+            return true;
+        }
+        if ((spin & 0xFFu) == 0) {
+            if (__atomic_load_n(&slot->alive, __ATOMIC_ACQUIRE) == 0u) {  // the kernel left (its idle timeout raced with this request)
+                const unsigned long long r2 = __atomic_load_n(&slot->resp, __ATOMIC_ACQUIRE);
+                if ((uint32_t)(r2 >> 32) == seq) { *out = (uint32_t)r2; return true; }
                 if (!launch(seq - 1)) { ctx->mbox_broken = true; return false; }
             }
-            if (AixTrace::now() - t0 > 2.0) {  // never hang the caller: give the mailbox up for this ctx
+            if ((spin & 0xFFFFu) == 0 && AixTrace::now() - t0 > 2.0) {  // never hang the caller: give the mailbox up for this ctx
                 mbox_stop(ctx);
                 ctx->mbox_broken = true;
                 return false;
             }
         }
     }
-    *out = (uint32_t)slot->value[0];
-    return true;
 }
 
 }  // namespace aix

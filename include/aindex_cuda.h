@@ -282,6 +282,18 @@ int aix_count13_multi(aix_multi *mg, const aix_mphf *m, const uint8_t *bytes, ui
 int aix_count13_multi_dev(aix_multi *mg, const aix_mphf *m, const uint8_t *const *shards_dev, const uint64_t *lens, int fmt,
                           uint64_t *tf_out, aix_count_stats *stats);
 
+/* AIndexCompressed::fill_index_from_reads over the GPUs of mg (hash.hpp:407-444 splits the byte range of the reads file over
+ * worker threads): ix[r] = the same 23-mer index uploaded on the GPU of aix_multi_ctx(mg, r).  GPU r looks up the windows that
+ * start in its byte range; buckets are cut into one range per GPU with equal numbers of slots; keys go to the owner of their
+ * bucket by direct peer copies (NVLink), the owner sorts them and owns that slice of positions[].  Outputs are the arrays
+ * aix_positions_build23 gives (bit-identical), stats (nullable) the phase times (max over GPUs) and the bytes that crossed GPUs. */
+typedef struct aix_multi_build_stats {
+    double total_ms, upload_scan_ms, emit_partition_ms, exchange_ms, sort_finalize_ms, download_ms;
+    uint64_t keys, peer_bytes, positions;
+} aix_multi_build_stats;
+int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *const *ix, const uint8_t *reads, uint64_t len,
+                                uint64_t *indices_out, uint64_t *positions_out, aix_multi_build_stats *stats);
+
 /* ---- coverage: aindex/core/aindex.py:314-322 ------------------------------------- */
 /* n_seq sequences concatenated in `seqs`, sequence s = seqs[offs[s] .. offs[s+1]).
  * out holds sum_s max(0, len_s-k+1) values: out[.] = tf >= cutoff ? tf : 0.
@@ -364,6 +376,11 @@ int aix_write_dat(aix_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, u
  * alt_dev = spare buffer of n keys; *result_in_alt = 1 when the sorted keys ended up in alt_dev. */
 int aix_sort_u64_dev(aix_ctx *ctx, uint64_t *keys_dev, uint64_t *alt_dev, uint64_t n, int begin_bit, int end_bit,
                      int *result_in_alt);
+/* stable partition of n u64 keys into n_ranges <= 16 key ranges (bounds[r] = first key of range r, HOST array; bounds[0]
+ * counts as 0): out_dev = the keys grouped by range in range order, input order kept inside a range; counts_out[r] (HOST) =
+ * keys of range r.  The routing step of the multi-GPU positions build (keys to the owner of their bucket range). */
+int aix_partition_u64_dev(aix_ctx *ctx, const uint64_t *keys_dev, uint64_t *out_dev, uint64_t n, const uint64_t *bounds,
+                          int n_ranges, uint64_t *counts_out);
 /* run-length encoding of a sorted array (`uniq -c`): uniq_dev[r], counts_dev[r] for the *n_runs distinct keys */
 int aix_rle_u64_dev(aix_ctx *ctx, const uint64_t *sorted_dev, uint64_t n, uint64_t *uniq_dev, uint32_t *counts_dev,
                     uint64_t *n_runs);

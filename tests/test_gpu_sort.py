@@ -120,3 +120,78 @@ def test_write_dat_equals_the_oracle_writer(capi, oracle, ctx, golden_dir, tmp_p
     assert open(gd, "rb").read() == open(od, "rb").read() and open(gk, "rb").read() == open(okp, "rb").read()
     ctx.write_dat(k[:0], c[:0], gd, None)
     assert os.path.getsize(gd) == 0
+
+
+@pytest.mark.parametrize("n", [0, 1, 4095, 4096, 4097, 300_001])
+@pytest.mark.parametrize("n_ranges", [1, 2, 3, 8, 16])
+def test_partition_by_range_is_stable(capi, ctx, n, n_ranges):
+    """the routing pass of the multi-GPU positions build: keys grouped by key range, input order kept inside a range"""
+    import torch
+    rng = np.random.default_rng(n + n_ranges)
+    keys = rng.integers(0, 1 << 40, size=n, dtype=np.uint64)
+    bounds = np.sort(rng.integers(0, 1 << 40, size=n_ranges, dtype=np.uint64))
+    bounds[0] = 0
+    if n_ranges > 2:
+        bounds[2] = bounds[1]  # an empty range
+    k = torch.from_numpy(keys.view(np.int64).copy()).cuda()
+    out = torch.full_like(k, -1)
+    counts = np.zeros(n_ranges, dtype=np.uint64)
+    torch.cuda.synchronize()
+    ctx.check(capi.lib().aix_partition_u64_dev(ctx.handle, k.data_ptr(), out.data_ptr(), n, bounds.ctypes.data, n_ranges, counts.ctypes.data))
+    owner = np.searchsorted(bounds, keys, side="right") - 1
+    # ranges with equal bounds: the key belongs to the LAST range whose bound is <= key
+    want = keys[np.argsort(owner, kind="stable")]
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    assert np.array_equal(counts, np.bincount(owner, minlength=n_ranges).astype(np.uint64))
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 4])
+@pytest.mark.parametrize("regime", ["exact", "tf_smaller", "tf_larger"])
+def test_positions_build_multi_equals_single(capi, oracle, golden_dir, ranks, regime):
+    """aix_positions_build23_multi (reads sharded by byte range, keys routed to the owner of their bucket range, owner
+    sorts): bit-identical to the single-GPU build and to the reference's files.  On a 1-GPU box the contexts share
+    device 0 (peer copies become device copies); the sharding, routing, ordering and slicing logic is the same."""
+    import ctypes as C
+    import torch
+    lib = capi.lib()
+    n_dev = torch.cuda.device_count()
+    ids = list(range(ranks)) if n_dev >= ranks else [0] * ranks
+    mg = C.c_void_p()
+    assert lib.aix_multi_create(ranks, (C.c_int * ranks)(*ids), C.byref(mg)) == 0
+    oidx = oracle.Index23.load_prefix(os.path.join(golden_dir, "idx23"))
+    reads = np.fromfile(os.path.join(golden_dir, "idx23.reads"), dtype=np.uint8)
+    tf = oidx.tf.copy()
+    if regime == "tf_smaller":
+        tf = np.maximum(1, tf // 2)
+    elif regime == "tf_larger":
+        tf[::2] += 3
+    ctxs, ms, ixs = [], [], []
+    try:
+        for r in range(ranks):
+            c = capi.Context.__new__(capi.Context)
+            c._h = C.c_void_p(lib.aix_multi_ctx(mg, r))
+            ctxs.append(c)
+            m = capi.Mphf.from_arrays(c, oidx.mphf.n, oidx.mphf.hash_domain, oidx.mphf.seed, oidx.mphf.words, oidx.mphf.block_ranks)
+            ms.append(m)
+            ixs.append(capi.Index23.upload(c, m, oidx.checker, tf))
+        handles = (C.c_void_p * ranks)(*[ix._h for ix in ixs])
+        want_i, want_p = ixs[0].positions_build(reads)
+        if regime == "exact":
+            assert np.array_equal(want_p, np.fromfile(os.path.join(golden_dir, "idx23.index.bin"), dtype=np.uint64))
+        for img in (reads, reads[:-1], reads[:5000], reads[:30], np.frombuffer(b"\n~\n" + reads[:4000].tobytes(), dtype=np.uint8)):
+            wi, wp = ixs[0].positions_build(img)
+            gi = np.zeros(oidx.n + 1, dtype=np.uint64)
+            gp = np.full(max(1, wp.size), 0xDEAD, dtype=np.uint64)
+            st = capi.MultiBuildStats()
+            rc = lib.aix_positions_build23_multi(mg, handles, img.ctypes.data if img.size else None, img.size, gi.ctypes.data, gp.ctypes.data, C.byref(st))
+            assert rc == 0, lib.aix_multi_last_error(mg)
+            assert np.array_equal(gi, wi) and np.array_equal(gp[:wp.size], wp), (regime, ranks, img.size)
+            assert st.positions == wp.size
+    finally:
+        for ix in ixs:
+            ix.close()
+        for m in ms:
+            m.close()
+        for c in ctxs:
+            c._h = C.c_void_p()  # borrowed from the aix_multi
+        lib.aix_multi_destroy(mg)
