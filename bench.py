@@ -59,12 +59,16 @@ def parse_args():
     ap.add_argument("--count-genome", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi-legs", dest="multi_legs", action="store_false", default=True,
+                    help="skip the single-process (C-ABI) multi-GPU legs at N > 1")
+    ap.add_argument("--multi-positions-reads", type=int, default=50_000_000, help="reads of the N-GPU positions build (C5 = 50 M)")
     ap.add_argument("--configs", default="c4,c1,c5", help="other BASELINE configs measured at N=1 ('' = none)")
     ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the BASELINE sizes for --configs (smoke runs)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+from bench_common import PF13 as PF13_PATH  # noqa: E402
 from bench_common import (ClockSampler, _tmp_root, _wrap_device_i64, build_index, cpu_count_run, cpu_query_runs,  # noqa: E402,F401
                           make_hit_queries, make_queries, make_reads, ncu_traffic, peak_hbm_gbs, ref_harness_path,
                           write_index_files)
@@ -270,6 +274,138 @@ def count13_multi_gpu_vs_reference(torch, dist, capi, ctx, stream, dev, rank, wo
         import traceback
         traceback.print_exc()
         out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+
+def single_process_multi_legs(torch, capi, args, world, extra):
+    """aix_count13_multi_dev and aix_positions_build23_multi on all `world` GPUs from this one process (rank 0), while the
+    other ranks idle: (1) 13-mer counting, the same shards as the torchrun step (count + exchange, device resident), next
+    to the torchrun number; (2) the C5 positions index built by all GPUs -- bit-equality with the single-GPU build is
+    checked on a 5 M-read prefix (host arrays), the full 50 M-read build is timed with its phase times and the bytes that
+    crossed NVLink."""
+    import ctypes as C
+    lib = capi.lib()
+    out = {}
+    mg = C.c_void_p()
+    if lib.aix_multi_create(world, None, C.byref(mg)) != 0:
+        raise RuntimeError((lib.aix_multi_last_error(None) or b"").decode())
+    ctxs = []
+    try:
+        out["gpus"] = int(lib.aix_multi_size(mg))
+        out["peer_access"] = bool(lib.aix_multi_peer_access(mg))
+        for r in range(world):
+            c = capi.Context.__new__(capi.Context)
+            c._h = C.c_void_p(lib.aix_multi_ctx(mg, r))
+            ctxs.append(c)
+        # ---- (1) counting: one 25 M-read shard per GPU, generated on that GPU with the torchrun ranks' seeds
+        if args.count_reads > 0 and os.path.exists(PF13_PATH):
+            shards = []
+            for r in range(world):
+                d = torch.device("cuda", r)
+                with torch.cuda.device(d):
+                    shards.append(make_reads(torch, d, args.count_genome, args.count_reads, 150, 11, 12 + r).reshape(-1))
+                    torch.cuda.synchronize(d)
+            m13 = capi.Mphf.load(ctxs[0], PF13_PATH)
+            ptrs = (C.c_void_p * world)(*[t.data_ptr() for t in shards])
+            lens = (C.c_uint64 * world)(*[t.numel() for t in shards])
+            n_kmers = args.count_reads * 138 * world
+
+            def step(tf=None, st=None):
+                rc = lib.aix_count13_multi_dev(mg, m13._h, ptrs, lens, capi.FMT_PLAIN, tf, st)
+                if rc != 0:
+                    raise RuntimeError((lib.aix_multi_last_error(mg) or b"").decode())
+
+            for _ in range(2):
+                step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step()
+            dt = (time.perf_counter() - t0) / args.steps
+            st = capi.CountStats()
+            tf = np.zeros(1 << 26, dtype=np.uint64)
+            t0 = time.perf_counter()
+            step(tf.ctypes.data, C.byref(st))
+            full_s = time.perf_counter() - t0
+            torchrun = extra.get("count13", {}).get("value")
+            out["count13"] = {"value": n_kmers / dt, "unit": "k-mers/s", "ms_per_step": dt * 1e3,
+                              "what": "aix_count13_multi_dev: count + exchange over peer pointers, host wall clock around the call",
+                              "torchrun_value": torchrun, "ratio_to_torchrun": (n_kmers / dt) / torchrun if torchrun else None,
+                              "stats_ok": bool(st.valid == n_kmers and st.sequences == args.count_reads * world),
+                              "tf_sum_ok": bool(int(tf.sum()) == n_kmers),
+                              "with_permutation_and_download_ms": full_s * 1e3}
+            del shards, tf
+            lib.aix_mphf_destroy(ctxs[0]._h, m13._h)
+            m13._h = C.c_void_p()
+            for r in range(world):
+                with torch.cuda.device(r):
+                    torch.cuda.empty_cache()
+        # ---- (2) positions index over all GPUs
+        d0 = torch.device("cuda", 0)
+        n_reads = args.multi_positions_reads
+        with torch.cuda.device(d0):
+            reads = make_reads(torch, d0, 250_000_000 if n_reads >= 10_000_000 else 5 * n_reads, n_reads, 150, 31, 32)
+            n_bytes = reads.numel()
+            pad = torch.full((64,), 10, device=d0, dtype=torch.uint8)
+            reads = torch.cat([reads.reshape(-1), pad])
+            stream0 = torch.cuda.ExternalStream(ctxs[0].stream, device=d0)
+            torch.cuda.synchronize(d0)
+            res = {}
+            for tag, nr in (("check_5M_reads", min(n_reads, 5_000_000)), ("full", n_reads)):
+                nb = nr * 151
+                mphf, index, checker_t, tf_t, n_keys = build_index(torch, capi, ctxs[0], reads[:nb])
+                # replicate the index: the host arrays go to every other GPU
+                info = mphf.info
+                words, ranks = mphf.arrays()
+                chk_h, tf_h = checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32)
+                ms, ixs = [mphf], [index]
+                for r in range(1, world):
+                    m = capi.Mphf.from_arrays(ctxs[r], info["n"], info["hash_domain"], info["seed"], words, ranks)
+                    ms.append(m)
+                    ixs.append(capi.Index23.upload(ctxs[r], m, chk_h, tf_h))
+                handles = (C.c_void_p * world)(*[ix._h for ix in ixs])
+                r_host = ctxs[0].pinned((nb,), np.uint8)
+                torch.from_numpy(r_host).copy_(reads[:nb])
+                torch.cuda.synchronize(d0)
+                st = capi.MultiBuildStats()
+                gi = np.zeros(n_keys + 1, dtype=np.uint64)
+                if tag == "full":
+                    def build(pos_ptr=None):
+                        rc = lib.aix_positions_build23_multi(mg, handles, r_host.ctypes.data, nb, gi.ctypes.data, pos_ptr, C.byref(st))
+                        if rc != 0:
+                            raise RuntimeError((lib.aix_multi_last_error(mg) or b"").decode())
+                    build()  # warm-up (pools)
+                    build()
+                    dev_ms = st.emit_partition_ms + st.exchange_ms + st.sort_finalize_ms
+                    res[tag] = {"reads": nr, "index_keys": n_keys, "occurrences": int(st.positions), "stats": st.as_dict(),
+                                "value": st.positions / (dev_ms / 1e3), "unit": "occurrences/s (emit + exchange + sort phases, max over GPUs; "
+                                "reads upload and positions download excluded)", "device_phases_ms": dev_ms,
+                                "nvlink_bytes": int(st.peer_bytes), "single_gpu_ms": (extra.get("c5_positions") or {}).get("ms_per_step")}
+                else:
+                    gp = np.zeros(nr * 128, dtype=np.uint64)
+                    rc = lib.aix_positions_build23_multi(mg, handles, r_host.ctypes.data, nb, gi.ctypes.data, gp.ctypes.data, C.byref(st))
+                    if rc != 0:
+                        raise RuntimeError((lib.aix_multi_last_error(mg) or b"").decode())
+                    with torch.cuda.stream(stream0):
+                        pos = capi.Positions.build_dev(index, reads.data_ptr(), nb, 23)
+                        si, sp = pos.download()
+                        pos.close()
+                    res[tag] = {"reads": nr, "index_keys": n_keys, "indices_equal_single_gpu": bool(np.array_equal(gi, si)),
+                                "positions_equal_single_gpu": bool(np.array_equal(gp, sp)), "stats": st.as_dict()}
+                    del gp, si, sp
+                for ix in ixs:
+                    ix.close()
+                for m in ms:
+                    m.close()
+                del r_host, mphf, index, checker_t, tf_t
+                for c in ctxs:
+                    c.trim()
+                torch.cuda.empty_cache()
+            out["positions_build"] = res
+    finally:
+        for c in ctxs:
+            c._h = C.c_void_p()  # borrowed from the aix_multi
+        lib.aix_multi_destroy(mg)
     return out
 
 
@@ -656,6 +792,22 @@ def run_ours(args):
         if "c5" in names:
             extra["c5_positions"] = _guard(lambda: bench_configs.run_c5(ctx, stream, dev, cargs))
             torch.cuda.empty_cache()
+    # ---- N > 1: the same multi-GPU work from ONE process through the C-ABI (aix_multi: one context + one host thread per
+    #      GPU, no torch.distributed on the data path); the other ranks release their memory and wait
+    if world > 1 and args.multi_legs:
+        del index, mphf, checker_t, tf_t
+        torch.cuda.empty_cache()
+        ctx.trim()
+        barrier()
+        # the idle ranks wait on the rendezvous store, not in an NCCL kernel that would spin on the GPUs rank 0 is using
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            extra["single_process_multi_gpu"] = _guard(lambda: single_process_multi_legs(torch, capi, args, world, extra))
+            store.set("aix_multi_legs_done", "1")
+        else:
+            store.wait(["aix_multi_legs_done"], datetime.timedelta(minutes=30))
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:

@@ -16,3 +16,10 @@ ncu --set full --clock-control none --import-source on -k regex:"positions_emit|
 $CMD > gpurun_out/${TAG}_c5_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"rs_pass|rs_hist" -s 8 -c 3 -o gpurun_out/${TAG}_c5sort -f $CMD > gpurun_out/${TAG}_ncu_c5sort.log 2>&1
 ls -la gpurun_out/ | tail -12
+# C1 / C4 kernels at 5 % of the BASELINE sizes (traffic per unit for bench.py's roofline.traffic)
+for spec in "c1:tf13_stream_kernel:3:1" "c4:coverage_kernel:1:1"; do
+  IFS=: read cfg pat skip cnt <<< "$spec"
+  CMD="python bench_configs.py --configs $cfg --scale 0.05 --no-checks"
+  $CMD > gpurun_out/${TAG}_${cfg}_plain.log 2>&1 &&
+  ncu --set full --clock-control none -k regex:"$pat" -s $skip -c $cnt -o gpurun_out/${TAG}_${cfg} -f $CMD > gpurun_out/${TAG}_ncu_${cfg}.log 2>&1
+done

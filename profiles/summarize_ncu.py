@@ -3,7 +3,7 @@
 JSON summaries that are committed under profiles/.
 
   python profiles/summarize_ncu.py launches gpurun_out/<tag>_launches.csv  profiles/<name>.txt
-  python profiles/summarize_ncu.py kernel   gpurun_out/<tag>_<k>.ncu-rep   profiles/<name>.txt [traffic-key]
+  python profiles/summarize_ncu.py kernel   gpurun_out/<tag>_<k>.ncu-rep   profiles/<name>.txt [traffic-key [units-profiled]]
 
 `kernel` also updates profiles/traffic.json[traffic-key] = DRAM read+write bytes per launch,
 which bench.py reports as roofline.traffic (B200_PROFILING.md: from one `ncu --set full` capture).
@@ -74,7 +74,7 @@ def launches(src, dst):
     print(open(dst).read()[:3000])
 
 
-def kernel(src, dst, traffic_key=None):
+def kernel(src, dst, traffic_key=None, units_profiled=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -101,6 +101,8 @@ def kernel(src, dst, traffic_key=None):
         d = json.load(open(p)) if os.path.exists(p) else {}
         d[traffic_key] = {"bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic),
                           "source": os.path.relpath(dst, os.path.dirname(HERE))}
+        if units_profiled:
+            d[traffic_key]["units_profiled"] = int(units_profiled)  # bench.py scales the traffic to the units of its own launch
         json.dump(d, open(p, "w"), indent=1, sort_keys=True)
     print(open(dst).read())
 
@@ -109,4 +111,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else None)
