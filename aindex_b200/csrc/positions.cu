@@ -799,13 +799,22 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         aix_ctx *ctx = mg->ctx[r];
         cudaStream_t st = ctx->stream;
         PerGpu &me = g[r];
-        auto fail_cuda = [&](cudaError_t e) { cudaGetLastError(); rcs[r] = PB_FAIL(ctx, e); };
+        const char *phase = "start";
+        auto fail_cuda = [&](cudaError_t e) {
+            cudaGetLastError();
+            size_t fr = 0, to = 0;
+            cudaMemGetInfo(&fr, &to);
+            rcs[r] = ctx->fail(e == cudaErrorMemoryAllocation ? AIX_ERR_NOMEM : AIX_ERR_CUDA,
+                               "multi-GPU positions build, GPU %d of %d, phase %s: %s (%.1f of %.1f GB free)", r, n, phase,
+                               cudaGetErrorString(e), fr / 1e9, to / 1e9);
+        };
         cudaError_t e = cudaSetDevice(ctx->device);
         if (e != cudaSuccess) fail_cuda(e);
         const uint64_t lo = c[r], hi = c[r + 1];
         const uint64_t img_len = hi > lo ? (hi - lo) + K - 1 : 0;   // bytes [lo, hi + K - 1) <= len
         double t0 = AixTrace::now();
         // ---- phase 1: upload the shard, prefix sum of tf (every GPU keeps the offsets: its finalize pass needs them)
+        phase = "upload + prefix sum";
         if (rcs[r] == AIX_OK) {
             e = aix_pool_alloc(ctx, &me.reads_dev, img_len + 64, st);
             if (e == cudaSuccess && img_len) e = cudaMemcpyAsync(me.reads_dev, reads + lo, img_len, cudaMemcpyHostToDevice, st);
@@ -851,6 +860,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         t_up[r] = ms_since(t0);
         bar.wait();
         // ---- phase 2: emit keys in position order, partition them by owner
+        phase = "emit + partition";
         t0 = AixTrace::now();
         if (!any_failed() && hi > lo && nb && total) {
             uint64_t cap = 0;
@@ -873,6 +883,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         t_emit[r] = ms_since(t0);
         bar.wait();
         // ---- phase 3: every owner makes room for what it will receive
+        phase = "receive buffers";
         t0 = AixTrace::now();
         if (!any_failed()) {
             for (int s2 = 0; s2 < n; ++s2) me.recv_total += counts[(size_t)s2 * n + r];
@@ -883,6 +894,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         }
         bar.wait();
         // ---- phase 4: the exchange -- part o of this GPU goes to owner o, behind the parts of the GPUs before this one
+        phase = "exchange";
         if (!any_failed()) {
             uint64_t seg = 0;
             for (int o = 0; o < n && rcs[r] == AIX_OK; ++o) {
@@ -903,6 +915,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         t_exch[r] = ms_since(t0);
         bar.wait();
         // ---- phase 5: sort the received keys on the bucket bits, turn them into this GPU's slice of positions[]
+        phase = "sort + finalize";
         t0 = AixTrace::now();
         if (!any_failed()) {
             uint64_t *sorted = me.recv;
@@ -918,6 +931,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         }
         t_sort[r] = ms_since(t0);
         // ---- phase 6: download the slice (and the offsets, from GPU 0)
+        phase = "download";
         t0 = AixTrace::now();
         if (rcs[r] == AIX_OK && !any_failed()) {
             const uint64_t cnt = slot_lo[r + 1] - slot_lo[r];

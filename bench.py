@@ -186,7 +186,13 @@ def sharded_index_check(torch, dist, capi, ctx, stream, dev, args, rank, world, 
         ctx.sync()
         barrier()
         ms = max_over_ranks(a.elapsed_time(b))
-        same = torch.tensor([1 if torch.equal(res.to(torch.int32), out_dev[:nq]) else 0], device=dev, dtype=torch.int32)
+        diff = torch.nonzero(res.to(torch.int32) != out_dev[:nq]).reshape(-1)
+        if diff.numel():  # diagnosis on stderr: which queries, what the two paths say
+            d = diff[:8]
+            sys.stderr.write(f"[bench] rank {rank}: sharded index differs from the replicated one on {diff.numel()} of {nq} queries; "
+                             f"first {d.tolist()}: sharded {res[d].tolist()} replicated {out_dev[:nq][d].tolist()} "
+                             f"(replicated hits in the batch: {int((out_dev[:nq] > 0).sum())}, sharded hits: {int((res > 0).sum())})\n")
+        same = torch.tensor([1 if diff.numel() == 0 else 0], device=dev, dtype=torch.int32)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         out = {"equal": bool(int(same.item())), "queries_per_rank": nq, "value": world * nq / (ms / 1e3), "unit": "queries/s (aggregate)",
                "ms_per_step": ms, "records_per_rank": sh.hi - sh.lo, "equals_reference_1M": None}
