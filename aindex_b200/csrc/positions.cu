@@ -887,10 +887,18 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         t0 = AixTrace::now();
         if (!any_failed()) {
             for (int s2 = 0; s2 < n; ++s2) me.recv_total += counts[(size_t)s2 * n + r];
-            e = aix_pool_alloc(ctx, &me.recv, (me.recv_total ? me.recv_total : 1) * 8, st);
-            if (e == cudaSuccess) e = aix_pool_alloc(ctx, &me.alt, (me.recv_total ? me.recv_total : 1) * 8, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) fail_cuda(e);
+            if (me.recv_total > total + (n_win_end - first)) {  // cannot be: more keys than windows
+                rcs[r] = ctx->fail(AIX_ERR_STATE, "multi-GPU positions build: GPU %d would receive %llu keys of %llu windows", r,
+                                   (unsigned long long)me.recv_total, (unsigned long long)(n_win_end - first));
+            } else {
+                static char what[3][64];
+                snprintf(what[0], 64, "receive buffer (%llu keys)", (unsigned long long)me.recv_total);
+                phase = what[0];
+                e = aix_pool_alloc(ctx, &me.recv, (me.recv_total ? me.recv_total : 1) * 8, st);
+                if (e == cudaSuccess) { phase = "receive buffer: spare"; e = aix_pool_alloc(ctx, &me.alt, (me.recv_total ? me.recv_total : 1) * 8, st); }
+                if (e == cudaSuccess) { phase = "receive buffer: sync"; e = cudaStreamSynchronize(st); }
+                if (e != cudaSuccess) fail_cuda(e);
+            }
         }
         bar.wait();
         // ---- phase 4: the exchange -- part o of this GPU goes to owner o, behind the parts of the GPUs before this one

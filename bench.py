@@ -173,8 +173,20 @@ def sharded_index_check(torch, dist, capi, ctx, stream, dev, args, rank, world, 
     unmodified reference's on the first 1 M queries."""
     from aindex_b200 import dist as D
     nq = min(args.queries, 20_000_000)
+    shared = None
     try:
-        sh = D.ShardedIndex23(n_keys).attach(ctx, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32), stream)
+        # every rank must split THE SAME index: the GPU MPHF builder's peeling order (hence the ids) differs from run to
+        # run, so rank 0 writes its files once and every rank loads its slice of them
+        pbox = [None]
+        if rank == 0:
+            shared = tempfile.mkdtemp(prefix="aix_shard_", dir=_tmp_root())
+            pbox[0] = write_index_files(shared, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
+        dist.broadcast_object_list(pbox, src=0)
+        prefix0 = pbox[0]
+        m_sh = capi.Mphf.load(ctx, prefix0 + ".pf")
+        chk = np.memmap(prefix0 + ".kmers.bin", dtype=np.uint64, mode="r")
+        tfs = np.memmap(prefix0 + ".tf.bin", dtype=np.uint32, mode="r")
+        sh = D.ShardedIndex23(n_keys).attach(ctx, m_sh, chk, tfs, stream)
         recs = q_dev[:nq]
         res = sh.query(recs)  # warm-up (NCCL all-to-all buffers)
         ctx.sync()
@@ -197,19 +209,18 @@ def sharded_index_check(torch, dist, capi, ctx, stream, dev, args, rank, world, 
         out = {"equal": bool(int(same.item())), "queries_per_rank": nq, "value": world * nq / (ms / 1e3), "unit": "queries/s (aggregate)",
                "ms_per_step": ms, "records_per_rank": sh.hi - sh.lo, "equals_reference_1M": None}
         if rank == 0 and ref_harness_path():
-            tmpdir = tempfile.mkdtemp(prefix="aix_shard_", dir=_tmp_root())
-            try:
-                prefix = write_index_files(tmpdir, mphf, checker_t.cpu().numpy().view(np.uint64), tf_t.cpu().numpy().view(np.uint32))
-                n1 = min(nq, 1_000_000)
-                kind, secs, ref = cpu_query_runs(prefix, recs[:n1].cpu().numpy(), os.cpu_count() or 1, 1)
-                out["equals_reference_1M"] = bool(kind == "reference" and np.array_equal(ref, res[:n1].cpu().numpy().astype(np.uint32)))
-            finally:
-                shutil.rmtree(tmpdir, ignore_errors=True)
+            n1 = min(nq, 1_000_000)
+            kind, secs, ref = cpu_query_runs(prefix0, recs[:n1].cpu().numpy(), os.cpu_count() or 1, 1)
+            out["equals_reference_1M"] = bool(kind == "reference" and np.array_equal(ref, res[:n1].cpu().numpy().astype(np.uint32)))
         return out
     except Exception as e:  # noqa: BLE001
         import traceback
         traceback.print_exc()
         return {"equal": None, "error": f"{type(e).__name__}: {e}"}
+    finally:
+        barrier()  # every rank is done with rank 0's files
+        if shared:
+            shutil.rmtree(shared, ignore_errors=True)
 
 
 def count13_multi_gpu_vs_reference(torch, dist, capi, ctx, stream, dev, rank, world, creads, peer, hist_tensor, rs_out):
