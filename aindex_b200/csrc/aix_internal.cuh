@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -86,6 +87,7 @@ struct aix_ctx {
     // 100 GB again (measured: 50-700 ms per build with cudaMalloc / cudaFree, more while NVML is being polled).
     // aix_ctx_trim() hands the cached memory back.
     cudaMemPool_t pool = nullptr;
+    std::unordered_set<void *> plain_allocs;  // cudaMalloc'ed buffers that travel through the builders' pool-free calls (multi-GPU exchange buffers)
     void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
     // single-query mailbox (tf_query.cu): a one-thread resident kernel that polls a request slot in mapped host memory,
     // so that get_tf_value() costs two PCIe traversals instead of a kernel launch + a stream synchronisation
@@ -151,8 +153,20 @@ template <typename T>
 static inline cudaError_t aix_pool_alloc(aix_ctx *ctx, T **p, size_t bytes, cudaStream_t st) {
     return aix_pool_alloc(ctx, (void **)p, bytes, st);
 }
+// buffers another GPU copies into / out of (multi-GPU exchange): plain cudaMalloc memory, peer-accessible through
+// cudaDeviceEnablePeerAccess; remembered so that aix_pool_free releases them the right way
+template <typename T>
+static inline cudaError_t aix_plain_alloc(aix_ctx *ctx, T **p, size_t bytes) {
+    cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 1);
+    if (e == cudaSuccess) ctx->plain_allocs.insert((void *)*p);
+    return e;
+}
 static inline void aix_pool_free(aix_ctx *ctx, void *p, cudaStream_t st) {
     if (!p) return;
+    if (ctx && ctx->plain_allocs.erase(p)) {
+        cudaFree(p);
+        return;
+    }
     if (ctx && ctx->pool) cudaFreeAsync(p, st);
     else cudaFree(p);
 }

@@ -119,15 +119,6 @@ int aix_multi_create(int n_dev, const int *dev_ids, aix_multi **out) {
             if (e == cudaErrorPeerAccessAlreadyEnabled) e = cudaSuccess;
             cudaGetLastError();
             if (e != cudaSuccess) mg->peer_ok = false;
-            // the builders' pool memory must be reachable by direct peer copies as well
-            if (e == cudaSuccess && mg->ctx[i]->pool) {
-                cudaMemAccessDesc d = {};
-                d.location.type = cudaMemLocationTypeDevice;
-                d.location.id = mg->ctx[j]->device;
-                d.flags = cudaMemAccessFlagsProtReadWrite;
-                cudaMemPoolSetAccess(mg->ctx[i]->pool, &d, 1);
-                cudaGetLastError();
-            }
         }
     }
     *out = mg;

@@ -866,7 +866,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
             uint64_t cap = 0;
             int rc = emit_keys<K>(ctx, st, ix[r]->dev(), ix[r]->mphf_dev(), me.reads_dev, 0, hi - lo, lo, pos_bits, hi - lo, &me.keys, &cap, &me.n_valid);
             if (rc == AIX_OK) {
-                e = aix_pool_alloc(ctx, &me.part, (me.n_valid ? me.n_valid : 1) * 8, st);
+                e = aix_plain_alloc(ctx, &me.part, (me.n_valid ? me.n_valid : 1) * 8);  // read by the other GPUs' copy engines
                 if (e != cudaSuccess) fail_cuda(e);
                 else {
                     std::vector<uint64_t> kb(n);
@@ -894,8 +894,8 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
                 static char what[3][64];
                 snprintf(what[0], 64, "receive buffer (%llu keys)", (unsigned long long)me.recv_total);
                 phase = what[0];
-                e = aix_pool_alloc(ctx, &me.recv, (me.recv_total ? me.recv_total : 1) * 8, st);
-                if (e == cudaSuccess) { phase = "receive buffer: spare"; e = aix_pool_alloc(ctx, &me.alt, (me.recv_total ? me.recv_total : 1) * 8, st); }
+                e = aix_plain_alloc(ctx, &me.recv, (me.recv_total ? me.recv_total : 1) * 8);  // written by the other GPUs
+                if (e == cudaSuccess) { phase = "receive buffer: spare"; e = aix_plain_alloc(ctx, &me.alt, (me.recv_total ? me.recv_total : 1) * 8); }
                 if (e == cudaSuccess) { phase = "receive buffer: sync"; e = cudaStreamSynchronize(st); }
                 if (e != cudaSuccess) fail_cuda(e);
             }
