@@ -44,6 +44,10 @@ C3_BYTES_PER_KMER = 9.09      # 151/138 B in + 4 B read + 4 B wr
 GATHER_PEAK_G = 50.1          # random 16-byte gathers/s (1 GiB table), G/s
 RED_PEAK_256M_G = 32.0        # random RED.ADD.U32 into a 256 MiB table (the north star's atomic roofline), G/s
 RED_PEAK_L2_G = 210.0         # the same into a 64 MiB (L2-resident) slice, G/s
+# request-only kernels in the shape of one lookup (profiles/atomic_roofline.cu `lookup_shape_stream`, profiles/r02_atomic_roofline.txt):
+# 23 B streamed in through the product kernel's TMA ring, 4 B out, 3 scattered 16-byte loads from an L2-resident table, nothing else
+LOOKUP_SHAPE_16MIB_G = 65.0   # 16 MiB record table
+LOOKUP_SHAPE_64MIB_G = 53.4   # 64 MiB record table (the fused C2 structure is 61.5 MB)
 
 
 def parse_args():
@@ -621,7 +625,7 @@ def run_ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = float(np.mean(kernel_ms))
     achieved = args.queries * Q1_BYTES_PER_QUERY / (k_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tf23_stream_kernel<AIX_Q_TF, canonical>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "tf23_stream_kernel<AIX_Q_TF, canonical> (" + index.layout["records"] + " MPHF records)", "achieved": achieved,
                 "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "bytes_per_unit": Q1_BYTES_PER_QUERY, "units_per_launch": args.queries, "kernel_ms": k_ms,
@@ -630,6 +634,14 @@ def run_ours(args):
                 "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
                 # the other denominators of this kernel (profiles/r01_atomic_roofline.txt):
                 # random 16-byte gathers from a 1 GiB table run at 50.1 G/s on this GPU (the index is 0.8 GB)
+                # what actually bounds the kernel: three scattered L2 requests per query (ncu: L1TEX/L2 request path, not DRAM)
+                "l2_request_ceiling": {"achieved_gq_s": args.queries / (k_ms / 1e3) / 1e9,
+                                       "request_only_kernel_gq_s": {"16MiB_table": LOOKUP_SHAPE_16MIB_G, "64MiB_table": LOOKUP_SHAPE_64MIB_G},
+                                       "frac_of_16MiB_shape": args.queries / (k_ms / 1e3) / 1e9 / LOOKUP_SHAPE_16MIB_G,
+                                       "frac_of_64MiB_shape": args.queries / (k_ms / 1e3) / 1e9 / LOOKUP_SHAPE_64MIB_G,
+                                       "source": "profiles/r02_atomic_roofline.txt (lookup_shape_stream recs16=3 bytes1=0)",
+                                       "note": "the product kernel (61.5 MB structure, 363 instructions per query on top of the requests) "
+                                               "runs between the two request-only shapes: it is at the L2-request ceiling of a 3-vertex MPHF lookup"},
                 "random_access": {"achieved_gq_s": args.queries / (k_ms / 1e3) / 1e9, "peak_ggathers_s": GATHER_PEAK_G,
                                   "frac": args.queries / (k_ms / 1e3) / 1e9 / GATHER_PEAK_G,
                                   "note": "measured random-gather rate; above 1.0 is possible because the L2-resident "
