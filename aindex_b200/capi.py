@@ -38,7 +38,7 @@ class CountStats(C.Structure):
 class MultiBuildStats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("upload_scan_ms", C.c_double), ("emit_partition_ms", C.c_double),
                 ("exchange_ms", C.c_double), ("sort_finalize_ms", C.c_double), ("download_ms", C.c_double),
-                ("keys", C.c_uint64), ("peer_bytes", C.c_uint64), ("positions", C.c_uint64)]
+                ("keys", C.c_uint64), ("peer_bytes", C.c_uint64), ("positions", C.c_uint64), ("alloc_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -91,6 +91,7 @@ SIGNATURES = {
     "aix_index23_fill_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "aix_tf23_batch": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
     "aix_tf23_batch_dev": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
+    "aix_tf23_single_call_latency": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _vp, _vp]),
     "aix_tf23_probes_dev": (_i, [_vp, _vp, _u64, _i, _vp, _u32, _vp, _u64, _vp]),
     "aix_probe23_dev": (_i, [_vp, _vp, _vp, _u64, _vp]),
     "aix_probes_bucket_dev": (_i, [_vp, _vp, _u64, _vp, _i, _vp, _vp, _vp]),
@@ -499,6 +500,16 @@ class Index23:
         self.ctx.check(lib().aix_tf23_batch(self.ctx.handle, self._h, _p(recs), recs.shape[1], _p(lens), q,
                                             mode, _p(out)))
         return out
+
+    def single_call_latency(self, kmers) -> dict:
+        """ns per single get_tf_value call measured from C (aix_tf23_single_call_latency): echo = transport only."""
+        recs, _ = as_records(kmers)
+        n = recs.shape[0]
+        tf = np.zeros(n, dtype=np.uint32)
+        echo, query = C.c_double(0), C.c_double(0)
+        self.ctx.check(lib().aix_tf23_single_call_latency(self.ctx.handle, self._h, _p(recs), recs.shape[1], n, _p(tf),
+                                                          C.byref(echo), C.byref(query)))
+        return {"echo_ns": echo.value, "query_ns": query.value, "tf": tf}
 
     def query_dev(self, recs_ptr: int, stride: int, lens_ptr, q: int, mode: int, out_ptr: int):
         self.ctx.check(lib().aix_tf23_batch_dev(self.ctx.handle, self._h, recs_ptr, stride, lens_ptr, q, mode,

@@ -88,6 +88,8 @@ struct aix_ctx {
     // aix_ctx_trim() hands the cached memory back.
     cudaMemPool_t pool = nullptr;
     std::unordered_set<void *> plain_allocs;  // cudaMalloc'ed buffers that travel through the builders' pool-free calls (multi-GPU exchange buffers)
+    bool defer_plain_free = false;      // cudaFree of multi-GB buffers blocks for tens of ms: the multi-GPU build collects them ...
+    std::vector<void *> plain_deferred; // ... here and releases them after its last phase (aix_plain_release)
     void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
     // single-query mailbox (tf_query.cu): a one-thread resident kernel that polls a request slot in mapped host memory,
     // so that get_tf_value() costs two PCIe traversals instead of a kernel launch + a stream synchronisation
@@ -164,11 +166,18 @@ static inline cudaError_t aix_plain_alloc(aix_ctx *ctx, T **p, size_t bytes) {
 static inline void aix_pool_free(aix_ctx *ctx, void *p, cudaStream_t st) {
     if (!p) return;
     if (ctx && ctx->plain_allocs.erase(p)) {
-        cudaFree(p);
+        if (ctx->defer_plain_free) ctx->plain_deferred.push_back(p);
+        else cudaFree(p);
         return;
     }
     if (ctx && ctx->pool) cudaFreeAsync(p, st);
     else cudaFree(p);
+}
+
+static inline void aix_plain_release(aix_ctx *ctx) {
+    for (void *p : ctx->plain_deferred) cudaFree(p);
+    ctx->plain_deferred.clear();
+    ctx->defer_plain_free = false;
 }
 
 struct aix_multi {  // multi.cu: one ctx (and one host thread at a time) per GPU of one box, one process
@@ -224,6 +233,32 @@ struct AixTrace {
         double t = now();
         fprintf(stderr, "[aix trace] %s: %-70s %9.3f ms\n", what, phase, (t - t_last) * 1e3);
         t_last = t;
+    }
+};
+
+// device time of the work enqueued between the constructor and done(), printed when AIX_TRACE is set (CUDA events on
+// the stream: unlike AixTrace::mark this leaves out allocation and host-side waiting)
+struct AixTraceSpan {
+    bool on;
+    cudaStream_t st;
+    cudaEvent_t e0, e1;
+    explicit AixTraceSpan(cudaStream_t s) : on(getenv("AIX_TRACE") != nullptr), st(s), e0(nullptr), e1(nullptr) {
+        if (on) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, st);
+        }
+    }
+    void done(const char *what) {
+        if (!on) return;
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[aix trace] device span: %-70s %9.3f ms\n", what, ms);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        on = false;
     }
 };
 

@@ -336,10 +336,12 @@ static int emit_keys(aix_ctx *ctx, cudaStream_t st, Index23Dev id, MphfDev md, c
         e = aix_pool_alloc(ctx, &keys, cap * 8, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, (8 + e_tiles) * 8, st);
         if (e == cudaSuccess) {
+            AixTraceSpan span(st);
             positions_emit_kernel<K><<<(unsigned)e_tiles, kEmitThreads, 0, st>>>(id, md, reads_dev, start, n_win_end, pos_base, pos_bits, keys, cap,
                                                                                 scratch + 8, (unsigned int *)(scratch + 1), scratch);
             ctx->launches++;
             e = cudaGetLastError();
+            span.done("positions_emit_kernel");
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(&n_valid, scratch, 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -791,7 +793,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
     std::vector<uint64_t> counts((size_t)n * n, 0), bounds(n + 1, 0), slot_lo(n + 1, 0);
     unsigned long long total = 0;
     std::vector<int> rcs(n, AIX_OK);
-    std::vector<double> t_emit(n, 0), t_exch(n, 0), t_sort(n, 0), t_up(n, 0), t_down(n, 0);
+    std::vector<double> t_emit(n, 0), t_exch(n, 0), t_sort(n, 0), t_up(n, 0), t_down(n, 0), t_alloc(n, 0);
     HostBarrier bar(n);
     auto any_failed = [&]() { for (int r = 0; r < n; ++r) if (rcs[r] != AIX_OK) return true; return false; };
     const double t_all = AixTrace::now();
@@ -810,6 +812,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         };
         cudaError_t e = cudaSetDevice(ctx->device);
         if (e != cudaSuccess) fail_cuda(e);
+        ctx->defer_plain_free = true;  // exchange buffers are released after the last phase (cudaFree blocks for tens of ms)
         const uint64_t lo = c[r], hi = c[r + 1];
         const uint64_t img_len = hi > lo ? (hi - lo) + K - 1 : 0;   // bytes [lo, hi + K - 1) <= len
         double t0 = AixTrace::now();
@@ -866,7 +869,9 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
             uint64_t cap = 0;
             int rc = emit_keys<K>(ctx, st, ix[r]->dev(), ix[r]->mphf_dev(), me.reads_dev, 0, hi - lo, lo, pos_bits, hi - lo, &me.keys, &cap, &me.n_valid);
             if (rc == AIX_OK) {
+                const double ta = AixTrace::now();
                 e = aix_plain_alloc(ctx, &me.part, (me.n_valid ? me.n_valid : 1) * 8);  // read by the other GPUs' copy engines
+                t_alloc[r] += ms_since(ta);
                 if (e != cudaSuccess) fail_cuda(e);
                 else {
                     std::vector<uint64_t> kb(n);
@@ -880,7 +885,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         }
         aix_pool_free(ctx, me.reads_dev, st);
         me.reads_dev = nullptr;
-        t_emit[r] = ms_since(t0);
+        t_emit[r] = ms_since(t0) - t_alloc[r];
         bar.wait();
         // ---- phase 3: every owner makes room for what it will receive
         phase = "receive buffers";
@@ -900,21 +905,26 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
                 if (e != cudaSuccess) fail_cuda(e);
             }
         }
+        t_alloc[r] += ms_since(t0);
         bar.wait();
-        // ---- phase 4: the exchange -- part o of this GPU goes to owner o, behind the parts of the GPUs before this one
+        // ---- phase 4: the exchange -- part o of this GPU goes to owner o, behind the parts of the GPUs before this one.
+        // Step i sends to owner (r + i) mod n: every step is a permutation, so no GPU receives from two peers at once
+        // (all GPUs starting with owner 0 would share its 900 GB/s of NVLink ingress).
         phase = "exchange";
+        t0 = AixTrace::now();
         if (!any_failed()) {
-            uint64_t seg = 0;
-            for (int o = 0; o < n && rcs[r] == AIX_OK; ++o) {
+            std::vector<uint64_t> seg(n + 1, 0);
+            for (int o = 0; o < n; ++o) seg[o + 1] = seg[o] + counts[(size_t)r * n + o];
+            for (int i = 0; i < n && rcs[r] == AIX_OK; ++i) {
+                const int o = (r + i) % n;
                 const uint64_t cnt = counts[(size_t)r * n + o];
                 uint64_t off = 0;
                 for (int s2 = 0; s2 < r; ++s2) off += counts[(size_t)s2 * n + o];
                 if (cnt) {
-                    e = o == r ? cudaMemcpyAsync(g[o].recv + off, me.part + seg, cnt * 8, cudaMemcpyDeviceToDevice, st)
-                               : cudaMemcpyPeerAsync(g[o].recv + off, mg->ctx[o]->device, me.part + seg, ctx->device, cnt * 8, st);
+                    e = o == r ? cudaMemcpyAsync(g[o].recv + off, me.part + seg[o], cnt * 8, cudaMemcpyDeviceToDevice, st)
+                               : cudaMemcpyPeerAsync(g[o].recv + off, mg->ctx[o]->device, me.part + seg[o], ctx->device, cnt * 8, st);
                     if (e != cudaSuccess) fail_cuda(e);
                 }
-                seg += cnt;
             }
             if (rcs[r] == AIX_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail_cuda(e);
         }
@@ -953,6 +963,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         aix_pool_free(ctx, me.recv, st); aix_pool_free(ctx, me.alt, st);
         aix_pool_free(ctx, me.positions, st); aix_pool_free(ctx, me.indices, st);
         cudaStreamSynchronize(st);
+        aix_plain_release(ctx);
         bar.wait();
     };
     {
@@ -966,7 +977,7 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         auto mx = [&](const std::vector<double> &v) { double m = 0; for (double x : v) m = x > m ? x : m; return m; };
         stats->total_ms = ms_since(t_all);
         stats->upload_scan_ms = mx(t_up); stats->emit_partition_ms = mx(t_emit); stats->exchange_ms = mx(t_exch);
-        stats->sort_finalize_ms = mx(t_sort); stats->download_ms = mx(t_down);
+        stats->sort_finalize_ms = mx(t_sort); stats->download_ms = mx(t_down); stats->alloc_ms = mx(t_alloc);
         uint64_t moved = 0, all = 0;
         for (int r = 0; r < n; ++r)
             for (int o = 0; o < n; ++o) { all += counts[(size_t)r * n + o]; if (o != r) moved += counts[(size_t)r * n + o]; }

@@ -100,10 +100,27 @@ __global__ void __launch_bounds__(kRsMaxRadix) rs_base_kernel(const unsigned lon
     base[blockIdx.x * kRsMaxRadix + threadIdx.x] = block_scan_u64(v, sm, total);
 }
 
-// One digit pass.  Stable: equal digits keep their input order.  kRsThreads = 512 (8192-key tiles, 2 CTAs / SM) or
-// 256 (4096-key tiles, 4 CTAs / SM: same threads per SM, finer interleaving of the load / rank / look-back / store phases).
-template <int kRsThreads, typename Digit>
-__global__ void __launch_bounds__(kRsThreads, 1024 / kRsThreads)
+// The lanes of the warp whose digit equals this lane's: kBits ballots.  MATCH.ANY gives the same mask in one instruction,
+// but it runs on the SM's address-divergence unit at ~2 cycles per distinct value in the warp: with 128-256 digit values
+// almost every lane is distinct, and ncu showed that pipe at 85 % with DRAM at 28 % (profiles/r02_c5sort_ncu.txt).
+// Ballots run on the ALU / vote path at full rate.
+template <int kBits>
+__device__ __forceinline__ uint32_t warp_peers(uint32_t d, bool valid) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (int b = 0; b < kBits; ++b) {
+        const bool p = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, p);
+        peers &= p ? m : ~m;
+    }
+    return peers;
+}
+
+// One digit pass.  Stable: equal digits keep their input order.  256 threads x 16 keys = 4096-key tiles, 4 CTAs / SM
+// (512-thread tiles were slower: 55.5 vs 48.5 ms per 6.4 G-key pass).  kBits = width of the digit (the number of ballots
+// per key); kBits = 0 selects the match_any ranking with a run-time width (kept for A/B runs, AIX_RS_RANK=match).
+template <int kRsThreads, int kBits, int kMinBlocks, typename Digit>
+__global__ void __launch_bounds__(kRsThreads, kMinBlocks)
 rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, Digit dg, int bits,
                const unsigned long long *__restrict__ digit_base, unsigned long long *__restrict__ status,
                unsigned int *__restrict__ tile_counter) {
@@ -118,7 +135,7 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
     __shared__ uint32_t s_wsum[kRsMaxRadix / 32];
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t radix = 1u << bits;
+    const uint32_t radix = 1u << bits;  // kBits >= bits (ballots above the width see zero bits)
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (uint32_t i = tid; i < kRsWarps * radix; i += kRsThreads) whist[i] = 0;
     __syncthreads();
@@ -128,38 +145,31 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
 
     // keys, warp-striped: item j of lane l of warp w = tile_base + w*32*ITEMS + j*32 + l
     uint64_t key[kRsItems];
-    uint16_t pos[kRsItems];
+    uint32_t pos2[kRsItems / 2];  // two 16-bit slots per word: rank in the warp's digit group, later the stage slot
     const uint32_t wbase = warp * (32 * kRsItems) + lane;
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t idx = wbase + j * 32;
         key[j] = idx < tile_n ? (uint64_t)__ldcs((const unsigned long long *)(in + tile_base + idx)) : ~0ull;
     }
-    // rank inside the warp: lanes with the same digit form a group (match_any).  Every lane of a group reads the digit's
-    // running count of this warp (one broadcast LDS), the group's lowest lane then adds the group size.  The matches
-    // of eight items are issued back to back (MATCH.ANY has a long latency: it was 30 % of the stall samples when
-    // each one sat in front of the shared-memory update that depends on it, profiles/r02_c5sort_ncu.txt).
+    // rank inside the warp: lanes with the same digit form a group.  Every lane of a group reads the digit's running
+    // count of this warp (one broadcast LDS), the group's lowest lane then adds the group size.
     uint32_t *my_hist = whist + warp * radix;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int j0 = 0; j0 < kRsItems; j0 += 8) {
-        uint32_t peers[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const bool valid = wbase + (j0 + u) * 32 < tile_n;
-            const uint32_t d = valid ? dg(key[j0 + u]) : 0xFFFFFFFFu;
-            peers[u] = __match_any_sync(0xFFFFFFFFu, d);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const bool valid = wbase + (j0 + u) * 32 < tile_n;
-            const uint32_t d = dg(key[j0 + u]);
-            const uint32_t base = valid ? my_hist[d] : 0u;
-            __syncwarp();
-            if (valid && (peers[u] & lt) == 0u) my_hist[d] = base + __popc(peers[u]);
-            __syncwarp();
-            pos[j0 + u] = (uint16_t)(base + __popc(peers[u] & lt));
-        }
+    for (int j = 0; j < kRsItems; ++j) {
+        const bool valid = wbase + j * 32 < tile_n;
+        const uint32_t d = dg(key[j]);
+        uint32_t peers;
+        if (kBits) peers = warp_peers<kBits>(d, valid);
+        else peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu);
+        const uint32_t base = valid ? my_hist[d] : 0u;
+        __syncwarp();
+        if (valid && (peers & lt) == 0u) my_hist[d] = base + __popc(peers);
+        __syncwarp();
+        const uint32_t r = (base + __popc(peers & lt)) & 0xFFFFu;
+        if (j & 1) pos2[j >> 1] |= r << 16;
+        else pos2[j >> 1] = r;
     }
     __syncthreads();
     // per digit: exclusive prefix over the warps, tile total; publish the aggregate at once
@@ -195,15 +205,14 @@ rs_pass_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint
     // stage slot of every key
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
-        if (wbase + j * 32 < tile_n) {
-            const uint32_t d = dg(key[j]);
-            pos[j] = (uint16_t)(pos[j] + my_hist[d] + s_dstart[d]);
-        }
+        const uint32_t d = dg(key[j]) & (radix - 1u);
+        const uint32_t add = my_hist[d] + s_dstart[d];
+        pos2[j >> 1] += (j & 1) ? add << 16 : add;  // slots stay below 4096: no carry out of either half
     }
     __syncthreads();  // whist is dead from here on: stage may overwrite it
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j)
-        if (wbase + j * 32 < tile_n) stage[pos[j]] = key[j];
+        if (wbase + j * 32 < tile_n) stage[(j & 1) ? pos2[j >> 1] >> 16 : pos2[j >> 1] & 0xFFFFu] = key[j];
     // look back over the earlier tiles, one thread per digit
     if (tid < radix) {
         unsigned long long excl = 0;
@@ -281,6 +290,59 @@ __global__ void rle_counts_kernel(const unsigned long long *__restrict__ starts,
     counts[r] = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c;  // the tf arrays are u32 (src/hash.hpp:97)
 }
 
+// ranking variant of the pass kernel: ballots (default) or match_any (AIX_RS_RANK=match, for A/B runs)
+static bool rs_rank_by_match() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AIX_RS_RANK");
+        v = (e && !strcmp(e, "match")) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int kBits, int kMinBlocks, typename Digit>
+static cudaError_t rs_launch_one(unsigned tiles, cudaStream_t st, const uint64_t *in, uint64_t *out, uint64_t n, const Digit &dg, int bits,
+                                 const unsigned long long *base, unsigned long long *status, unsigned int *counter) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(rs_pass_kernel<256, kBits, kMinBlocks, Digit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)rs_smem(256));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    rs_pass_kernel<256, kBits, kMinBlocks, Digit><<<tiles, 256, rs_smem(256), st>>>(in, out, n, dg, bits, base, status, counter);
+    return cudaGetLastError();
+}
+
+// the sort passes: digit width 1..8, ballot ranking; AIX_RS_RANK=match / AIX_RS_MINBLOCKS=3 select the A/B variants
+static cudaError_t rs_launch_pass(unsigned tiles, cudaStream_t st, const uint64_t *in, uint64_t *out, uint64_t n, const BitsDigit &dg, int bits,
+                                  const unsigned long long *base, unsigned long long *status, unsigned int *counter) {
+    static int three = -1;
+    if (three < 0) {
+        const char *e = getenv("AIX_RS_MINBLOCKS");
+        three = (e && atoi(e) == 3) ? 1 : 0;
+    }
+    if (rs_rank_by_match()) return rs_launch_one<0, 4>(tiles, st, in, out, n, dg, bits, base, status, counter);
+#define AIX_RS_CASE(B)                                                                                          \
+    case B:                                                                                                     \
+        return three ? rs_launch_one<B, 3>(tiles, st, in, out, n, dg, bits, base, status, counter)              \
+                     : rs_launch_one<B, 4>(tiles, st, in, out, n, dg, bits, base, status, counter);
+    switch (bits) {
+        AIX_RS_CASE(1) AIX_RS_CASE(2) AIX_RS_CASE(3) AIX_RS_CASE(4) AIX_RS_CASE(5) AIX_RS_CASE(6) AIX_RS_CASE(7)
+        default: return three ? rs_launch_one<8, 3>(tiles, st, in, out, n, dg, bits, base, status, counter)
+                              : rs_launch_one<8, 4>(tiles, st, in, out, n, dg, bits, base, status, counter);
+    }
+#undef AIX_RS_CASE
+}
+
+// the range partition: at most 16 ranges = 4 ballots (rounds above the digit's width see zero bits and change nothing)
+static cudaError_t rs_launch_pass(unsigned tiles, cudaStream_t st, const uint64_t *in, uint64_t *out, uint64_t n, const RangeDigit &dg, int bits,
+                                  const unsigned long long *base, unsigned long long *status, unsigned int *counter) {
+    return rs_launch_one<4, 4>(tiles, st, in, out, n, dg, bits, base, status, counter);
+}
+
 int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt, uint64_t n, int begin_bit, int end_bit,
                    uint64_t **sorted) {
     *sorted = keys;
@@ -292,22 +354,9 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     const int total_bits = end_bit - begin_bit;
     plan.n_pass = (total_bits + kRsMaxBits - 1) / kRsMaxBits;
     plan.bits = (total_bits + plan.n_pass - 1) / plan.n_pass;
-    static int variant = 0;  // threads per CTA of the pass kernel (AIX_RS_THREADS = 256 | 512 for A/B runs)
-    if (!variant) {
-        const char *e = getenv("AIX_RS_THREADS");
-        variant = (e && atoi(e) == 512) ? 512 : 256;  // measured at 6.4 G keys: 48.5 ms vs 55.5 ms per pass
-    }
-    const int threads = variant, tile_keys = threads * kRsItems;
-    const size_t smem = rs_smem(threads);
+    const int tile_keys = 256 * kRsItems;
     const uint64_t tiles = (n + tile_keys - 1) / tile_keys;
     if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "radix sort: too many keys");
-    static bool attr_set[64] = {};
-    if (!attr_set[ctx->device & 63]) {
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<512, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(512)));
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, RangeDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
-        attr_set[ctx->device & 63] = true;
-    }
     AixTrace trace(st, "radix sort");
     // scratch: hist[8][256] | base[8][256] | counters[8] (+pad) | status[tiles][radix]
     const size_t front = (size_t)kRsMaxPasses * kRsMaxRadix * 8 * 2 + 64;
@@ -340,12 +389,9 @@ int radix_sort_u64(aix_ctx *ctx, cudaStream_t st, uint64_t *keys, uint64_t *alt,
     uint64_t *src = keys, *dst = alt;
     for (int p = 0; p < plan.n_pass; ++p) {
         if ((e = cudaMemsetAsync(status, 0, (size_t)tiles * ((size_t)1 << plan.width(p)) * 8, st)) != cudaSuccess) return fail(e, "memset");
-        if (threads == 256)
-            rs_pass_kernel<256, BitsDigit><<<(unsigned)tiles, 256, smem, st>>>(src, dst, n, BitsDigit{plan.shift(p), (1u << plan.width(p)) - 1u}, plan.width(p),
-                                                                               base + p * kRsMaxRadix, status, counters + p);
-        else
-            rs_pass_kernel<512, BitsDigit><<<(unsigned)tiles, 512, smem, st>>>(src, dst, n, BitsDigit{plan.shift(p), (1u << plan.width(p)) - 1u}, plan.width(p),
-                                                                               base + p * kRsMaxRadix, status, counters + p);
+        if ((e = rs_launch_pass((unsigned)tiles, st, src, dst, n, BitsDigit{plan.shift(p), (1u << plan.width(p)) - 1u}, plan.width(p),
+                                base + p * kRsMaxRadix, status, counters + p)) != cudaSuccess)
+            return fail(e, "pass launch");
         ctx->launches++;
         trace.mark("digit pass");
         uint64_t *t = src; src = dst; dst = t;
@@ -373,11 +419,6 @@ int partition_by_range(aix_ctx *ctx, cudaStream_t st, const uint64_t *keys, uint
     while ((1 << bits) < n_ranges) ++bits;
     const uint64_t tiles = (n + 256 * kRsItems - 1) / (256 * kRsItems);
     if (tiles >= (1ull << 31)) return ctx->fail(AIX_ERR_ARG, "partition: too many keys");
-    static bool attr_set[64] = {};
-    if (!attr_set[ctx->device & 63]) {
-        AIX_CUDA(ctx, cudaFuncSetAttribute(rs_pass_kernel<256, RangeDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem(256)));
-        attr_set[ctx->device & 63] = true;
-    }
     const size_t front = (size_t)kRsMaxRadix * 8 * 2 + 64;
     const size_t status_bytes = (size_t)tiles * ((size_t)1 << bits) * 8;
     unsigned char *scratch = nullptr;
@@ -396,10 +437,10 @@ int partition_by_range(aix_ctx *ctx, cudaStream_t st, const uint64_t *keys, uint
     if (hgrid < 1) hgrid = 1;
     rs_hist1_kernel<RangeDigit><<<hgrid, 512, 0, st>>>(keys, n, dg, hist);
     rs_base_kernel<<<1, kRsMaxRadix, 0, st>>>(hist, base);
-    rs_pass_kernel<256, RangeDigit><<<(unsigned)tiles, 256, rs_smem(256), st>>>(keys, out, n, dg, bits, base, status, counter);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = rs_launch_pass((unsigned)tiles, st, keys, out, n, dg, bits, base, status, counter);
     ctx->launches += 3;
     unsigned long long h[kRsMaxRanges];
-    if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, hist, sizeof h, cudaMemcpyDeviceToHost, st);
     aix_pool_free(ctx, scratch, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -714,11 +714,15 @@ int launch_tf13(aix_ctx *ctx, const aix_index13 *ix, cudaStream_t st, const uint
 // host spins on the answer: two PCIe traversals per call.  The kernel bounds its own life (idle timeout on
 // %globaltimer AND a hard cap of empty polls), so an implicit device synchronisation elsewhere waits a millisecond at
 // most; the host relaunches it on demand and falls back to the launch path if it ever fails to answer.
-// Slot layout (192 bytes of mapped host memory).  Request: six 16-byte chunks, each = 12 payload bytes + the sequence
-// number; the host writes every chunk with ONE 16-byte store, the device reads the first three chunks per poll (one
-// PCIe round trip: the loads are issued together) and accepts a request when their tags agree, so no ordering between
-// chunks is needed.  Payload bytes 0..1 = length, kind (23 / 13); bytes 2.. = the query.  Response: ONE 64-bit word
-// {tf, sequence number} written with one store -- no fence, no second word.  `alive` is cleared by the kernel's last store.
+// Slot layout (192 bytes of mapped host memory).  Request: up to six 16-byte chunks, each = 12 payload bytes + the
+// sequence number; the host writes every chunk with ONE 16-byte store.  Payload bytes 0..1 = length, kind; bytes 2.. = the
+// query.  The device polls chunk 0 ALONE: reads of host memory queue behind each other on the bus (measured on this box,
+// profiles/r02_mailbox.txt: one 16-byte read in flight 3.8 us per echo, three 4.6 us, twelve 10 us), so one read per poll
+// it is.  An upper-case ACGT 13- or 23-mer -- every query that can hit -- travels 2-bit packed inside chunk 0 (kinds
+// kMboxPacked23 / 13) and is answered after that one read; any other string needs chunks 1..2 (3..5 beyond 34 bytes),
+// fetched once chunk 0's tag has changed and accepted when their tags agree, so no ordering between chunks is needed.
+// Response: ONE 64-bit word {tf, sequence number} written with one store -- no fence, no second word.  `alive` is cleared
+// by the kernel's last store.
 struct MboxSlot {
     uint32_t req[6][4];      // [c][0..2] payload, [c][3] tag
     unsigned long long resp; // (seq << 32) | tf
@@ -744,6 +748,10 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
+constexpr uint32_t kMboxEcho = 0xEEu;      // answered with its length at once (transport latency probe)
+constexpr uint32_t kMboxPacked23 = 0xB7u;  // payload bytes 2..9 = the 23-mer, code of character j ("ACGT" order) at bits [2j+1:2j]
+constexpr uint32_t kMboxPacked13 = 0xBDu;  // same for a 13-mer
+
 __global__ void __launch_bounds__(32) mailbox_kernel(Index23Dev ix, MphfDev m23, MphfDev m13, const uint64_t *tf13_mphf,
                                                    const uint64_t *tf13_direct, MboxSlot *slot, uint32_t seen,
                                                    unsigned long long idle_ns, uint32_t max_empty_polls) {
@@ -751,9 +759,9 @@ __global__ void __launch_bounds__(32) mailbox_kernel(Index23Dev ix, MphfDev m23,
     uint64_t t_last = global_timer_ns();
     uint32_t empty = 0;
     for (;;) {
-        const uint4 c0 = ld_relaxed_sys_u32x4(slot->req[0]), c1 = ld_relaxed_sys_u32x4(slot->req[1]), c2 = ld_relaxed_sys_u32x4(slot->req[2]);
+        const uint4 c0 = ld_relaxed_sys_u32x4(slot->req[0]);
         const uint32_t s = c0.w;
-        if (s == seen || c1.w != s || c2.w != s) {  // nothing new (or a request half written: the next poll sees the rest)
+        if (s == seen) {  // nothing new
             if ((++empty & 15u) == 0u) {
                 if (ld_relaxed_sys_u32(&slot->quit) != 0u) break;
                 if (empty > max_empty_polls || global_timer_ns() - t_last > idle_ns) break;
@@ -761,24 +769,43 @@ __global__ void __launch_bounds__(32) mailbox_kernel(Index23Dev ix, MphfDev m23,
             continue;
         }
         uint32_t b[18];  // payload words
-        b[0] = c0.x; b[1] = c0.y; b[2] = c0.z; b[3] = c1.x; b[4] = c1.y; b[5] = c1.z; b[6] = c2.x; b[7] = c2.y; b[8] = c2.z;
-        const uint32_t len0 = b[0] & 0xFFu, kind = (b[0] >> 8) & 0xFFu;
-        const uint32_t len = len0 > kMboxPayload ? kMboxPayload : len0;
 #pragma unroll
-        for (int j = 9; j < 18; ++j) b[j] = 0;
-        if (len > 34u) {  // long odd strings: the other three chunks (their tags must agree as well)
-            uint4 c3, c4, c5;
+        for (int j = 3; j < 18; ++j) b[j] = 0;
+        b[0] = c0.x; b[1] = c0.y; b[2] = c0.z;
+        const uint32_t len0 = b[0] & 0xFFu;
+        uint32_t kind = (b[0] >> 8) & 0xFFu;
+        uint32_t len = len0 > kMboxPayload ? kMboxPayload : len0;
+        const bool one_chunk = kind == kMboxEcho || kind == kMboxPacked23 || kind == kMboxPacked13;
+        if (!one_chunk) {  // a string: chunks 1..2 (their tags must agree; the host stored them before chunk 0)
+            uint4 c1, c2;
             do {
-                c3 = ld_relaxed_sys_u32x4(slot->req[3]); c4 = ld_relaxed_sys_u32x4(slot->req[4]); c5 = ld_relaxed_sys_u32x4(slot->req[5]);
-            } while (c3.w != s || c4.w != s || c5.w != s);
-            b[9] = c3.x; b[10] = c3.y; b[11] = c3.z; b[12] = c4.x; b[13] = c4.y; b[14] = c4.z; b[15] = c5.x; b[16] = c5.y; b[17] = c5.z;
+                c1 = ld_relaxed_sys_u32x4(slot->req[1]); c2 = ld_relaxed_sys_u32x4(slot->req[2]);
+            } while (c1.w != s || c2.w != s);
+            b[3] = c1.x; b[4] = c1.y; b[5] = c1.z; b[6] = c2.x; b[7] = c2.y; b[8] = c2.z;
+            if (len > 34u) {
+                uint4 c3, c4, c5;
+                do {
+                    c3 = ld_relaxed_sys_u32x4(slot->req[3]); c4 = ld_relaxed_sys_u32x4(slot->req[4]); c5 = ld_relaxed_sys_u32x4(slot->req[5]);
+                } while (c3.w != s || c4.w != s || c5.w != s);
+                b[9] = c3.x; b[10] = c3.y; b[11] = c3.z; b[12] = c4.x; b[13] = c4.y; b[14] = c4.z; b[15] = c5.x; b[16] = c5.y; b[17] = c5.z;
+            }
         }
         // the query bytes start at payload byte 2: realign into words
         uint32_t q[17];
 #pragma unroll
         for (int j = 0; j < 17; ++j) q[j] = __funnelshift_r(b[j], b[j + 1], 16);
+        if (kind == kMboxPacked23 || kind == kMboxPacked13) {  // back to the string the caller passed: same path from here on
+            const uint64_t w0 = ascii8_from_codes_le(q[0] & 0xFFFFu), w1 = ascii8_from_codes_le(q[0] >> 16),
+                           w2 = ascii8_from_codes_le(q[1] & 0xFFFFu);
+            len = kind == kMboxPacked23 ? 23u : 13u;
+            kind = len;
+            q[0] = (uint32_t)w0; q[1] = (uint32_t)(w0 >> 32); q[2] = (uint32_t)w1; q[3] = (uint32_t)(w1 >> 32);
+            q[4] = (uint32_t)w2; q[5] = (uint32_t)(w2 >> 32);
+        }
         uint64_t res[2] = {0, 0};
-        if (kind == 23u) {
+        if (kind == kMboxEcho) {
+            res[0] = len0;
+        } else if (kind == 23u) {
             const uint64_t mask2 = len >= 23u ? 0x00FFFFFFFFFFFFFFull : (len > 16u ? ((1ull << (8 * (len - 16u))) - 1) : 0ull);
             const uint64_t mask1 = len >= 16u ? ~0ull : (len > 8u ? ((1ull << (8 * (len - 8u))) - 1) : 0ull);
             const uint64_t mask0 = len >= 8u ? ~0ull : ((1ull << (8 * len)) - 1);
@@ -822,7 +849,8 @@ static bool mbox_enabled() {
 }
 
 // one TF query (k = 23 on ix23, or k = 13 on ix13) through the mailbox; false = not answered (caller takes the launch path)
-static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *rec, uint32_t len, uint32_t *out) {
+static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 *ix13, const uint8_t *rec, uint32_t len, uint32_t *out,
+                       bool echo = false) {
     if (!mbox_enabled() || ctx->mbox_broken || len > kMboxPayload) return false;
     if (!ctx->mbox_host) {
         if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
@@ -863,14 +891,30 @@ static bool mbox_query(aix_ctx *ctx, const aix_index23 *ix23, const aix_index13 
             return false;
         }
     }
-    // request: six 16-byte chunks {12 payload bytes, sequence number}; the first three cover a 23-byte query
+    // request: 16-byte chunks {12 payload bytes, sequence number}.  An upper-case ACGT k-mer of the index's k goes 2-bit
+    // packed in chunk 0 alone; anything else as its bytes in three (six beyond 34 bytes) chunks.
     const uint32_t seq = ++ctx->mbox_seq;
     alignas(16) uint8_t pay[72] = {0};
+    int n_chunks;
+    uint64_t packed = 0;
+    bool acgt = !echo && len == (ix23 ? 23u : 13u);
+    for (uint32_t j = 0; acgt && j < len; ++j) {
+        const uint8_t ch = rec[j];
+        const uint32_t code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+        if (code > 3u) acgt = false;
+        packed |= (uint64_t)(code & 3u) << (2 * j);
+    }
     pay[0] = (uint8_t)len;
-    pay[1] = ix23 ? 23 : 13;
-    memcpy(pay + 2, rec, len);
-    const int n_chunks = len > 34u ? 6 : 3;
-    for (int c = n_chunks - 1; c >= 0; --c) {  // chunk 0 (the one the poll looks at first) last
+    if (acgt) {
+        pay[1] = (uint8_t)(ix23 ? kMboxPacked23 : kMboxPacked13);
+        memcpy(pay + 2, &packed, 8);
+        n_chunks = 1;
+    } else {
+        pay[1] = echo ? (uint8_t)kMboxEcho : (ix23 ? 23 : 13);
+        memcpy(pay + 2, rec, len);
+        n_chunks = echo ? 1 : (len > 34u ? 6 : 3);
+    }
+    for (int c = n_chunks - 1; c >= 0; --c) {  // chunk 0 (the one the device polls) last
         alignas(16) uint32_t w[4];
         memcpy(w, pay + 12 * c, 12);
         w[3] = seq;
@@ -1086,6 +1130,26 @@ int aix_tf23_batch_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs_
     if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     return launch_tf23(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
+}
+
+int aix_tf23_single_call_latency(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uint32_t stride, uint64_t n, uint32_t *tf_out,
+                                 double *echo_ns, double *query_ns) {
+    if (!ctx || !ix || !recs || !stride || !echo_ns || !query_ns) return AIX_ERR_ARG;
+    *echo_ns = *query_ns = 0;
+    if (n == 0) return AIX_OK;
+    const uint32_t len = stride > kMboxPayload ? kMboxPayload : stride;
+    uint32_t v = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (!mbox_query(ctx, ix, nullptr, recs, len, &v, phase == 0)) return ctx->fail(AIX_ERR_CUDA, "the mailbox kernel is not available");
+        const double t0 = AixTrace::now();
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!mbox_query(ctx, ix, nullptr, recs + i * stride, len, &v, phase == 0))
+                return ctx->fail(AIX_ERR_CUDA, "the mailbox kernel stopped answering");
+            if (phase == 1 && tf_out) tf_out[i] = v;
+        }
+        (phase == 0 ? *echo_ns : *query_ns) = (AixTrace::now() - t0) * 1e9 / (double)n;
+    }
+    return AIX_OK;
 }
 
 int aix_tf23_batch(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uint32_t stride, const uint8_t *lens,

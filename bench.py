@@ -397,10 +397,10 @@ def single_process_multi_legs(torch, capi, args, world, extra):
                             raise RuntimeError((lib.aix_multi_last_error(mg) or b"").decode())
                     build()  # warm-up (pools)
                     build()
-                    dev_ms = st.emit_partition_ms + st.exchange_ms + st.sort_finalize_ms
+                    dev_ms = st.emit_partition_ms + st.alloc_ms + st.exchange_ms + st.sort_finalize_ms
                     res[tag] = {"reads": nr, "index_keys": n_keys, "occurrences": int(st.positions), "stats": st.as_dict(),
-                                "value": st.positions / (dev_ms / 1e3), "unit": "occurrences/s (emit + exchange + sort phases, max over GPUs; "
-                                "reads upload and positions download excluded)", "device_phases_ms": dev_ms,
+                                "value": st.positions / (dev_ms / 1e3), "unit": "occurrences/s (emit + exchange-buffer cudaMalloc + exchange + sort "
+                                "phases, max over GPUs; reads upload and positions download excluded)", "device_phases_ms": dev_ms,
                                 "nvlink_bytes": int(st.peer_bytes), "single_gpu_ms": (extra.get("c5_positions") or {}).get("ms_per_step")}
                 else:
                     gp = np.zeros(nr * 128, dtype=np.uint64)

@@ -166,6 +166,12 @@ int aix_tf23_batch(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uin
 int aix_tf23_batch_dev(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs_dev,
                        uint32_t stride, const uint8_t *lens_dev, uint64_t q, int mode,
                        void *out_dev);
+/* Latency of single calls (aix_tf23_batch with q == 1, mode AIX_Q_TF = AindexWrapper::get_tf_value, python_wrapper.cpp:610-627)
+ * measured from C, without an interpreter in the loop: the n queries (n x stride bytes, host) are sent one by one through the
+ * resident mailbox kernel, first as echo requests (answered at once: host store -> device poll over PCIe -> device store ->
+ * host load = the transport's share), then as real lookups (tf_out[n], may be NULL).  Nanoseconds per call, averaged. */
+int aix_tf23_single_call_latency(aix_ctx *ctx, const aix_index23 *ix, const uint8_t *recs, uint32_t stride, uint64_t n,
+                                 uint32_t *tf_out, double *echo_ns, double *query_ns);
 /* Index split by hash-id range over several GPUs (one aix_index23 per rank holding records [lo, hi) of the
  * checker / tf arrays, uploaded with aix_index23_upload[_dev] on the slice; the MPHF is replicated):
  *   aix_tf23_probes_dev: query i -> probes_dev[4*i .. 4*i+3] = {id1, kmer1, id2, kmer2}; id = ~0 means "no probe".
@@ -290,6 +296,7 @@ int aix_count13_multi_dev(aix_multi *mg, const aix_mphf *m, const uint8_t *const
 typedef struct aix_multi_build_stats {
     double total_ms, upload_scan_ms, emit_partition_ms, exchange_ms, sort_finalize_ms, download_ms;
     uint64_t keys, peer_bytes, positions;
+    double alloc_ms; /* cudaMalloc of the exchange buffers (peer-visible memory outside the pool), not part of exchange_ms */
 } aix_multi_build_stats;
 int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *const *ix, const uint8_t *reads, uint64_t len,
                                 uint64_t *indices_out, uint64_t *positions_out, aix_multi_build_stats *stats);

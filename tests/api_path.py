@@ -80,6 +80,20 @@ if __name__ == "__main__":
     line = {"queries": N, "ours_single_call_qps": sq, "ours_coverage_calls_per_s": cov_single, "hit_fraction": float((out_list > 0).mean()),
             "ours_list_str_qps": N / dt_list, "ours_ndarray_qps": N / best,
             "ndarray_equals_list": bool(np.array_equal(out_arr, out_list))}
+    # the single-call path timed from C (no interpreter in the loop): transport-only echo, then real lookups
+    try:
+        from aindex_b200 import capi
+        ctx = capi.Context(0)
+        m = capi.Mphf.load(ctx, PREFIX + ".pf")
+        kb = np.fromfile(PREFIX + ".kmers.bin", dtype=np.uint64)
+        tfb = np.fromfile(PREFIX + ".tf.bin", dtype=np.uint32)
+        ix = capi.Index23.upload(ctx, m, kb, tfb)
+        lat = ix.single_call_latency(arr[:20000])
+        line["c_single_call_echo_ns"] = lat["echo_ns"]
+        line["c_single_call_lookup_ns"] = lat["query_ns"]
+        line["c_single_call_equals_batch"] = bool(np.array_equal(lat["tf"], out_list[:20000]))
+    except Exception as exc:  # report, do not hide
+        line["c_single_call_error"] = repr(exc)
     r = subprocess.run([sys.executable, __file__, "--reference"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     if r.returncode == 0 and r.stdout.strip():
         ref = json.loads(r.stdout.strip().splitlines()[-1])

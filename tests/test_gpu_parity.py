@@ -745,6 +745,12 @@ def test_single_query_mailbox(capi, oracle, ctx, idx23, oidx23, m13, g13, monkey
         idx23.query([q[i % len(q)]])
     rate_on = n / (time.perf_counter() - t0)
     print(f"[single-call path through ctypes] {rate_on:.0f} calls/s")
+    # the same calls timed from C (no interpreter in the loop), echo requests first: same answers
+    k23 = np.frombuffer(b"".join(x for x in q if len(x) == 23), dtype=np.uint8).reshape(-1, 23)
+    lat = idx23.single_call_latency(k23)
+    assert np.array_equal(lat["tf"], idx23.query(k23))
+    assert 0 < lat["echo_ns"] <= lat["query_ns"] * 1.5
+    print(f"[single call from C] echo {lat['echo_ns']:.0f} ns, lookup {lat['query_ns']:.0f} ns")
 
 
 # ---------------------------------------------------------------------------- size-independent properties
