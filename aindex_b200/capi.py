@@ -91,6 +91,8 @@ SIGNATURES = {
     "aix_index23_fill_dev": (_i, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "aix_tf23_batch": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
     "aix_tf23_batch_dev": (_i, [_vp, _vp, _vp, _u32, _vp, _u64, _i, _vp]),
+    "aix_index23_filter_stats": (_i, [_vp, _vp]),
+    "aix_index23_set_filter": (_i, [_vp, _i]),
     "aix_tf23_single_call_latency": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _vp, _vp]),
     "aix_tf23_probes_dev": (_i, [_vp, _vp, _u64, _i, _vp, _u32, _vp, _u64, _vp]),
     "aix_probe23_dev": (_i, [_vp, _vp, _vp, _u64, _vp]),
@@ -500,6 +502,17 @@ class Index23:
         self.ctx.check(lib().aix_tf23_batch(self.ctx.handle, self._h, _p(recs), recs.shape[1], _p(lens), q,
                                             mode, _p(out)))
         return out
+
+    @property
+    def filter_stats(self) -> dict:
+        a = np.zeros(6, dtype=np.uint64)
+        self.ctx.check(lib().aix_index23_filter_stats(self._h, _p(a)))
+        rate = None if int(a[5]) == 0xFFFFFFFFFFFFFFFF else int(a[5]) / 1e6
+        return {"filter_bytes": int(a[0]), "queries_counted": int(a[1]), "passed": int(a[2]), "batches_filter": int(a[3]),
+                "batches_direct": int(a[4]), "pass_rate": rate}
+
+    def set_filter(self, mode: str = "auto"):
+        self.ctx.check(lib().aix_index23_set_filter(self._h, {"auto": 0, "on": 1, "off": 2}[mode]))
 
     def single_call_latency(self, kmers) -> dict:
         """ns per single get_tf_value call measured from C (aix_tf23_single_call_latency): echo = transport only."""

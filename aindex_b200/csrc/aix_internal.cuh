@@ -42,6 +42,17 @@ struct aix_index23 {
     int fp_bits = 0;            // 8 or 4 when fp_dev is set
     uint4 *frecs_dev = nullptr; // fused MPHF + 4-bit fingerprint records (device_common.cuh); replaces the tier when set
     uint64_t frecs_bytes = 0;
+    // front filter (device_common.cuh: Index23Dev::bloom) and what the batch launcher has learnt about the traffic:
+    // the filter kernel counts the queries it saw and those that passed the filter (sampled CTAs); the counts come back
+    // with an asynchronous 16-byte copy after each of its launches and steer the next launches (tf_query.cu)
+    uint2 *bloom_dev = nullptr;
+    uint32_t bloom_words = 0;
+    unsigned long long *qstats_dev = nullptr;            // {queries, passed}
+    volatile unsigned long long *qstats_host = nullptr;  // pinned copy
+    mutable unsigned long long seen_q = 0, seen_p = 0, launches_filter = 0, launches_direct = 0;
+    mutable double pass_rate = -1.0;                     // < 0: nothing observed yet
+    mutable int direct_since_probe = 0;
+    int filter_mode = 0;                                 // 0 = decide from the pass rate, 1 = always, 2 = never (aix_index23_set_filter)
     // the MPHF as this index's kernels see it: the fused records when they exist
     aix::MphfDev mphf_dev() const {
         aix::MphfDev d = mphf->dev();
@@ -51,6 +62,7 @@ struct aix_index23 {
     aix::Index23Dev dev() const {
         aix::Index23Dev d;
         d.n = n; d.canonical_only = canonical_only; d.recs = recs_dev; d.fp = fp_dev; d.fp_bits = fp_bits;
+        d.bloom = bloom_dev; d.bloom_words = bloom_words;
         return d;
     }
 };

@@ -52,7 +52,25 @@ struct Index23Dev {
     // Exact: fp mismatch => checker mismatch; a match is always confirmed on the full record.
     const uint8_t *fp;  // nullptr = tier disabled (index too large to keep it in L2)
     int fp_bits;        // 8: fp[h]; 4: nibble (h & 1) of fp[h >> 1] (half the L2 footprint, 1/16 false positives)
+    // Optional membership filter in FRONT of the MPHF (canonical-only indexes): a blocked Bloom filter, one 64-bit word
+    // per key (two bits in each half), ~8 bits per key.  A k-mer whose four bits are not all set is in no record: the
+    // query is answered with ONE 8-byte L2 request and without the Jenkins hash, the three MPHF record loads and the
+    // rank.  No false negatives (every stored k-mer set its bits), so answers do not change.  tf_query.cu decides per
+    // batch whether the filter pays (miss-dominated batches) from the pass rate it observes.
+    const uint2 *bloom;    // nullptr = no filter
+    uint32_t bloom_words;
 };
+
+// word and bit masks of a canonical 23-mer code in the front filter (same function builds and tests)
+__device__ __forceinline__ void bloom_slot(uint64_t c, uint32_t n_words, uint32_t &word, uint32_t &mlo, uint32_t &mhi) {
+    uint32_t h = (uint32_t)c * 0x9E3779B1u + (uint32_t)(c >> 32) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    uint32_t g = h * 0x297A2D39u;
+    g ^= g >> 15;
+    word = __umulhi(h, n_words);
+    mlo = (1u << (g & 31u)) | (1u << ((g >> 5) & 31u));
+    mhi = (1u << ((g >> 10) & 31u)) | (1u << ((g >> 15) & 31u));
+}
 
 __device__ __host__ __forceinline__ uint32_t fingerprint8(uint64_t kmer) {
     uint32_t x = (uint32_t)kmer ^ (uint32_t)(kmer >> 23);
@@ -82,6 +100,11 @@ __device__ __forceinline__ ulonglong2 ld_evict_last_u64x2(const ulonglong2 *p) {
     ulonglong2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
                  : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_evict_last_u32x2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_policy_evict_last()));
     return v;
 }
 __device__ __forceinline__ uint4 ld_evict_first_u32x4(const uint4 *p) {

@@ -173,6 +173,142 @@ __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(
     }
 }
 
+// ---- front filter (Index23Dev::bloom) ---------------------------------------------------------------------------
+// every stored (canonical) k-mer sets its four bits
+__global__ void __launch_bounds__(256) bloom_build_kernel(const uint4 *__restrict__ recs, uint64_t n, unsigned long long *__restrict__ bloom,
+                                                        uint32_t n_words) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = recs[i];
+    uint32_t word, mlo, mhi;
+    bloom_slot(((uint64_t)r.y << 32) | r.x, n_words, word, mlo, mhi);
+    atomicOr(bloom + word, ((unsigned long long)mhi << 32) | mlo);
+}
+
+// get_tf_values on a canonical-only index for batches in which most queries are absent: the ring of tf23_stream_kernel,
+// but a query is first tested against the front filter.  Rejected queries are answered 0 on the spot; the others (stored
+// k-mers, ~3 % false positives, strings with a non-ACGT byte) are queued per warp -- a 16-bit slot number in shared
+// memory -- and go through query23 in batches of 32, all lanes busy, with the tail of the queue drained when the
+// warp has seen its last tile.  Same answers as tf23_stream_kernel<AIX_Q_TF, true> (tests/test_gpu_parity.py).
+// qstats: {queries seen, queries that passed the filter}, reported by one CTA in 16 (a rate is all the host needs).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_filter_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
+                                                                              uint64_t n_tiles, uint32_t *__restrict__ out,
+                                                                              unsigned long long *__restrict__ qstats) {
+    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kStSlot];
+    __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
+    __shared__ uint16_t queue[kStWarps][64];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;  // this warp's first tile
+    if (tile0 >= n_tiles) return;
+    const uint64_t left = n_tiles - tile0;
+    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
+    const uint64_t policy = l2_policy_evict_first();
+    constexpr uint32_t kStride = kStWarps * kStTileBytes;
+    const uint8_t *src = recs + tile0 * kStTileBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStStages - 1; ++s) {
+            if ((uint32_t)s < my_tiles) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(kStTileBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(ring0 + (uint32_t)kStSlot * s), "l"(src + (uint64_t)kStride * s), "r"(kStTileBytes), "r"(bar0 + 8u * s), "l"(policy) : "memory");
+            }
+        }
+    }
+    src += (uint64_t)kStride * (kStStages - 1);
+    const uint64_t i0 = tile0 * 32u;  // first query of this warp; slot s of the warp = query i0 + (s >> 5) * 256 + (s & 31)
+    const uint64_t last_query = n_tiles * 32u - 1;
+    uint16_t *wq = queue[wid];
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qn = 0, n_passed = 0;
+    // queued slots [0, cnt) through the full lookup, one per lane
+    auto drain = [&](uint32_t cnt) {
+        if (lane < cnt) {
+            const uint32_t s = wq[lane];
+            const uint64_t i = i0 + (uint64_t)(s >> 5) * (kStWarps * 32u) + (s & 31u);
+            const uint8_t *p = recs + i * 23;
+            uint64_t r0, r1, r2;
+            if (i != last_query) load_window23(p, r0, r1, r2);
+            else {  // the last query of the batch: never read past the buffer
+                r0 = r1 = r2 = 0;
+#pragma unroll 1
+                for (int j = 0; j < 23; ++j) {
+                    const uint64_t b = p[j];
+                    if (j < 8) r0 |= b << (8 * j);
+                    else if (j < 16) r1 |= b << (8 * (j - 8));
+                    else r2 |= b << (8 * (j - 16));
+                }
+            }
+            query23<AIX_Q_TF, true>(ix, m, r0, r1, r2, 23u, p, i, out);
+        }
+        __syncwarp();
+    };
+    uint32_t slot = 0, phase = 0;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
+            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
+        }
+        src += kStride;
+        {
+            uint32_t done;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
+            } while (!done);
+        }
+        const uint32_t base = lane * 23u;
+        const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
+        uint32_t x0, x1, x2, x3, x4, x5, x6;
+        asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
+                     "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
+                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
+        __syncwarp();
+        const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
+                       y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
+        const uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
+                       r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
+        bool all_acgt;
+        const uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
+        uint32_t word, mlo, mhi;
+        bloom_slot(u <= r ? u : r, ix.bloom_words, word, mlo, mhi);
+        const uint2 w = ld_evict_last_u32x2(ix.bloom + word);
+        const bool pass = !all_acgt || ((w.x & mlo) == mlo && (w.y & mhi) == mhi);
+        if (!pass) __stcs(out + i0 + (uint64_t)it * (kStWarps * 32u) + lane, 0u);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+        if (b) {
+            if (pass) wq[qn + __popc(b & lt)] = (uint16_t)(it * 32u + lane);
+            qn += __popc(b);
+            n_passed += __popc(b);
+            __syncwarp();
+            if (qn >= 32u) {
+                drain(32u);
+                const uint16_t v = wq[32u + lane];
+                __syncwarp();
+                wq[lane] = v;
+                qn -= 32u;
+                __syncwarp();
+            }
+        }
+        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+    }
+    if (qn) drain(qn);
+    if ((blockIdx.x & 15u) == 0u && lane == 0) {
+        atomicAdd(qstats, (unsigned long long)my_tiles * 32ull);
+        atomicAdd(qstats + 1, (unsigned long long)n_passed);
+    }
+}
+
 // get_freq for 23-mers held as 6-byte dna_bitset records (dna_bitseq.hpp:22-61: 4 bases per byte, first base in
 // bits 7:6; 23 bases = 46 bits + 2 zero bits): the smallest form a query batch can cross PCIe in (6 B instead of 23).
 // The 46-bit value is get_dna23_bitset of the string, so this is PHASH_MAP::get_freq(uint64_t) (hash.hpp:123-140).
@@ -627,6 +763,33 @@ static void launch_stream(const aix_ctx *ctx, cudaStream_t st, const Index23Dev 
 }
 
 
+// Does the next batch go through the front filter?  AIX_INDEX23_FILTER=on|off forces; otherwise the pass rate the filter
+// kernel reported decides: unknown -> yes (the first batches are the probe), <= 25 % passed -> yes, else the direct
+// kernel with one filtered batch in 32 to notice when the traffic changes.  (With more than a quarter of the queries
+// passing, the filter's extra request and the second pass over the passing queries cost more than the filter saves.)
+static bool filter_wanted(const aix_index23 *ix) {
+    if (!ix->bloom_dev || !ix->canonical_only) return false;
+    static int env_mode = -1;  // 0 auto, 1 on, 2 off
+    if (env_mode < 0) {
+        const char *e = getenv("AIX_INDEX23_FILTER");
+        env_mode = !e ? 0 : (!strcmp(e, "on") ? 1 : (!strcmp(e, "off") ? 2 : 0));
+    }
+    const int forced = ix->filter_mode ? ix->filter_mode : env_mode;
+    if (forced) return forced == 1;
+    const unsigned long long q = ix->qstats_host[0], p = ix->qstats_host[1];
+    if (q > ix->seen_q && p >= ix->seen_p && p - ix->seen_p <= q - ix->seen_q) {
+        ix->pass_rate = (double)(p - ix->seen_p) / (double)(q - ix->seen_q);
+        ix->seen_q = q;
+        ix->seen_p = p;
+    }
+    if (ix->pass_rate < 0 || ix->pass_rate <= 0.25) return true;
+    if (++ix->direct_since_probe >= 32) {
+        ix->direct_since_probe = 0;
+        return true;
+    }
+    return false;
+}
+
 template <int kMode>
 static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
                           const uint8_t *lens, uint64_t q, void *out) {
@@ -635,7 +798,29 @@ static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_
     const bool fixed = (stride == 23 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
     if (fixed && tf23_kernel_choice() == 1 && q >= 32) {
         const uint64_t n_tiles = q / 32;
-        if (ix->canonical_only) {
+        if (kMode == AIX_Q_TF && q >= 4096 && filter_wanted(ix)) {
+            const uint64_t grid = (n_tiles + kStTilesPerCta - 1) / kStTilesPerCta;
+            // register budget of the filter kernel: 4 resident CTAs (64 registers) measured best -- 86.5 G q/s against
+            // 79.6 (68 registers, what ptxas picks) and 83.8 (5 CTAs); AIX_FILTER_MINBLOCKS for A/B runs
+            static int fmin = -1;
+            if (fmin < 0) {
+                const char *e = getenv("AIX_FILTER_MINBLOCKS");
+                fmin = e ? atoi(e) : 4;
+            }
+            // (pinning the filter in the persisting part of L2 with an access-policy window bought 2 %, 86.4 -> 88.3 G q/s:
+            // the kernel is bound by the ALU pipe, 216 instructions per query, not by the filter's L2 misses -- not worth
+            // a device-wide L2 carve-out that the counting kernels would pay for; profiles/r02_filter_sweep.txt)
+            uint32_t *out32 = (uint32_t *)out;
+            unsigned long long *qs = ix->qstats_dev;
+            const unsigned g = (unsigned)grid;
+            if (fmin >= 5) tf23_filter_kernel<5><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            else if (fmin == 4) tf23_filter_kernel<4><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            else tf23_filter_kernel<1><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            // the counts travel back behind the kernel; the next launches read whatever has arrived
+            cudaMemcpyAsync((void *)ix->qstats_host, ix->qstats_dev, 16, cudaMemcpyDeviceToHost, st);
+            ix->launches_filter++;
+        } else if (ix->canonical_only) {
+            ix->launches_direct++;
             if (tf23_min_blocks() >= 6) launch_stream<kMode, true, 6>(ctx, st, id, md, recs, n_tiles, out);
             else if (tf23_min_blocks() == 5) launch_stream<kMode, true, 5>(ctx, st, id, md, recs, n_tiles, out);
             else launch_stream<kMode, true, 1>(ctx, st, id, md, recs, n_tiles, out);
@@ -1053,6 +1238,33 @@ int aix_index23_upload_dev(aix_ctx *ctx, const aix_mphf *m, const uint64_t *chec
         return ctx->fail(AIX_ERR_CUDA, "index23 upload: %s", cudaGetErrorString(e));
     }
     ix->canonical_only = flag ? 0 : 1;
+    // front filter of the batch path: canonical-only whole indexes, AIX_BLOOM_BITS per key (default 8, 0 = none)
+    int bloom_bits = 8;
+    if (const char *eb = getenv("AIX_BLOOM_BITS")) bloom_bits = atoi(eb);
+    if (ix->canonical_only && n >= 1024 && n == m->n && bloom_bits > 0 && bloom_bits <= 64) {
+        const uint64_t words = (n * (uint64_t)bloom_bits + 63) / 64;
+        if (words < (1ull << 32)) {
+            cudaError_t eb = cudaMalloc(&ix->bloom_dev, words * 8);
+            if (eb == cudaSuccess) eb = cudaMalloc(&ix->qstats_dev, 16);
+            if (eb == cudaSuccess) eb = cudaHostAlloc((void **)&ix->qstats_host, 16, cudaHostAllocDefault);
+            if (eb == cudaSuccess) {
+                ix->qstats_host[0] = ix->qstats_host[1] = 0;
+                ix->bloom_words = (uint32_t)words;
+                cudaMemsetAsync(ix->bloom_dev, 0, words * 8, ctx->stream);
+                cudaMemsetAsync(ix->qstats_dev, 0, 16, ctx->stream);
+                bloom_build_kernel<<<aix_grid(n, 256), 256, 0, ctx->stream>>>(ix->recs_dev, n, (unsigned long long *)ix->bloom_dev, ix->bloom_words);
+                ctx->launches++;
+                eb = cudaStreamSynchronize(ctx->stream);
+            }
+            if (eb != cudaSuccess) {  // no room: the index works without the filter
+                cudaGetLastError();
+                if (ix->bloom_dev) cudaFree(ix->bloom_dev);
+                if (ix->qstats_dev) cudaFree(ix->qstats_dev);
+                if (ix->qstats_host) cudaFreeHost((void *)ix->qstats_host);
+                ix->bloom_dev = nullptr; ix->qstats_dev = nullptr; ix->qstats_host = nullptr; ix->bloom_words = 0;
+            }
+        }
+    }
     *out = ix;
     return AIX_OK;
 }
@@ -1105,7 +1317,27 @@ void aix_index23_destroy(aix_ctx *ctx, aix_index23 *ix) {
     if (ix->recs_dev) cudaFree(ix->recs_dev);
     if (ix->fp_dev) cudaFree(ix->fp_dev);
     if (ix->frecs_dev) cudaFree(ix->frecs_dev);
+    if (ix->bloom_dev) cudaFree(ix->bloom_dev);
+    if (ix->qstats_dev) cudaFree(ix->qstats_dev);
+    if (ix->qstats_host) cudaFreeHost((void *)ix->qstats_host);
     delete ix;
+}
+
+int aix_index23_set_filter(aix_index23 *ix, int mode) {
+    if (!ix || mode < 0 || mode > 2) return AIX_ERR_ARG;
+    ix->filter_mode = mode;
+    return AIX_OK;
+}
+
+int aix_index23_filter_stats(const aix_index23 *ix, uint64_t info[6]) {
+    if (!ix || !info) return AIX_ERR_ARG;
+    info[0] = (uint64_t)ix->bloom_words * 8;
+    info[1] = ix->qstats_host ? ix->qstats_host[0] : 0;
+    info[2] = ix->qstats_host ? ix->qstats_host[1] : 0;
+    info[3] = ix->launches_filter;
+    info[4] = ix->launches_direct;
+    info[5] = ix->pass_rate < 0 ? ~0ull : (uint64_t)(ix->pass_rate * 1e6);
+    return AIX_OK;
 }
 
 int aix_index23_info(const aix_index23 *ix, uint64_t info[2]) {

@@ -146,6 +146,15 @@ int aix_index23_info(const aix_index23 *ix, uint64_t info[2]);
  * the separate fingerprint tier (0 when the fingerprints ride inside the MPHF records), info[2] = MPHF record bytes,
  * info[3] = 0 wide MPHF records, 1 compact (48 pairs + u32 rank), 2 fused (16 pairs + 16 x 4-bit fingerprint + u32 rank) */
 int aix_index23_layout(const aix_index23 *ix, uint64_t info[4]);
+/* Front filter of the batch tf path (a blocked Bloom filter over the stored k-mers of a canonical-only index, built at
+ * upload; AIX_BLOOM_BITS per key, default 8, 0 = none).  Batches in which most queries are absent are answered through it
+ * (one 8-byte request per absent query instead of the hash + three MPHF records); the launcher decides per batch from the
+ * pass rate the filter kernel reports (AIX_INDEX23_FILTER=on|off forces).  Answers do not depend on the choice.
+ * info = {filter bytes, queries counted (sampled CTAs), of those passed, batches through the filter, batches direct,
+ *         last pass rate * 1e6 (~0 = none observed yet)}. */
+int aix_index23_filter_stats(const aix_index23 *ix, uint64_t info[6]);
+/* mode 0: the launcher decides per batch (default), 1: every batch through the filter, 2: never */
+int aix_index23_set_filter(aix_index23 *ix, int mode);
 /* index fill on the GPU (replaces compute_index / index_hash_pp, hash.cpp:671-723,
  * :779-881): checker_out[h] = kmers[i], tf_out[h] = counts[i], h = mphf(kmers[i]) */
 int aix_index23_fill(aix_ctx *ctx, const aix_mphf *m, const uint64_t *kmers,
@@ -296,7 +305,7 @@ int aix_count13_multi_dev(aix_multi *mg, const aix_mphf *m, const uint8_t *const
 typedef struct aix_multi_build_stats {
     double total_ms, upload_scan_ms, emit_partition_ms, exchange_ms, sort_finalize_ms, download_ms;
     uint64_t keys, peer_bytes, positions;
-    double alloc_ms; /* cudaMalloc of the exchange buffers (peer-visible memory outside the pool), not part of exchange_ms */
+    double alloc_ms; /* cudaMalloc / cudaFree of the exchange buffers (peer-visible memory outside the pool), not part of exchange_ms */
 } aix_multi_build_stats;
 int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *const *ix, const uint8_t *reads, uint64_t len,
                                 uint64_t *indices_out, uint64_t *positions_out, aix_multi_build_stats *stats);

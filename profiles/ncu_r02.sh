@@ -8,7 +8,10 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --count-rea
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:tf23_stream -s 3 -c 1 -o gpurun_out/${TAG}_tf23 -f $CMD > gpurun_out/${TAG}_ncu_tf23.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tf23_filter -s 3 -c 1 -o gpurun_out/${TAG}_tf23 -f $CMD > gpurun_out/${TAG}_ncu_tf23.log 2>&1
+# the direct kernel (no front filter): what hit-dominated batches run
+AIX_INDEX23_FILTER=off $CMD > gpurun_out/${TAG}_plain3.log 2>&1 &&
+AIX_INDEX23_FILTER=off ncu --set full --clock-control none --import-source on -k regex:tf23_stream -s 3 -c 1 -o gpurun_out/${TAG}_tf23direct -f $CMD > gpurun_out/${TAG}_ncu_tf23direct.log 2>&1
 # positions build at 10 % of C5 (755 M windows, 640 M keys): emit pass, one digit pass of the sort, finalize
 CMD="python bench_configs.py --configs c5 --scale 0.1 --no-checks"
 $CMD > gpurun_out/${TAG}_c5_plain.log 2>&1 &&

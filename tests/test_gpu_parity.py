@@ -860,6 +860,44 @@ def test_tf23_layout_and_kernel_variants(capi, oracle, ctx, oidx23, monkeypatch,
     m.close()
 
 
+@pytest.mark.parametrize("bits", ["8", "3", "64"])
+def test_tf23_front_filter(capi, oracle, ctx, oidx23, monkeypatch, bits):
+    """The Bloom filter in front of the MPHF (batches of absent k-mers: one 8-byte request instead of the lookup): forced
+    on, forced off and left to the launcher, the fixed-stride TF path gives the oracle's answers for stored k-mers on
+    both strands, absent k-mers, strings with lower-case / N / control bytes, at batch sizes around the tile, the
+    queue and the CTA; a sparse filter (3 bits per key: most queries pass) and a wide one (64 bits per key) as well."""
+    monkeypatch.setenv("AIX_BLOOM_BITS", bits)
+    m = capi.Mphf.from_arrays(ctx, oidx23.mphf.n, oidx23.mphf.hash_domain, oidx23.mphf.seed, oidx23.mphf.words,
+                              oidx23.mphf.block_ranks)
+    ix = capi.Index23.upload(ctx, m, oidx23.checker, oidx23.tf)
+    assert ix.filter_stats["filter_bytes"] == (oidx23.checker.size * int(bits) + 63) // 64 * 8
+    rng = np.random.default_rng(77 + int(bits))
+    km = ctx.decode(oidx23.checker, 23)
+    for nq, p_hit in ((4096, 0.5), (4127, 0.0), (65_536, 0.02), (100_003, 0.9), (300_000, 0.0), (262_144, 1.0)):
+        r23 = rng.choice(ACGT, size=(nq, 23))
+        hit = rng.random(nq) < p_hit
+        pick = rng.integers(0, oidx23.checker.size, size=int(hit.sum()))
+        r23[hit] = km[pick]
+        flip = hit & (rng.random(nq) < 0.5)
+        r23[flip] = ctx.decode(ctx.revcomp(ctx.encode(r23[flip], 23), 23), 23)
+        odd = rng.random(nq) < 0.01
+        r23[odd, rng.integers(0, 23, size=int(odd.sum()))] = rng.choice(np.frombuffer(b"Nnacgt\n\x00~", dtype=np.uint8), size=int(odd.sum()))
+        want = oidx23.batch(r23, None, oracle.MODE_TF)
+        for mode in ("on", "off", "auto", "auto"):
+            ix.set_filter(mode)
+            assert np.array_equal(ix.query(r23), want), f"filter {mode}, {nq} queries, hit fraction {p_hit}"
+    st = ix.filter_stats
+    assert st["batches_filter"] > 0 and st["batches_direct"] > 0 and st["queries_counted"] > 0
+    # every stored k-mer passes its own filter: no false negatives on either strand
+    ix.set_filter("on")
+    reps = -(-8192 // km.shape[0])
+    allk = np.tile(km, (reps, 1))
+    assert np.array_equal(ix.query(allk), np.tile(oidx23.tf, reps))
+    assert np.array_equal(ix.query(ctx.decode(ctx.revcomp(ctx.encode(allk, 23), 23), 23)), np.tile(oidx23.tf, reps))
+    ix.close()
+    m.close()
+
+
 @pytest.mark.parametrize("kernel", [0, 1])
 def test_tf23_fused_layout(capi, oracle, ctx, oidx23, monkeypatch, kernel, golden_dir):
     """The fused layout (16 pair values + 16 x 4-bit fingerprints + rank per 16-byte MPHF record; the default when the
