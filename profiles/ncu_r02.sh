@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 ncu captures (B200_PROFILING.md recipe: the plain run must exit 0 right before each ncu run; one GPU).
-#   bash profiles/ncu_r02.sh <tag>        -> gpurun_out/<tag>_{tf23,c5emit,c5sort}.ncu-rep + launch list
+#   bash profiles/ncu_r02.sh <tag>        -> gpurun_out/<tag>_*_ncu.txt summaries (+ the report of the headline kernel) + launch list
+# gpurun brings back at most 64 MiB: the reports are summarised on the box and all but the headline kernel's are deleted.
 set -u
 TAG="${1:-r02}"
 mkdir -p gpurun_out
@@ -26,3 +27,14 @@ for spec in "c1:tf13_stream_kernel:3:1" "c4:coverage_kernel:1:1"; do
   $CMD > gpurun_out/${TAG}_${cfg}_plain.log 2>&1 &&
   ncu --set full --clock-control none -k regex:"$pat" -s $skip -c $cnt -o gpurun_out/${TAG}_${cfg} -f $CMD > gpurun_out/${TAG}_ncu_${cfg}.log 2>&1
 done
+
+# summaries on the box (the reports together exceed what gpurun_out may carry back)
+for r in tf23 tf23direct c5emit c5sort c1 c4; do
+  [ -f gpurun_out/${TAG}_$r.ncu-rep ] && python profiles/summarize_ncu.py kernel gpurun_out/${TAG}_$r.ncu-rep gpurun_out/${TAG}_${r}_ncu.txt > /dev/null 2>&1
+done
+python profiles/summarize_ncu.py launches gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launches.txt > /dev/null 2>&1
+python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix18tf23_filter_kernelILi4E 100000000 gpurun_out/${TAG}_tf23_instr.txt > /dev/null 2>&1
+python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23direct.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix18tf23_stream_kernelILi0ELb1ELi1E 100000000 gpurun_out/${TAG}_tf23direct_instr.txt > /dev/null 2>&1
+python profiles/instr_breakdown.py gpurun_out/${TAG}_c5sort.ncu-rep aindex_b200/csrc/_obj/radix_sort.o _ZN3aix14rs_pass_kernelILi256ELi7ELi4ENS_9BitsDigitE 640000000 gpurun_out/${TAG}_c5sort_instr.txt > /dev/null 2>&1
+rm -f gpurun_out/${TAG}_tf23direct.ncu-rep gpurun_out/${TAG}_c5emit.ncu-rep gpurun_out/${TAG}_c1.ncu-rep gpurun_out/${TAG}_c4.ncu-rep gpurun_out/${TAG}_launches.csv
+du -sh gpurun_out
