@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -99,9 +100,8 @@ struct aix_ctx {
     // 100 GB again (measured: 50-700 ms per build with cudaMalloc / cudaFree, more while NVML is being polled).
     // aix_ctx_trim() hands the cached memory back.
     cudaMemPool_t pool = nullptr;
-    std::unordered_set<void *> plain_allocs;  // cudaMalloc'ed buffers that travel through the builders' pool-free calls (multi-GPU exchange buffers)
-    bool defer_plain_free = false;      // cudaFree of multi-GB buffers blocks for tens of ms: the multi-GPU build collects them ...
-    std::vector<void *> plain_deferred; // ... here and releases them after its last phase (aix_plain_release)
+    std::unordered_map<void *, size_t> plain_allocs;        // cudaMalloc'ed buffers in use (multi-GPU exchange buffers) and their sizes
+    std::vector<std::pair<void *, size_t>> plain_cache;     // ... and the freed ones, kept for the next build (aix_plain_alloc)
     void *small_host = nullptr;         // pinned + device-mapped staging of the small-batch path (batch_pipeline.cuh)
     // single-query mailbox (tf_query.cu): a one-thread resident kernel that polls a request slot in mapped host memory,
     // so that get_tf_value() costs two PCIe traversals instead of a kernel launch + a stream synchronisation
@@ -159,37 +159,68 @@ struct aix_ctx {
     }
 };
 
+// Buffers another GPU copies into / out of (multi-GPU exchange) are plain cudaMalloc memory, peer-accessible through
+// cudaDeviceEnablePeerAccess.  cudaMalloc / cudaFree of tens of GB block for tens of ms each, so freed buffers are kept in a
+// per-ctx cache (as the pool keeps its blocks) and handed out again when the size fits; aix_ctx_trim returns them to the
+// driver, and so does any allocation that fails while the cache holds memory.
+static inline void aix_plain_cache_flush(aix_ctx *ctx) {
+    for (auto &b : ctx->plain_cache) cudaFree(b.first);
+    ctx->plain_cache.clear();
+}
 static inline cudaError_t aix_pool_alloc(aix_ctx *ctx, void **p, size_t bytes, cudaStream_t st) {
-    if (!ctx->pool) return cudaMalloc(p, bytes ? bytes : 1);
-    return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, st);
+    cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, st) : cudaMalloc(p, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation && !ctx->plain_cache.empty()) {
+        cudaGetLastError();
+        cudaStreamSynchronize(st);
+        aix_plain_cache_flush(ctx);
+        e = ctx->pool ? cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, st) : cudaMalloc(p, bytes ? bytes : 1);
+    }
+    return e;
 }
 template <typename T>
 static inline cudaError_t aix_pool_alloc(aix_ctx *ctx, T **p, size_t bytes, cudaStream_t st) {
     return aix_pool_alloc(ctx, (void **)p, bytes, st);
 }
-// buffers another GPU copies into / out of (multi-GPU exchange): plain cudaMalloc memory, peer-accessible through
-// cudaDeviceEnablePeerAccess; remembered so that aix_pool_free releases them the right way
 template <typename T>
 static inline cudaError_t aix_plain_alloc(aix_ctx *ctx, T **p, size_t bytes) {
-    cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 1);
-    if (e == cudaSuccess) ctx->plain_allocs.insert((void *)*p);
+    if (!bytes) bytes = 1;
+    // best fit among the cached blocks that are large enough and at most 25 % too large
+    int best = -1;
+    for (int i = 0; i < (int)ctx->plain_cache.size(); ++i) {
+        const size_t have = ctx->plain_cache[i].second;
+        if (have >= bytes && have <= bytes + bytes / 4 && (best < 0 || have < ctx->plain_cache[best].second)) best = i;
+    }
+    if (best >= 0) {
+        *p = (T *)ctx->plain_cache[best].first;
+        ctx->plain_allocs[(void *)*p] = ctx->plain_cache[best].second;
+        ctx->plain_cache.erase(ctx->plain_cache.begin() + best);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->plain_cache.empty()) {
+        cudaGetLastError();
+        aix_plain_cache_flush(ctx);
+        e = cudaMalloc((void **)p, bytes);
+    }
+    if (e == cudaSuccess) ctx->plain_allocs[(void *)*p] = bytes;
     return e;
 }
+// frees a builder temporary: pool memory goes back to the pool (stream-ordered), a plain buffer into the cache -- after the
+// stream has drained, since the next user may be another stream or another GPU
 static inline void aix_pool_free(aix_ctx *ctx, void *p, cudaStream_t st) {
     if (!p) return;
-    if (ctx && ctx->plain_allocs.erase(p)) {
-        if (ctx->defer_plain_free) ctx->plain_deferred.push_back(p);
-        else cudaFree(p);
-        return;
+    if (ctx) {
+        auto it = ctx->plain_allocs.find(p);
+        if (it != ctx->plain_allocs.end()) {
+            const size_t bytes = it->second;
+            ctx->plain_allocs.erase(it);
+            cudaStreamSynchronize(st);
+            ctx->plain_cache.emplace_back(p, bytes);
+            return;
+        }
     }
     if (ctx && ctx->pool) cudaFreeAsync(p, st);
     else cudaFree(p);
-}
-
-static inline void aix_plain_release(aix_ctx *ctx) {
-    for (void *p : ctx->plain_deferred) cudaFree(p);
-    ctx->plain_deferred.clear();
-    ctx->defer_plain_free = false;
 }
 
 struct aix_multi {  // multi.cu: one ctx (and one host thread at a time) per GPU of one box, one process

@@ -73,6 +73,7 @@ void aix_ctx_destroy(aix_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto &b : ctx->scratch)
         if (b.p) cudaFree(b.p);
+    aix_plain_cache_flush(ctx);
     aix_count13_peers_close(ctx);
     if (ctx->small_host) cudaFreeHost(ctx->small_host);
     if (ctx->c13_hist32) cudaFree(ctx->c13_hist32);
@@ -108,6 +109,7 @@ int aix_ctx_trim(aix_ctx *ctx) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     AIX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->pool) AIX_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+    aix_plain_cache_flush(ctx);
     return AIX_OK;
 }
 

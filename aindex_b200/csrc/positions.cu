@@ -812,7 +812,6 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         };
         cudaError_t e = cudaSetDevice(ctx->device);
         if (e != cudaSuccess) fail_cuda(e);
-        ctx->defer_plain_free = true;  // the sorted-key buffer is released after the last phase (cudaFree blocks for tens of ms)
         const uint64_t lo = c[r], hi = c[r + 1];
         const uint64_t img_len = hi > lo ? (hi - lo) + K - 1 : 0;   // bytes [lo, hi + K - 1) <= len
         double t0 = AixTrace::now();
@@ -929,14 +928,8 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
             if (rcs[r] == AIX_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail_cuda(e);
         }
         t_exch[r] = ms_since(t0);
-        {   // the sent keys go back to the driver now (the sort needs the room on a full GPU): a blocking cudaFree
-            const double tf0 = AixTrace::now();
-            ctx->defer_plain_free = false;
-            aix_pool_free(ctx, me.part, st);
-            ctx->defer_plain_free = true;
-            me.part = nullptr;
-            t_alloc[r] += ms_since(tf0);
-        }
+        aix_pool_free(ctx, me.part, st);
+        me.part = nullptr;
         bar.wait();
         // ---- phase 5: sort the received keys on the bucket bits, turn them into this GPU's slice of positions[]
         phase = "sort + finalize";
@@ -969,7 +962,6 @@ extern "C" int aix_positions_build23_multi(aix_multi *mg, const aix_index23 *con
         aix_pool_free(ctx, me.recv, st); aix_pool_free(ctx, me.alt, st);
         aix_pool_free(ctx, me.positions, st); aix_pool_free(ctx, me.indices, st);
         cudaStreamSynchronize(st);
-        aix_plain_release(ctx);
         bar.wait();
     };
     {
