@@ -61,15 +61,23 @@ struct Index23Dev {
     uint32_t bloom_words;
 };
 
-// word and bit masks of a canonical 23-mer code in the front filter (same function builds and tests)
-__device__ __forceinline__ void bloom_slot(uint64_t c, uint32_t n_words, uint32_t &word, uint32_t &mlo, uint32_t &mhi) {
+// word and bit masks of a canonical 23-mer code in the front filter (same functions build and test); split in two so that
+// a kernel can issue the load of the word before it needs the masks
+__device__ __forceinline__ void bloom_word(uint64_t c, uint32_t n_words, uint32_t &word, uint32_t &g) {
     uint32_t h = (uint32_t)c * 0x9E3779B1u + (uint32_t)(c >> 32) * 0x85EBCA77u;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    uint32_t g = h * 0x297A2D39u;
+    g = h * 0x297A2D39u;
     g ^= g >> 15;
     word = __umulhi(h, n_words);
+}
+__device__ __forceinline__ void bloom_masks(uint32_t g, uint32_t &mlo, uint32_t &mhi) {
     mlo = (1u << (g & 31u)) | (1u << ((g >> 5) & 31u));
     mhi = (1u << ((g >> 10) & 31u)) | (1u << ((g >> 15) & 31u));
+}
+__device__ __forceinline__ void bloom_slot(uint64_t c, uint32_t n_words, uint32_t &word, uint32_t &mlo, uint32_t &mhi) {
+    uint32_t g;
+    bloom_word(c, n_words, word, g);
+    bloom_masks(g, mlo, mhi);
 }
 
 __device__ __host__ __forceinline__ uint32_t fingerprint8(uint64_t kmer) {

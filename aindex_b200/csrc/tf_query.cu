@@ -251,56 +251,74 @@ __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_filter_kernel(
         }
         __syncwarp();
     };
+    // Software pipeline, one tile deep: iteration `it` encodes tile `it` and PREFETCHES its filter word into L1, then finishes
+    // tile `it - 1`, whose word was prefetched an iteration ago -- the word's latency (L2, or HBM for the half of the filter
+    // that is not resident) is covered by a tile's worth of encode instead of stalling the warp at the test (ncu of the
+    // unpipelined loop: 40 % of all stall samples sat on the first use of the word).  A prefetch rather than an early load:
+    // a loaded value carried over the loop edge is copied into the "previous" registers at the top of the next
+    // iteration, and that copy waits for the load.
     uint32_t slot = 0, phase = 0;
-    for (uint32_t it = 0; it < my_tiles; ++it) {
-        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
-            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                         ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
-        }
-        src += kStride;
-        {
-            uint32_t done;
-            do {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
-            } while (!done);
-        }
-        const uint32_t base = lane * 23u;
-        const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
-        uint32_t x0, x1, x2, x3, x4, x5, x6;
-        asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
-                     "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
-                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
-        __syncwarp();
-        const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
-                       y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
-        const uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
-                       r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
-        bool all_acgt;
-        const uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
-        uint32_t word, mlo, mhi;
-        bloom_slot(u <= r ? u : r, ix.bloom_words, word, mlo, mhi);
-        const uint2 w = ld_evict_last_u32x2(ix.bloom + word);
-        const bool pass = !all_acgt || ((w.x & mlo) == mlo && (w.y & mhi) == mhi);
-        if (!pass) __stcs(out + i0 + (uint64_t)it * (kStWarps * 32u) + lane, 0u);
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
-        if (b) {
-            if (pass) wq[qn + __popc(b & lt)] = (uint16_t)(it * 32u + lane);
-            qn += __popc(b);
-            n_passed += __popc(b);
+    uint32_t word_prev = 0, g_prev = 0;
+    bool acgt_prev = true;
+    for (uint32_t it = 0; it <= my_tiles; ++it) {
+        uint32_t word = 0, g = 0;
+        bool all_acgt = true;
+        if (it < my_tiles) {
+            if (lane == 0 && it + (kStStages - 1) < my_tiles) {
+                const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
+            }
+            src += kStride;
+            {
+                uint32_t done;
+                do {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
+                } while (!done);
+            }
+            const uint32_t base = lane * 23u;
+            const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
+            uint32_t x0, x1, x2, x3, x4, x5, x6;
+            asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
+                         "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
+                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
             __syncwarp();
-            if (qn >= 32u) {
-                drain(32u);
-                const uint16_t v = wq[32u + lane];
+            const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
+                           y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
+            const uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
+                           r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
+            const uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
+            bloom_word(u <= r ? u : r, ix.bloom_words, word, g);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.bloom + word));
+            if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+        }
+        if (it > 0) {  // finish tile it - 1
+            const uint2 w_prev = ld_evict_last_u32x2(ix.bloom + word_prev);
+            uint32_t mlo, mhi;
+            bloom_masks(g_prev, mlo, mhi);
+            const bool pass = !acgt_prev || ((w_prev.x & mlo) == mlo && (w_prev.y & mhi) == mhi);
+            if (!pass) __stcs(out + i0 + (uint64_t)(it - 1u) * (kStWarps * 32u) + lane, 0u);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+            if (b) {
+                if (pass) wq[qn + __popc(b & lt)] = (uint16_t)((it - 1u) * 32u + lane);
+                qn += __popc(b);
+                n_passed += __popc(b);
                 __syncwarp();
-                wq[lane] = v;
-                qn -= 32u;
-                __syncwarp();
+                if (qn >= 32u) {
+                    drain(32u);
+                    const uint16_t v = wq[32u + lane];
+                    __syncwarp();
+                    wq[lane] = v;
+                    qn -= 32u;
+                    __syncwarp();
+                }
             }
         }
-        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+        word_prev = word;
+        g_prev = g;
+        acgt_prev = all_acgt;
     }
     if (qn) drain(qn);
     if ((blockIdx.x & 15u) == 0u && lane == 0) {
@@ -800,12 +818,12 @@ static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_
         const uint64_t n_tiles = q / 32;
         if (kMode == AIX_Q_TF && q >= 4096 && filter_wanted(ix)) {
             const uint64_t grid = (n_tiles + kStTilesPerCta - 1) / kStTilesPerCta;
-            // register budget of the filter kernel: 4 resident CTAs (64 registers) measured best -- 86.5 G q/s against
-            // 79.6 (68 registers, what ptxas picks) and 83.8 (5 CTAs); AIX_FILTER_MINBLOCKS for A/B runs
+            // register budget of the filter kernel: what ptxas picks (64 registers, 4 resident CTAs) measured best with the
+            // prefetch pipeline -- 89.0 G q/s against 84.7 with a cap of 56 or 48 registers; AIX_FILTER_MINBLOCKS for A/B runs
             static int fmin = -1;
             if (fmin < 0) {
                 const char *e = getenv("AIX_FILTER_MINBLOCKS");
-                fmin = e ? atoi(e) : 4;
+                fmin = e ? atoi(e) : 1;
             }
             // (pinning the filter in the persisting part of L2 with an access-policy window bought 2 %, 86.4 -> 88.3 G q/s:
             // the kernel is bound by the ALU pipe, 216 instructions per query, not by the filter's L2 misses -- not worth
