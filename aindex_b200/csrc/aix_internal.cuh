@@ -111,6 +111,10 @@ struct aix_ctx {
     const void *mbox_owner = nullptr;   // the index the running kernel serves
     bool mbox_launched = false, mbox_broken = false;
     uint32_t mbox_seq = 0;
+    // front filter of a 23-mer index held in persisting L2 lines (tf_query.cu: l2_window_on): the set-aside configured on
+    // this device, and whether persisting lines may still be resident (aix_l2_unpin hands the set-aside back)
+    mutable size_t l2_set_aside = 0;
+    mutable bool l2_pinned = false;
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
     uint64_t *c13_hist64 = nullptr;     // u64[4^13]
@@ -125,6 +129,15 @@ struct aix_ctx {
     uint64_t *c23_kmers_dev = nullptr;
     uint32_t *c23_counts_dev = nullptr;
     uint64_t c23_n = 0;
+
+    // persisting L2 lines of a front filter back to normal lines: called where another kernel family starts (counting,
+    // builds, coverage, 13-mer queries), whose working sets want the whole L2
+    void l2_unpin() const {
+        if (l2_pinned) {
+            cudaCtxResetPersistingL2Cache();
+            l2_pinned = false;
+        }
+    }
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];

@@ -828,6 +828,7 @@ int aix_count13_begin(aix_ctx *ctx) {
     if (!ctx) return AIX_ERR_ARG;
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
     AIX_TRY(c13_alloc(ctx));
+    ctx->l2_unpin();
     AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist32, 0, AIX_TOTAL_13MERS * 4, ctx->stream));
     AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_hist64, 0, AIX_TOTAL_13MERS * 8, ctx->stream));
     AIX_CUDA(ctx, cudaMemsetAsync(ctx->c13_stats_dev, 0, kStatWords * 8, ctx->stream));

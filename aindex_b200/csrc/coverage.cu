@@ -136,6 +136,7 @@ static int coverage_on(aix_ctx *ctx, cudaStream_t st, int slot, const aix_index2
     if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
     if (n_seq == 0 || total_out == 0) return AIX_OK;
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->l2_unpin();
     if (n_seq >= (1ull << 32)) return ctx->fail(AIX_ERR_ARG, "coverage: at most 2^32-1 sequences per call");
     const uint64_t n_ctas = (total_out + kCovBlock - 1) / kCovBlock;
     void *oo;

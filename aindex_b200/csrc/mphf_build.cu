@@ -324,6 +324,7 @@ static int build_impl(aix_ctx *ctx, const uint64_t *kmers_dev, uint64_t n, int k
     *out = nullptr;
     if (k != 13 && k != 23) return ctx->fail(AIX_ERR_ARG, "k must be 13 or 23");
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->l2_unpin();
     // mphf.hpp:27: hash_domain = (ceil(n * gamma) + 2) / 3
     const uint64_t hash_domain = ((uint64_t)std::ceil((double)n * 1.23) + 2) / 3;
     const uint64_t n_nodes = 3 * hash_domain;
@@ -666,6 +667,7 @@ static int c23_multi_pass(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, 
 int aix_canonical23_count_dev(aix_ctx *ctx, const uint8_t *reads_dev, uint64_t len, uint64_t *n_out) {
     if (!ctx || !n_out) return AIX_ERR_ARG;
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->l2_unpin();
     if (ctx->c23_kmers_dev) { cudaFree(ctx->c23_kmers_dev); ctx->c23_kmers_dev = nullptr; }
     if (ctx->c23_counts_dev) { cudaFree(ctx->c23_counts_dev); ctx->c23_counts_dev = nullptr; }
     ctx->c23_n = 0;

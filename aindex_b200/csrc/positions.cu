@@ -45,7 +45,8 @@ __device__ __forceinline__ uint64_t bucket23(const Index23Dev &ix, const MphfDev
     uint64_t r0, r1, r2;
     load_window23(p, r0, r1, r2);
     bool all_acgt;
-    uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
+    uint64_t u, r;
+    encode_validate23_rc(r0, r1, r2, all_acgt, u, r);
     if (all_acgt) {
         Hit h = lookup_packed23<true>(ix, m, u, r, true, r0, r1, r2);  // one probe of min(u, r)
         return h.strand ? h.h : kNoBucket;
@@ -421,6 +422,7 @@ static int build_core(aix_ctx *ctx, Index23Dev id, MphfDev md, F tf, uint64_t n,
                       uint64_t start, unsigned long long **indices_dev, unsigned long long **positions_dev,
                       uint64_t *total_out) {
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->l2_unpin();
     cudaStream_t st = ctx->stream;
     unsigned long long *indices = nullptr, *positions = nullptr, *tiles = nullptr;
     cudaError_t e = aix_pool_alloc(ctx, &indices, (n + 1) * 8, st);

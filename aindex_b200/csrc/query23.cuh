@@ -9,26 +9,45 @@
 
 namespace aix {
 
-// 2-bit value of a 23-byte string (words zero padded past byte 22) AND whether every byte is an
-// upper-case ACGT letter: the letter code of each byte selects the one byte value that is valid
-// for it ("ACGT"[code], by PRMT) and the word is compared with that expectation.
+// 2-bit value of a 23-byte string (words zero padded past byte 22), the value of its reverse complement, AND whether
+// every byte is an upper-case ACGT letter.  Per 4-byte word (7 instructions, one of them on the FMA pipe):
+//   x   = (w ^ w >> 1) & 0x06060606       letter code of each byte in its bits 2:1 (A 0, C 1, G 2, T 3)
+//   x * (2^5 + 2^11 + 2^17 + 2^23)        top byte = c3 c2 c1 c0, the four codes in REVERSE order: the six top bytes,
+//                                         little-endian, are the reversed code string, whose complement is the
+//                                         reverse complement r; the forward value is revcomp23(r) (two BREVs)
+//   PRMT("A.C.", "G.T.", nibbles 2c)      the one byte value that is valid for each code, compared with the word
+// (prmt.b32 by inline PTX: __byte_perm masks the selector with 0x7777 first, one more ALU instruction per word)
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 __device__ __forceinline__ uint32_t expect_acgt4(uint32_t c4) {  // c4: letter code in bits 1:0 of each byte
     const uint32_t t = c4 | (c4 >> 4);
     return __byte_perm(0x54474341u, 0u, __byte_perm(t, 0u, 0x4420));
 }
-__device__ __forceinline__ uint64_t encode_validate23(uint64_t r0, uint64_t r1, uint64_t r2, bool &all_acgt) {
+__device__ __forceinline__ void encode_validate23_rc(uint64_t r0, uint64_t r1, uint64_t r2, bool &all_acgt, uint64_t &u, uint64_t &r) {
     const uint32_t w[6] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32), (uint32_t)r2, (uint32_t)(r2 >> 32)};
     uint32_t p[6], bad = 0;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        const uint32_t c4 = ((w[j] >> 1) ^ (w[j] >> 2)) & 0x03030303u;
-        p[j] = (c4 * 0x40100401u) >> 24;  // c0<<6 | c1<<4 | c2<<2 | c3
-        const uint32_t diff = expect_acgt4(c4) ^ w[j];
+        const uint32_t x = (w[j] ^ (w[j] >> 1)) & 0x06060606u;
+        p[j] = x * 0x00820820u;
+        const uint32_t sel = prmt_b32(x + (x >> 4), 0u, 0x4420u);            // nibble i = 2 * code of byte i
+        const uint32_t diff = prmt_b32(0x00430041u, 0x00540047u, sel) ^ w[j];
         bad |= j == 5 ? (diff & 0x00FFFFFFu) : diff;  // byte 23 is padding
     }
     all_acgt = bad == 0;
-    const uint64_t all48 = ((uint64_t)((p[0] << 8) | p[1]) << 32) | ((uint64_t)((p[2] << 8) | p[3]) << 16) | ((p[4] << 8) | p[5]);
-    return all48 >> 2;  // 23 codes; the 24th byte is padding
+    const uint32_t p01 = prmt_b32(p[0], p[1], 0x0073u), p23 = prmt_b32(p[2], p[3], 0x0073u), p45 = prmt_b32(p[4], p[5], 0x0073u);
+    const uint32_t lo = prmt_b32(p01, p23, 0x5410u);
+    const uint64_t y = ((uint64_t)(p45 & 0x3FFFu) << 32) | lo;  // reversed code string; the 24th byte is padding
+    r = y ^ 0x3FFFFFFFFFFFULL;
+    u = reverse_pairs64(y) >> 18;  // == revcomp23(r): the complements cancel
+}
+__device__ __forceinline__ uint64_t encode_validate23(uint64_t r0, uint64_t r1, uint64_t r2, bool &all_acgt) {
+    uint64_t u, r;
+    encode_validate23_rc(r0, r1, r2, all_acgt, u, r);
+    return u;
 }
 
 // strict encoder of get_dna23_bitset (kmers.cpp:12-25): non-ACGT (and missing) bytes -> 0
@@ -109,8 +128,8 @@ __device__ __forceinline__ void query23(const Index23Dev &ix, const MphfDev &m, 
                                         uint32_t len, const uint8_t *p, uint64_t i, void *out) {
     // fast encode + validate (a valid query's ASCII words are the raw words themselves)
     bool all_acgt;
-    uint64_t u = encode_validate23(r0, r1, r2, all_acgt);
-    uint64_t r = revcomp23(u);
+    uint64_t u, r;
+    encode_validate23_rc(r0, r1, r2, all_acgt, u, r);
     const uint64_t e0 = r0, e1 = r1, e2 = r2;
     const bool valid = (len == 23u) && all_acgt;
 
@@ -200,8 +219,8 @@ template <bool kCanon>
 __device__ __forceinline__ Hit find23_window(const Index23Dev &ix, const MphfDev &m, uint64_t r0, uint64_t r1,
                                              uint64_t r2) {
     bool all_acgt;
-    uint64_t u = encode_validate23(r0, r1, r2, all_acgt);
-    uint64_t r = revcomp23(u);
+    uint64_t u, r;
+    encode_validate23_rc(r0, r1, r2, all_acgt, u, r);
     if (all_acgt) return lookup_packed23<kCanon>(ix, m, u, r, true, r0, r1, r2);
     // window with a non-ACGT byte: raw bytes forward, decoded reverse complement backward
     Hit hit = {0, 0, 0};

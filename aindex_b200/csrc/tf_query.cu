@@ -20,6 +20,8 @@
 #include "aix_internal.cuh"
 #include "batch_pipeline.cuh"
 #include "query23.cuh"
+#include "tf23_ring.cuh"
+#include "tf23_filter.cuh"
 
 namespace aix {
 
@@ -62,50 +64,6 @@ __global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, Mphf
     query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
 }
 
-
-// ---- K3 streaming form: persistent CTAs, one TMA ring per warp ------------------------------------
-// The fixed kernel above pays three dependent round trips per query (query bytes from HBM, MPHF
-// records, fingerprint / index record) and a CTA barrier between the first two.  Here every warp
-// owns a 3-slot ring of 32-query tiles (736 B) in shared memory that lane 0 fills with
-// cp.async.bulk (TMA, UBLKCP in SASS) two tiles ahead, completion signalled on one mbarrier per
-// slot: the query bytes are already on chip when a warp starts a tile and there is no CTA-wide
-// barrier.
-constexpr int kStWarps = 8;
-#ifndef AIX_ST_STAGES
-#define AIX_ST_STAGES 3
-#endif
-#ifndef AIX_ST_TILES
-#define AIX_ST_TILES 16
-#endif
-constexpr int kStStages = AIX_ST_STAGES;  // ring depth and tiles per warp are compile-time knobs (profiles/r01_tf23_sweep.txt)
-constexpr uint32_t kStTileBytes = 32u * 23u;  // 736 = 46 * 16: legal bulk-copy size, slots stay 16-byte aligned
-constexpr int kStSlot = 768;                  // the seventh word of lane 31 ends at byte 740
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
-}
-
-// tiles per warp and CTA: a CTA owns kStWarps * kStTilesPerWarp consecutive tiles (4096 queries), warp w takes
-// tiles w, w + 8, ...  Small enough that the hardware scheduler evens out SM speed differences (one wave of
-// resident CTAs per launch left a quarter of the warp slots idle at the tail), long enough that the two
-// exposed loads of the ring prologue are amortised.
-constexpr int kStTilesPerWarp = AIX_ST_TILES;
-constexpr int kStTilesPerCta = kStWarps * kStTilesPerWarp;
 
 template <int kMode, bool kCanon, int kMinBlocks>
 __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
@@ -170,160 +128,6 @@ __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(
         query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
         i += (uint64_t)kStWarps * 32u;
         if (++slot == kStStages) { slot = 0; phase ^= 1u; }
-    }
-}
-
-// ---- front filter (Index23Dev::bloom) ---------------------------------------------------------------------------
-// every stored (canonical) k-mer sets its four bits
-__global__ void __launch_bounds__(256) bloom_build_kernel(const uint4 *__restrict__ recs, uint64_t n, unsigned long long *__restrict__ bloom,
-                                                        uint32_t n_words) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4 r = recs[i];
-    uint32_t word, mlo, mhi;
-    bloom_slot(((uint64_t)r.y << 32) | r.x, n_words, word, mlo, mhi);
-    atomicOr(bloom + word, ((unsigned long long)mhi << 32) | mlo);
-}
-
-// get_tf_values on a canonical-only index for batches in which most queries are absent: the ring of tf23_stream_kernel,
-// but a query is first tested against the front filter.  Rejected queries are answered 0 on the spot; the others (stored
-// k-mers, ~3 % false positives, strings with a non-ACGT byte) are queued per warp -- a 16-bit slot number in shared
-// memory -- and go through query23 in batches of 32, all lanes busy, with the tail of the queue drained when the
-// warp has seen its last tile.  Same answers as tf23_stream_kernel<AIX_Q_TF, true> (tests/test_gpu_parity.py).
-// qstats: {queries seen, queries that passed the filter}, reported by one CTA in 16 (a rate is all the host needs).
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_filter_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
-                                                                              uint64_t n_tiles, uint32_t *__restrict__ out,
-                                                                              unsigned long long *__restrict__ qstats) {
-    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kStSlot];
-    __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
-    __shared__ uint16_t queue[kStWarps][64];
-    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;  // this warp's first tile
-    if (tile0 >= n_tiles) return;
-    const uint64_t left = n_tiles - tile0;
-    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
-    const uint64_t policy = l2_policy_evict_first();
-    constexpr uint32_t kStride = kStWarps * kStTileBytes;
-    const uint8_t *src = recs + tile0 * kStTileBytes;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages - 1; ++s) {
-            if ((uint32_t)s < my_tiles) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(kStTileBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                             ::"r"(ring0 + (uint32_t)kStSlot * s), "l"(src + (uint64_t)kStride * s), "r"(kStTileBytes), "r"(bar0 + 8u * s), "l"(policy) : "memory");
-            }
-        }
-    }
-    src += (uint64_t)kStride * (kStStages - 1);
-    const uint64_t i0 = tile0 * 32u;  // first query of this warp; slot s of the warp = query i0 + (s >> 5) * 256 + (s & 31)
-    const uint64_t last_query = n_tiles * 32u - 1;
-    uint16_t *wq = queue[wid];
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t qn = 0, n_passed = 0;
-    // queued slots [0, cnt) through the full lookup, one per lane
-    auto drain = [&](uint32_t cnt) {
-        if (lane < cnt) {
-            const uint32_t s = wq[lane];
-            const uint64_t i = i0 + (uint64_t)(s >> 5) * (kStWarps * 32u) + (s & 31u);
-            const uint8_t *p = recs + i * 23;
-            uint64_t r0, r1, r2;
-            if (i != last_query) load_window23(p, r0, r1, r2);
-            else {  // the last query of the batch: never read past the buffer
-                r0 = r1 = r2 = 0;
-#pragma unroll 1
-                for (int j = 0; j < 23; ++j) {
-                    const uint64_t b = p[j];
-                    if (j < 8) r0 |= b << (8 * j);
-                    else if (j < 16) r1 |= b << (8 * (j - 8));
-                    else r2 |= b << (8 * (j - 16));
-                }
-            }
-            query23<AIX_Q_TF, true>(ix, m, r0, r1, r2, 23u, p, i, out);
-        }
-        __syncwarp();
-    };
-    // Software pipeline, one tile deep: iteration `it` encodes tile `it` and PREFETCHES its filter word into L1, then finishes
-    // tile `it - 1`, whose word was prefetched an iteration ago -- the word's latency (L2, or HBM for the half of the filter
-    // that is not resident) is covered by a tile's worth of encode instead of stalling the warp at the test (ncu of the
-    // unpipelined loop: 40 % of all stall samples sat on the first use of the word).  A prefetch rather than an early load:
-    // a loaded value carried over the loop edge is copied into the "previous" registers at the top of the next
-    // iteration, and that copy waits for the load.
-    uint32_t slot = 0, phase = 0;
-    uint32_t word_prev = 0, g_prev = 0;
-    bool acgt_prev = true;
-    for (uint32_t it = 0; it <= my_tiles; ++it) {
-        uint32_t word = 0, g = 0;
-        bool all_acgt = true;
-        if (it < my_tiles) {
-            if (lane == 0 && it + (kStStages - 1) < my_tiles) {
-                const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                             ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
-            }
-            src += kStride;
-            {
-                uint32_t done;
-                do {
-                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                                 : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
-                } while (!done);
-            }
-            const uint32_t base = lane * 23u;
-            const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
-            uint32_t x0, x1, x2, x3, x4, x5, x6;
-            asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
-                         "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
-                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
-            __syncwarp();
-            const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
-                           y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
-            const uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
-                           r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
-            const uint64_t u = encode_validate23(r0, r1, r2, all_acgt), r = revcomp23(u);
-            bloom_word(u <= r ? u : r, ix.bloom_words, word, g);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.bloom + word));
-            if (++slot == kStStages) { slot = 0; phase ^= 1u; }
-        }
-        if (it > 0) {  // finish tile it - 1
-            const uint2 w_prev = ld_evict_last_u32x2(ix.bloom + word_prev);
-            uint32_t mlo, mhi;
-            bloom_masks(g_prev, mlo, mhi);
-            const bool pass = !acgt_prev || ((w_prev.x & mlo) == mlo && (w_prev.y & mhi) == mhi);
-            if (!pass) __stcs(out + i0 + (uint64_t)(it - 1u) * (kStWarps * 32u) + lane, 0u);
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
-            if (b) {
-                if (pass) wq[qn + __popc(b & lt)] = (uint16_t)((it - 1u) * 32u + lane);
-                qn += __popc(b);
-                n_passed += __popc(b);
-                __syncwarp();
-                if (qn >= 32u) {
-                    drain(32u);
-                    const uint16_t v = wq[32u + lane];
-                    __syncwarp();
-                    wq[lane] = v;
-                    qn -= 32u;
-                    __syncwarp();
-                }
-            }
-        }
-        word_prev = word;
-        g_prev = g;
-        acgt_prev = all_acgt;
-    }
-    if (qn) drain(qn);
-    if ((blockIdx.x & 15u) == 0u && lane == 0) {
-        atomicAdd(qstats, (unsigned long long)my_tiles * 32ull);
-        atomicAdd(qstats + 1, (unsigned long long)n_passed);
     }
 }
 
@@ -427,7 +231,8 @@ __global__ void __launch_bounds__(kQBlock) tf23_probes_kernel(MphfDev m, uint64_
     const uint32_t nb = len < 23u ? len : 23u;
     for (uint32_t j = 0; j < nb; ++j) w[j >> 3] |= (uint64_t)__ldg(p + j) << (8 * (j & 7));
     bool all_acgt;
-    const uint64_t u = encode_validate23(w[0], w[1], w[2], all_acgt), r = revcomp23(u);
+    uint64_t u, r;
+    encode_validate23_rc(w[0], w[1], w[2], all_acgt, u, r);
     uint64_t h1 = kNoProbe, k1 = 0, h2 = kNoProbe, k2 = 0, a, b, c, f0, f1, f2;
     if (len == 23u && all_acgt) {
         if (kCanon) {
@@ -808,6 +613,46 @@ static bool filter_wanted(const aix_index23 *ix) {
     return false;
 }
 
+// Access-policy window over the front filter for the launches that follow on `st`: its lines are kept in the persisting
+// part of L2 (set aside once per device, as much as the filter needs and the device allows); everything else the kernel
+// touches streams past them.  Returns false when the device cannot do it.
+static bool l2_window_on(const aix_ctx *ctx, cudaStream_t st, const void *base, size_t bytes) {
+    static int max_persist = -1, max_window = 0;
+    if (max_persist < 0) {
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    }
+    if (max_persist <= 0 || max_window <= 0 || bytes == 0) return false;
+    size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    const char *esa = getenv("AIX_FILTER_SETASIDE_MB"), *ehr = getenv("AIX_FILTER_HITRATIO");  // A/B knobs
+    if (esa && atol(esa) > 0) want = (size_t)atol(esa) << 20 < (size_t)max_persist ? (size_t)atol(esa) << 20 : (size_t)max_persist;
+    if (ctx->l2_set_aside < want) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        ctx->l2_set_aside = want;
+    }
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    v.accessPolicyWindow.hitRatio = ehr ? (float)atof(ehr) : (bytes <= ctx->l2_set_aside ? 1.0f : (float)((double)ctx->l2_set_aside / (double)bytes));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    ctx->l2_pinned = true;
+    return true;
+}
+static void l2_window_off(cudaStream_t st) {
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 template <int kMode>
 static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_t st, const uint8_t *recs, uint32_t stride,
                           const uint8_t *lens, uint64_t q, void *out) {
@@ -816,24 +661,37 @@ static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_
     const bool fixed = (stride == 23 && lens == nullptr && ((uintptr_t)recs & 15) == 0);
     if (fixed && tf23_kernel_choice() == 1 && q >= 32) {
         const uint64_t n_tiles = q / 32;
+        uint64_t done = n_tiles * 32;  // queries answered by the streaming kernel
         if (kMode == AIX_Q_TF && q >= 4096 && filter_wanted(ix)) {
-            const uint64_t grid = (n_tiles + kStTilesPerCta - 1) / kStTilesPerCta;
-            // register budget of the filter kernel: what ptxas picks (64 registers, 4 resident CTAs) measured best with the
-            // prefetch pipeline -- 89.0 G q/s against 84.7 with a cap of 56 or 48 registers; AIX_FILTER_MINBLOCKS for A/B runs
-            static int fmin = -1;
-            if (fmin < 0) {
-                const char *e = getenv("AIX_FILTER_MINBLOCKS");
-                fmin = e ? atoi(e) : 1;
-            }
-            // (pinning the filter in the persisting part of L2 with an access-policy window bought 2 %, 86.4 -> 88.3 G q/s:
-            // the kernel is bound by the ALU pipe, 216 instructions per query, not by the filter's L2 misses -- not worth
-            // a device-wide L2 carve-out that the counting kernels would pay for; profiles/r02_filter_sweep.txt)
+            // Which filter kernel (tf23_filter.cuh; profiles/r02_filter_sweep.txt has every number):
+            //   3 (default)  filter word LOADED a tile ahead, loop unrolled by two, ptxas held to 64 registers / 4 resident CTAs:
+            //                99.1 G q/s, and 102.7 with the filter's lines held in persisting L2 by an access-policy window
+            //                (AIX_FILTER_PERSIST=0 switches the window off; a larger set-aside or a hit ratio < 1 are slower)
+            //   1            word prefetched into L1 a tile ahead: 91.4 (39 % of the stall samples on the word's first use)
+            //   2            two queries per lane and iteration (needs an 8-byte aligned `out`): 17 % fewer instructions,
+            //                72 registers or 60 with ptxas held to 4 CTAs, 83.8 / 87.5 -- the kernel lives on resident warps
+            // AIX_FILTER_MINBLOCKS=1 lifts the register cap of 2 and 3.  Read per launch (the parity test switches kernels
+            // inside one process).
+            const char *ek = getenv("AIX_FILTER_KERNEL"), *em = getenv("AIX_FILTER_MINBLOCKS"), *ep = getenv("AIX_FILTER_PERSIST");
+            const int fker = ek ? atoi(ek) : 3, fmin = em ? atoi(em) : 4;
             uint32_t *out32 = (uint32_t *)out;
             unsigned long long *qs = ix->qstats_dev;
-            const unsigned g = (unsigned)grid;
-            if (fmin >= 5) tf23_filter_kernel<5><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
-            else if (fmin == 4) tf23_filter_kernel<4><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
-            else tf23_filter_kernel<1><<<g, kStWarps * 32, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            const unsigned g = (unsigned)((n_tiles + kStTilesPerCta - 1) / kStTilesPerCta), threads = kStWarps * 32;
+            if (fker == 3) {
+                if (fmin >= 4 && !(ep && atoi(ep) == 0) && l2_window_on(ctx, st, ix->bloom_dev, (size_t)ix->bloom_words * 8)) {
+                    tf23_filter3_kernel<4, kStTilesPerWarp, true><<<g, threads, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+                    l2_window_off(st);
+                } else if (fmin >= 4) tf23_filter3_kernel<4, kStTilesPerWarp><<<g, threads, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+                else tf23_filter3_kernel<1, kStTilesPerWarp><<<g, threads, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            } else if (fker == 2 && ((uintptr_t)out & 7) == 0) {
+                const uint64_t n64 = q / 64;  // tiles of 64 queries, half as many per warp
+                const unsigned g2 = (unsigned)((n64 + kStTilesPerCta / 2 - 1) / (kStTilesPerCta / 2));
+                if (fmin >= 4) tf23_filter2_kernel<4, kStTilesPerWarp / 2><<<g2, threads, 0, st>>>(id, md, recs, n64, out32, qs);
+                else tf23_filter2_kernel<1, kStTilesPerWarp / 2><<<g2, threads, 0, st>>>(id, md, recs, n64, out32, qs);
+                done = n64 * 64;
+            } else {
+                tf23_filter_kernel<1><<<g, threads, 0, st>>>(id, md, recs, n_tiles, out32, qs);
+            }
             // the counts travel back behind the kernel; the next launches read whatever has arrived
             cudaMemcpyAsync((void *)ix->qstats_host, ix->qstats_dev, 16, cudaMemcpyDeviceToHost, st);
             ix->launches_filter++;
@@ -845,8 +703,7 @@ static void launch23_mode(const aix_ctx *ctx, const aix_index23 *ix, cudaStream_
         } else {
             launch_stream<kMode, false, 6>(ctx, st, id, md, recs, n_tiles, out);
         }
-        // the last q % 32 queries: the same per-query code through the block kernel (its tile start stays 16-byte aligned)
-        const uint64_t done = n_tiles * 32;
+        // the last q % 32 (% 64) queries: the same per-query code through the block kernel (its tile start stays 16-byte aligned)
         if (done == q) return;
         recs += done * 23;
         out = (char *)out + done * out_bytes23(kMode);
@@ -1554,6 +1411,7 @@ int aix_tf13_batch_dev(aix_ctx *ctx, const aix_index13 *ix, const uint8_t *recs_
     if (!ctx || !ix) return AIX_ERR_ARG;
     if (q && (!recs_dev || !out_dev || !stride)) return ctx->fail(AIX_ERR_ARG, "null buffer");
     AIX_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->l2_unpin();
     return launch_tf13(ctx, ix, ctx->stream, recs_dev, stride, lens_dev, q, mode, out_dev);
 }
 

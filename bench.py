@@ -645,7 +645,7 @@ def run_ours(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = args.queries * Q1_BYTES_PER_QUERY / (k_ms / 1e3) / 1e9
     filtered = filter_after_q1["batches_filter"] > 0
-    k_name = ("tf23_filter_kernel (front Bloom filter, %d B; the %.1f %% of the queries that pass it go through the lookup of tf23_stream_kernel)"
+    k_name = ("tf23_filter3_kernel (front Bloom filter, %d B, its lines held in persisting L2; the %.1f %% of the queries that pass it go through the lookup of tf23_stream_kernel)"
               % (filter_after_q1["filter_bytes"], 100.0 * (filter_after_q1["pass_rate"] or 0.0))) if filtered else \
         "tf23_stream_kernel<AIX_Q_TF, canonical> (" + index.layout["records"] + " MPHF records)"
     roofline = {"bound": "hbm", "kernel": k_name, "achieved": achieved,

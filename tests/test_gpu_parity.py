@@ -883,11 +883,31 @@ def test_tf23_front_filter(capi, oracle, ctx, oidx23, monkeypatch, bits):
         odd = rng.random(nq) < 0.01
         r23[odd, rng.integers(0, 23, size=int(odd.sum()))] = rng.choice(np.frombuffer(b"Nnacgt\n\x00~", dtype=np.uint8), size=int(odd.sum()))
         want = oidx23.batch(r23, None, oracle.MODE_TF)
-        for mode in ("on", "off", "auto", "auto"):
+        for mode, kern in (("on", "1"), ("on", "2"), ("on", "3"), ("off", "1"), ("auto", "1"), ("auto", "3")):
+            monkeypatch.setenv("AIX_FILTER_KERNEL", kern)  # one query per lane and iteration / two
             ix.set_filter(mode)
-            assert np.array_equal(ix.query(r23), want), f"filter {mode}, {nq} queries, hit fraction {p_hit}"
+            assert np.array_equal(ix.query(r23), want), f"filter {mode}, kernel {kern}, {nq} queries, hit fraction {p_hit}"
     st = ix.filter_stats
     assert st["batches_filter"] > 0 and st["batches_direct"] > 0 and st["queries_counted"] > 0
+    # device buffers: the kernel with two queries per lane needs an 8-byte aligned result array, a 4-byte aligned one falls
+    # back to the kernel with one; neither writes outside [0, nq)
+    import torch
+    ix.set_filter("on")
+    for nq, p_hit in ((100_003, 0.05), (8191, 0.5), (4096 + 63, 0.0)):
+        r23 = rng.choice(ACGT, size=(nq, 23))
+        hit = rng.random(nq) < p_hit
+        r23[hit] = km[rng.integers(0, oidx23.checker.size, size=int(hit.sum()))]
+        r23[-1] = km[0]   # the last query of the batch is a stored k-mer (the queue's careful load)
+        want = oidx23.batch(r23, None, oracle.MODE_TF)
+        d = torch.from_numpy(r23).cuda()
+        for off, kern in ((0, "1"), (0, "2"), (1, "2"), (0, "3"), (1, "3")):
+            monkeypatch.setenv("AIX_FILTER_KERNEL", kern)
+            o = torch.full((nq + 3,), -7, dtype=torch.int32, device="cuda")
+            ix.query_dev(d.data_ptr(), 23, None, nq, capi.Q_TF, o.data_ptr() + 4 * off)
+            ctx.sync()
+            got = o.cpu().numpy()
+            assert np.array_equal(got[off:off + nq].view(np.uint32), want), f"device buffers, offset {off}, {nq} queries"
+            assert (got[:off] == -7).all() and (got[off + nq:] == -7).all()
     # every stored k-mer passes its own filter: no false negatives on either strand
     ix.set_filter("on")
     reps = -(-8192 // km.shape[0])
