@@ -130,12 +130,16 @@ struct aix_ctx {
     uint32_t *c23_counts_dev = nullptr;
     uint64_t c23_n = 0;
 
-    // persisting L2 lines of a front filter back to normal lines: called where another kernel family starts (counting,
-    // builds, coverage, 13-mer queries), whose working sets want the whole L2
+    // persisting L2 lines of a front filter back to normal lines and the set-aside back to the device: called where another
+    // kernel family starts (counting, builds, coverage, 13-mer queries), whose working sets want the whole L2 -- with the
+    // 50 MB set-aside left configured, the 64 MiB histogram slices of count13 no longer fit (190 -> 126 G k-mers/s)
     void l2_unpin() const {
-        if (l2_pinned) {
+        if (l2_pinned || l2_set_aside) {
             cudaCtxResetPersistingL2Cache();
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+            cudaGetLastError();
             l2_pinned = false;
+            l2_set_aside = 0;
         }
     }
 

@@ -654,6 +654,7 @@ def run_ours(args):
                 "bytes_per_unit": Q1_BYTES_PER_QUERY, "units_per_launch": args.queries, "kernel_ms": k_ms,
                 "achieved_one_probe_bytes": args.queries * Q1_BYTES_ONE_PROBE / (k_ms / 1e3) / 1e9,
                 "traffic": ncu_traffic("tf23_filter_kernel_q1_100M" if filtered else "tf23_stream_kernel_q1_100M", args.queries),
+                "traffic_frac": None,  # filled below: the DRAM bytes really moved per second against the same peak
                 "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
                 # the other denominators of this kernel (profiles/r01_atomic_roofline.txt):
                 # random 16-byte gathers from a 1 GiB table run at 50.1 G/s on this GPU (the index is 0.8 GB)
@@ -671,8 +672,11 @@ def run_ours(args):
                                           "three requests by one for absent k-mers"},
                 "random_access": {"achieved_gq_s": args.queries / (k_ms / 1e3) / 1e9, "peak_ggathers_s": GATHER_PEAK_G,
                                   "frac": args.queries / (k_ms / 1e3) / 1e9 / GATHER_PEAK_G,
-                                  "note": "measured random-gather rate; above 1.0 is possible because the L2-resident "
-                                          "fingerprint tier answers misses without touching the HBM record"}}
+                                  "note": "measured random-gather rate (informative: the front filter answers absent k-mers "
+                                          "from one 8-byte word, most of them without touching a record)"}}
+    if roofline["traffic"]:
+        roofline["traffic_gbs"] = roofline["traffic"] / (k_ms / 1e3) / 1e9
+        roofline["traffic_frac"] = roofline["traffic_gbs"] / peak_gbs
 
     # ---- 13-mer counting (second half of the metric), per-GPU shard of C3 -------------------------
     extra = {"index": {"keys": n_keys, "build_s": index_build_s, "hit_fraction": hits / args.queries,

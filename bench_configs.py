@@ -48,12 +48,27 @@ def timed(torch, ctx, stream, fn, reps=3, warmup=1):
     return a.elapsed_time(b) / reps
 
 
-def roof(units, bytes_per_unit, ms, kernel, traffic_key=None):
+GATHER_PEAK_G = 50.1  # random 16-byte gathers/s from a 1 GiB table on this GPU (profiles/r02_atomic_roofline.txt): one DRAM burst each
+
+
+def roof(units, bytes_per_unit, ms, kernel, traffic_key=None, random_access=False):
+    """`frac` is the contract's figure (algorithmic bytes against the HBM copy peak).  With a committed ncu capture,
+    `traffic_frac` = the DRAM bytes the kernel really moves per second against the same peak, and for kernels whose reads are
+    scattered records (`random_access`) `random_access.frac` = 64-byte DRAM bursts per second against the measured random-gather
+    rate -- the ceiling such a kernel can actually reach."""
     peak, src = bc.peak_hbm_gbs()
     ach = units * bytes_per_unit / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": src, "bytes_per_unit": bytes_per_unit, "units_per_launch": int(units), "kernel_ms": ms,
-            "traffic": bc.ncu_traffic(traffic_key, units) if traffic_key else None}
+    r = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "peak_source": src, "bytes_per_unit": bytes_per_unit, "units_per_launch": int(units), "kernel_ms": ms,
+         "traffic": bc.ncu_traffic(traffic_key, units) if traffic_key else None}
+    if r["traffic"]:
+        r["traffic_gbs"] = r["traffic"] / (ms / 1e3) / 1e9
+        r["traffic_frac"] = r["traffic_gbs"] / peak
+        if random_access:
+            bursts = r["traffic"] / 64.0 / (ms / 1e3) / 1e9
+            r["random_access"] = {"dram_bursts_64B_g_per_s": bursts, "peak_ggathers_s": GATHER_PEAK_G, "frac": bursts / GATHER_PEAK_G,
+                                  "note": "all DRAM traffic counted as 64-byte bursts (an upper bound of the scattered share)"}
+    return r
 
 
 def _ns(args, **defaults):
@@ -283,7 +298,7 @@ def run_c4(ctx, stream, dev, args=None, index_bundle=None):
     return {"config": "C4", "workload": f"coverage of {n_seq} x {seq_len} bp sequences (1% substitutions) on the C2 index ({n_keys} keys)",
             "metric": "coverage positions/s", "value": total_out / (ms / 1e3), "unit": "positions/s",
             "sequences_per_s": n_seq / (ms / 1e3), "ms_per_step": ms, "hit_fraction": hit,
-            "roofline": roof(total_out, 17, ms, "coverage_kernel<23, canonical>", "coverage_kernel_c4"), "e2e": e2e,
+            "roofline": roof(total_out, 17, ms, "coverage_kernel<23, canonical>", "coverage_kernel_c4", random_access=True), "e2e": e2e,
             "checks": checks, "cpu_baseline": cpu}
 
 
