@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--no-multi-legs", dest="multi_legs", action="store_false", default=True,
                     help="skip the single-process (C-ABI) multi-GPU legs at N > 1")
     ap.add_argument("--multi-positions-reads", type=int, default=50_000_000, help="reads of the N-GPU positions build (C5 = 50 M)")
-    ap.add_argument("--configs", default="c4,c1,c5", help="other BASELINE configs measured at N=1 ('' = none)")
+    ap.add_argument("--configs", default="c4,c1,c5,k1", help="other BASELINE configs (and k1 = the encoding kernels) measured at N=1 ('' = none)")
     ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the BASELINE sizes for --configs (smoke runs)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -851,6 +851,10 @@ def run_ours(args):
             torch.cuda.empty_cache()
         if "c5" in names:
             extra["c5_positions"] = _guard(lambda: bench_configs.run_c5(ctx, stream, dev, cargs))
+            torch.cuda.empty_cache()
+        if "k1" in names:  # the encoding kernels on their own (no BASELINE config)
+            cargs.checks = True
+            extra["k1_codec"] = _guard(lambda: bench_configs.run_k1(ctx, stream, dev, cargs))
             torch.cuda.empty_cache()
     # ---- N > 1: the same multi-GPU work from ONE process through the C-ABI (aix_multi: one context + one host thread per
     #      GPU, no torch.distributed on the data path); the other ranks release their memory and wait

@@ -486,7 +486,67 @@ def run_c5(ctx, stream, dev, args=None):
             "queries": queries, "e2e": e2e, "checks": checks, "cpu_baseline": cpu}
 
 
-RUNNERS = {"c1": run_c1, "c4": run_c4, "c5": run_c5}
+# ------------------------------------------------------------------------------------------ K1
+def run_k1(ctx, stream, dev, args=None):
+    """The encoding kernels on their own: dna_bitset packing (dna_bitseq.hpp:22-61) and the rolling forward /
+    reverse-complement 23-mers of a reads buffer (the loop of hash.cpp:1006-1032 without the lookup), input resident in HBM.
+    No CPU baseline: the reference never runs these loops on their own (the packing class is unused by its pipeline)."""
+    args = _ns(args)
+    torch, capi, lib = _env(dev)
+    n_reads = max(1600, int(3_500_000 * args.scale) // 16 * 16)       # n_reads * 151 stays a multiple of 16
+    reads = bc.make_reads(torch, dev, 50_000_000, n_reads, 150, 51, 52).reshape(-1)
+    n = reads.numel()
+    packed = torch.empty((n + 3) // 4 + 16, device=dev, dtype=torch.uint8)
+    fwd = torch.empty(n, device=dev, dtype=torch.int64)
+    rcv = torch.empty(n, device=dev, dtype=torch.int64)
+    valid = torch.empty(n + 16, device=dev, dtype=torch.uint8)
+
+    def pack_step():
+        ctx.check(lib.aix_pack_2bit_dev(ctx.handle, reads.data_ptr(), n, packed.data_ptr()))
+
+    def roll_step():
+        ctx.check(lib.aix_rolling_kmers_dev(ctx.handle, reads.data_ptr(), n, 23, fwd.data_ptr(), rcv.data_ptr(), valid.data_ptr()))
+
+    pack_ms = timed(torch, ctx, stream, pack_step, reps=10, warmup=3)
+    roll_ms = timed(torch, ctx, stream, roll_step, reps=5, warmup=2)
+    checks = {}
+    if args.checks:
+        # independent arithmetic on a sample: 4 bases per byte, first base in the top bits, anything but ACGT -> 0;
+        # window value = sum of code << 2 (22 - j), valid iff 23 upper-case ACGT letters
+        rng = np.random.default_rng(5)
+        code = np.zeros(256, dtype=np.uint64)
+        code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
+        starts = np.concatenate([rng.integers(0, n - 64, size=4000), np.arange(0, 400)]).astype(np.int64) // 4 * 4
+        idx = torch.from_numpy(starts[:, None] + np.arange(28)[None, :]).to(dev)
+        win = reads[idx].cpu().numpy()
+        c = code[win]
+        want_p = (c[:, 0:28:4] << np.uint64(6)) | (c[:, 1:28:4] << np.uint64(4)) | (c[:, 2:28:4] << np.uint64(2)) | c[:, 3:28:4]
+        got_p = packed[torch.from_numpy(starts[:, None] // 4 + np.arange(7)[None, :]).to(dev)].cpu().numpy()
+        checks["pack_equals_numpy"] = bool(np.array_equal(got_p.astype(np.uint64), want_p))
+        w23 = win[:, :23]
+        ok = np.isin(w23, np.frombuffer(b"ACGT", dtype=np.uint8)).all(axis=1)
+        sh = (np.uint64(2) * (np.uint64(22) - np.arange(23, dtype=np.uint64)))[None, :]
+        want_f = (c[:, :23] << sh).sum(axis=1, dtype=np.uint64)
+        want_r = ((np.uint64(3) - c[:, :23]) << (np.uint64(2) * np.arange(23, dtype=np.uint64))[None, :]).sum(axis=1, dtype=np.uint64)
+        st = torch.from_numpy(starts).to(dev)
+        got_v = valid[st].cpu().numpy().astype(bool)
+        got_f = fwd[st].cpu().numpy().view(np.uint64)
+        got_r = rcv[st].cpu().numpy().view(np.uint64)
+        checks["valid_equals_numpy"] = bool(np.array_equal(got_v, ok))
+        checks["rolling_equals_numpy_on_valid_windows"] = bool(np.array_equal(got_f[ok], want_f[ok]) and np.array_equal(got_r[ok], want_r[ok]))
+        checks["valid_windows_in_sample"] = int(ok.sum())
+    windows = n - 22
+    del packed, fwd, rcv, valid, reads
+    return {"config": "K1", "workload": f"{n_reads} x 150 bp reads ({n} bytes, plain format) resident in HBM: 2-bit packing; rolling 23-mers (forward, "
+                                        "reverse complement, validity) of every window",
+            "pack": {"metric": "bases packed/s", "value": n / (pack_ms / 1e3), "unit": "bases/s", "ms_per_step": pack_ms,
+                     "roofline": roof(n, 1.25, pack_ms, "pack2bit_vec_kernel")},
+            "rolling": {"metric": "windows/s", "value": windows / (roll_ms / 1e3), "unit": "windows/s", "ms_per_step": roll_ms,
+                        "roofline": roof(windows, 18, roll_ms, "rolling_vec_kernel<23> (1 B in, 8 + 8 + 1 B out per window)")},
+            "checks": checks, "cpu_baseline": None}
+
+
+RUNNERS = {"c1": run_c1, "c4": run_c4, "c5": run_c5, "k1": run_k1}
 
 
 def main():
