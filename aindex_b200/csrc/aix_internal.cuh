@@ -1,5 +1,6 @@
 // aix_internal.cuh -- host-side object definitions behind the opaque C-ABI handles.
 #pragma once
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -86,6 +87,14 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// Front filter of a 23-mer index held in persisting L2 lines (tf_query.cu: l2_window_on): the set-aside configured on a
+// device and whether persisting lines may still be resident.  A property of the DEVICE, shared by every ctx on it.
+struct AixL2State {
+    std::atomic<size_t> set_aside{0};
+    std::atomic<bool> pinned{false};
+};
+inline AixL2State g_aix_l2[64];
+
 struct aix_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // *_dev entry points + pipelines' compute
@@ -111,10 +120,6 @@ struct aix_ctx {
     const void *mbox_owner = nullptr;   // the index the running kernel serves
     bool mbox_launched = false, mbox_broken = false;
     uint32_t mbox_seq = 0;
-    // front filter of a 23-mer index held in persisting L2 lines (tf_query.cu: l2_window_on): the set-aside configured on
-    // this device, and whether persisting lines may still be resident (aix_l2_unpin hands the set-aside back)
-    mutable size_t l2_set_aside = 0;
-    mutable bool l2_pinned = false;
     // count13 streaming state
     uint32_t *c13_hist32 = nullptr;     // u32[4^13]
     uint64_t *c13_hist64 = nullptr;     // u64[4^13]
@@ -134,12 +139,13 @@ struct aix_ctx {
     // kernel family starts (counting, builds, coverage, 13-mer queries), whose working sets want the whole L2 -- with the
     // 50 MB set-aside left configured, the 64 MiB histogram slices of count13 no longer fit (190 -> 126 G k-mers/s)
     void l2_unpin() const {
-        if (l2_pinned || l2_set_aside) {
+        AixL2State &l2 = g_aix_l2[device & 63];
+        if (l2.pinned.load() || l2.set_aside.load()) {
             cudaCtxResetPersistingL2Cache();
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
             cudaGetLastError();
-            l2_pinned = false;
-            l2_set_aside = 0;
+            l2.pinned = false;
+            l2.set_aside = 0;
         }
     }
 

@@ -626,25 +626,27 @@ static bool l2_window_on(const aix_ctx *ctx, cudaStream_t st, const void *base, 
     size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
     const char *esa = getenv("AIX_FILTER_SETASIDE_MB"), *ehr = getenv("AIX_FILTER_HITRATIO");  // A/B knobs
     if (esa && atol(esa) > 0) want = (size_t)atol(esa) << 20 < (size_t)max_persist ? (size_t)atol(esa) << 20 : (size_t)max_persist;
-    if (ctx->l2_set_aside < want) {
+    AixL2State &l2 = g_aix_l2[ctx->device & 63];
+    if (l2.set_aside.load() < want) {
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        ctx->l2_set_aside = want;
+        l2.set_aside = want;
     }
+    const size_t set_aside = l2.set_aside.load();
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof v);
     v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
     v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-    v.accessPolicyWindow.hitRatio = ehr ? (float)atof(ehr) : (bytes <= ctx->l2_set_aside ? 1.0f : (float)((double)ctx->l2_set_aside / (double)bytes));
+    v.accessPolicyWindow.hitRatio = ehr ? (float)atof(ehr) : (bytes <= set_aside ? 1.0f : (float)((double)set_aside / (double)bytes));
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    ctx->l2_pinned = true;
+    l2.pinned = true;
     return true;
 }
 static void l2_window_off(cudaStream_t st) {
