@@ -68,66 +68,26 @@ __global__ void __launch_bounds__(kQBlock) tf23_fixed_kernel(Index23Dev ix, Mphf
 template <int kMode, bool kCanon, int kMinBlocks>
 __global__ void __launch_bounds__(kStWarps * 32, kMinBlocks) tf23_stream_kernel(Index23Dev ix, MphfDev m, const uint8_t *__restrict__ recs,
                                                                               uint64_t n_tiles, void *__restrict__ out) {
-    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kStSlot];
+    __shared__ __align__(128) uint8_t slots[kStWarps][kStStages][kStSlot];
     __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint32_t ring0 = smem_addr(&ring[wid][0][0]), bar0 = smem_addr(&bars[wid][0]);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;  // this warp's first tile
-    if (tile0 >= n_tiles) return;
-    const uint64_t left = n_tiles - tile0;                                // tiles from tile0 on
-    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
-    const uint64_t policy = l2_policy_evict_first();
-    constexpr uint32_t kStride = kStWarps * kStTileBytes;                 // bytes between a warp's consecutive tiles
-    const uint8_t *src = recs + tile0 * kStTileBytes;                     // next tile to fetch
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages - 1; ++s) {
-            if ((uint32_t)s < my_tiles) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(kStTileBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                             ::"r"(ring0 + (uint32_t)kStSlot * s), "l"(src + (uint64_t)kStride * s), "r"(kStTileBytes), "r"(bar0 + 8u * s), "l"(policy) : "memory");
-            }
-        }
-    }
-    src += (uint64_t)kStride * (kStStages - 1);
+    WarpRing<kStTileBytes, kStSlot> ring;
+    ring.init(&slots[wid][0][0], &bars[wid][0], lane);
+    uint64_t tile0;
+    const uint32_t my_tiles = warp_tiles<kStTilesPerWarp>(n_tiles, wid, tile0);
+    if (my_tiles == 0) return;
+    ring.start(recs + tile0 * kStTileBytes, my_tiles, lane);
     uint64_t i = tile0 * 32u + lane;  // query index of this lane in the current tile
-    uint32_t slot = 0, phase = 0;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        // refill the slot every lane finished reading in the previous iteration (the __syncwarp below)
-        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
-            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * sn), "r"(kStTileBytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                         ::"r"(ring0 + (uint32_t)kStSlot * sn), "l"(src), "r"(kStTileBytes), "r"(bar0 + 8u * sn), "l"(policy) : "memory");
-        }
-        src += kStride;
-        {
-            uint32_t done;
-            do {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(done) : "r"(bar0 + 8u * slot), "r"(phase) : "memory");
-            } while (!done);
-        }
-        const uint32_t base = lane * 23u;
-        const uint32_t a = ring0 + (uint32_t)kStSlot * slot + (base & ~3u), sh = (base & 3u) * 8u;
-        uint32_t x0, x1, x2, x3, x4, x5, x6;
-        asm volatile("ld.shared.u32 %0, [%7];\nld.shared.u32 %1, [%7+4];\nld.shared.u32 %2, [%7+8];\nld.shared.u32 %3, [%7+12];\n"
-                     "ld.shared.u32 %4, [%7+16];\nld.shared.u32 %5, [%7+20];\nld.shared.u32 %6, [%7+24];"
-                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6) : "r"(a) : "memory");
+        const uint32_t tile = ring.acquire(it, lane);
+        uint32_t x[7];
+        lds_words7(tile, lane * 23u, x);
         __syncwarp();
-        uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
-                 y3 = __funnelshift_r(x3, x4, sh), y4 = __funnelshift_r(x4, x5, sh), y5 = __funnelshift_r(x5, x6, sh);
-        uint64_t r0 = ((uint64_t)y1 << 32) | y0, r1 = ((uint64_t)y3 << 32) | y2,
-                 r2 = (((uint64_t)y5 << 32) | y4) & 0x00FFFFFFFFFFFFFFULL;
+        uint64_t r0, r1, r2;
+        words23(x, lane * 23u, r0, r1, r2);
         query23<kMode, kCanon>(ix, m, r0, r1, r2, 23u, recs + i * 23, i, out);
         i += (uint64_t)kStWarps * 32u;
-        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+        ring.advance();
     }
 }
 
@@ -506,51 +466,28 @@ __global__ void __launch_bounds__(kStWarps * 32) tf13_stream_kernel(MphfDev m, c
                                                                   const uint64_t *__restrict__ tf_direct,
                                                                   const uint8_t *__restrict__ recs, uint64_t n_tiles,
                                                                   void *__restrict__ out) {
-    __shared__ __align__(128) uint8_t ring[kStWarps][kStStages][kSt13Slot];
+    __shared__ __align__(128) uint8_t slots[kStWarps][kStStages][kSt13Slot];
     __shared__ __align__(8) uint64_t bars[kStWarps][kStStages];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages; ++s) mbar_init(&bars[wid][s], 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const uint64_t tile0 = (uint64_t)blockIdx.x * kStTilesPerCta + wid;
-    if (tile0 >= n_tiles) return;
-    const uint64_t left = n_tiles - tile0;
-    const uint32_t my_tiles = left >= (uint64_t)kStTilesPerCta ? (uint32_t)kStTilesPerWarp : (uint32_t)((left + kStWarps - 1) / kStWarps);
-    const uint64_t policy = l2_policy_evict_first();
-    constexpr uint32_t kStride = kStWarps * kSt13TileBytes;
-    const uint8_t *src = recs + tile0 * kSt13TileBytes;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStStages - 1; ++s)
-            if ((uint32_t)s < my_tiles) {
-                mbar_expect_tx(&bars[wid][s], kSt13TileBytes);
-                bulk_load(&ring[wid][s][0], src + (uint64_t)kStride * s, kSt13TileBytes, &bars[wid][s], policy);
-            }
-    }
-    src += (uint64_t)kStride * (kStStages - 1);
+    WarpRing<kSt13TileBytes, kSt13Slot> ring;
+    ring.init(&slots[wid][0][0], &bars[wid][0], lane);
+    uint64_t tile0;
+    const uint32_t my_tiles = warp_tiles<kStTilesPerWarp>(n_tiles, wid, tile0);
+    if (my_tiles == 0) return;
+    ring.start(recs + tile0 * kSt13TileBytes, my_tiles, lane);
     uint64_t i = tile0 * 32u + lane;
-    uint32_t slot = 0, phase = 0;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        if (lane == 0 && it + (kStStages - 1) < my_tiles) {
-            const uint32_t sn = slot == 0 ? kStStages - 1 : slot - 1;
-            mbar_expect_tx(&bars[wid][sn], kSt13TileBytes);
-            bulk_load(&ring[wid][sn][0], src, kSt13TileBytes, &bars[wid][sn], policy);
-        }
-        src += kStride;
-        mbar_wait(&bars[wid][slot], phase);
-        const uint32_t base = lane * 13u;
-        const uint32_t *t = reinterpret_cast<const uint32_t *>(&ring[wid][slot][base & ~3u]);
-        const uint32_t sh = (base & 3u) * 8u;
-        const uint32_t x0 = t[0], x1 = t[1], x2 = t[2], x3 = t[3];  // bytes base .. base+12 end inside the fourth word
+        const uint32_t tile = ring.acquire(it, lane);
+        const uint32_t base = lane * 13u, sh = (base & 3u) * 8u;
+        uint32_t x0, x1, x2, x3;  // bytes base .. base+12 end inside the fourth word
+        asm volatile("ld.shared.u32 %0, [%4];\nld.shared.u32 %1, [%4+4];\nld.shared.u32 %2, [%4+8];\nld.shared.u32 %3, [%4+12];"
+                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(tile + (base & ~3u)) : "memory");
         __syncwarp();
         const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh),
                        y3 = (x3 >> sh) & 0xFFu;
         query13<kMode>(m, tf_mphf, tf_direct, ((uint64_t)y1 << 32) | y0, ((uint64_t)y3 << 32) | y2, 13u, i, out);
         i += (uint64_t)kStWarps * 32u;
-        if (++slot == kStStages) { slot = 0; phase ^= 1u; }
+        ring.advance();
     }
 }
 
