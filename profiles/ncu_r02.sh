@@ -33,7 +33,7 @@ for r in tf23 tf23direct c5emit c5sort c1 c4; do
   [ -f gpurun_out/${TAG}_$r.ncu-rep ] && python profiles/summarize_ncu.py kernel gpurun_out/${TAG}_$r.ncu-rep gpurun_out/${TAG}_${r}_ncu.txt > /dev/null 2>&1
 done
 python profiles/summarize_ncu.py launches gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launches.txt > /dev/null 2>&1
-python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix18tf23_filter_kernelILi4E 100000000 gpurun_out/${TAG}_tf23_instr.txt > /dev/null 2>&1
+python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix19tf23_filter3_kernelILi4ELi16ELb1E 100000000 gpurun_out/${TAG}_tf23_instr.txt > /dev/null 2>&1
 python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23direct.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix18tf23_stream_kernelILi0ELb1ELi1E 100000000 gpurun_out/${TAG}_tf23direct_instr.txt > /dev/null 2>&1
 python profiles/instr_breakdown.py gpurun_out/${TAG}_c5sort.ncu-rep aindex_b200/csrc/_obj/radix_sort.o _ZN3aix14rs_pass_kernelILi256ELi7ELi4ENS_9BitsDigitE 640000000 gpurun_out/${TAG}_c5sort_instr.txt > /dev/null 2>&1
 rm -f gpurun_out/${TAG}_tf23direct.ncu-rep gpurun_out/${TAG}_c5emit.ncu-rep gpurun_out/${TAG}_c1.ncu-rep gpurun_out/${TAG}_c4.ncu-rep gpurun_out/${TAG}_launches.csv

@@ -13,7 +13,7 @@ AIX_INDEX23_FILTER=off ncu --set full --clock-control none --import-source on -k
 for r in tf23 tf23direct; do
   [ -f gpurun_out/${TAG}_$r.ncu-rep ] && python profiles/summarize_ncu.py kernel gpurun_out/${TAG}_$r.ncu-rep gpurun_out/${TAG}_${r}_ncu.txt > /dev/null 2>&1
 done
-python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix19tf23_filter3_kernelILi4ELi16ELb${WIN:-0}E 100000000 gpurun_out/${TAG}_tf23_instr.txt > /dev/null 2>&1
+python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix19tf23_filter3_kernelILi4ELi16ELb${WIN:-1}E 100000000 gpurun_out/${TAG}_tf23_instr.txt > /dev/null 2>&1
 python profiles/instr_breakdown.py gpurun_out/${TAG}_tf23direct.ncu-rep aindex_b200/csrc/_obj/tf_query.o _ZN3aix18tf23_stream_kernelILi0ELb1ELi1E 100000000 gpurun_out/${TAG}_tf23direct_instr.txt > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_tf23.ncu-rep --page source --csv > gpurun_out/${TAG}_tf23_src.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_tf23direct.ncu-rep
