@@ -623,7 +623,7 @@ def run_ours(args):
             gbs = (blk["h2d_bytes_per_step"] + blk["d2h_bytes_per_step"]) / (blk["ms_per_step"] / 1e3) / 1e9
             blk["pcie"] = {"h2d_plus_d2h_gbs": gbs, "pinned_h2d_copy_peak_gbs": h2d_peak, "utilisation_vs_h2d_peak": gbs / h2d_peak,
                            "note": "both directions are counted against a one-direction copy peak (full duplex): > 1 is possible; "
-                                   "the e2e rate is a bus number, the kernel takes 1.75 ms of the step"}
+                                   "the e2e rate is a bus number, the kernel takes %.2f ms of the step" % float(np.mean(kernel_ms))}
         del p6, po, stage, hq
     else:
         q_host = None
