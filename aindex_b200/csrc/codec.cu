@@ -73,13 +73,25 @@ __global__ void pack2bit_kernel(const uint8_t *__restrict__ seq, uint64_t first_
     out[i] = (uint8_t)b;
 }
 
-// vector form: one 128-bit coalesced load (16 bases) and one 32-bit coalesced store (4 packed bytes) per thread;
-// a warp turns 512 contiguous input bytes into 128 contiguous output bytes.  seq 16-byte aligned, out 4-byte aligned.
+// vector form: 128-bit coalesced loads (16 bases) and 32-bit coalesced stores (4 packed bytes); a warp turns 512
+// contiguous input bytes into 128 contiguous output bytes per step.  A thread takes kPackUnroll vectors, one CTA width
+// apart, and issues their loads together: with one 16-byte load per thread an SM has 32 KB in flight, about what HBM's
+// latency x bandwidth asks of it and no more (0.60 of the copy peak measured).  seq 16-byte aligned, out 4-byte aligned.
+constexpr int kPackUnroll = 4;
 __global__ void __launch_bounds__(256) pack2bit_vec_kernel(const uint4 *__restrict__ seq, uint64_t n_vec, uint32_t *__restrict__ out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_vec) return;
-    const uint4 v = __ldcs(seq + i);
-    __stcs(out + i, pack4_strict(v.x) | (pack4_strict(v.y) << 8) | (pack4_strict(v.z) << 16) | (pack4_strict(v.w) << 24));
+    const uint64_t i0 = (uint64_t)blockIdx.x * (256 * kPackUnroll) + threadIdx.x;
+    uint4 v[kPackUnroll];
+#pragma unroll
+    for (int j = 0; j < kPackUnroll; ++j) {
+        const uint64_t i = i0 + (uint64_t)j * 256;
+        v[j] = i < n_vec ? __ldcs(seq + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kPackUnroll; ++j) {
+        const uint64_t i = i0 + (uint64_t)j * 256;
+        if (i < n_vec)
+            __stcs(out + i, pack4_strict(v[j].x) | (pack4_strict(v[j].y) << 8) | (pack4_strict(v[j].z) << 16) | (pack4_strict(v[j].w) << 24));
+    }
 }
 
 // dna_bitset::ukmer(pos, k) (dna_bitseq.hpp:124-151): the 2k-bit big-endian substring of the packed stream that
@@ -246,7 +258,7 @@ static int pack2bit_launch(aix_ctx *ctx, cudaStream_t st, const uint8_t *seq_dev
     uint64_t done_out = 0;
     if ((((uintptr_t)seq_dev) & 15) == 0 && (((uintptr_t)packed_dev) & 3) == 0 && len >= 16) {
         const uint64_t n_vec = len / 16;
-        pack2bit_vec_kernel<<<aix_grid(n_vec, 256), 256, 0, st>>>((const uint4 *)seq_dev, n_vec, (uint32_t *)packed_dev);
+        pack2bit_vec_kernel<<<aix_grid(n_vec, 256 * kPackUnroll), 256, 0, st>>>((const uint4 *)seq_dev, n_vec, (uint32_t *)packed_dev);
         AIX_LAUNCH_CHECK(ctx);
         done_out = n_vec * 4;
     }
